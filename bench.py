@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: uint32 inclusive scan throughput (Gkeys/s) and the
+HBM-roofline fraction of the scan kernel, on 1..8 B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: launched by torchrun, one rank per GPU)
+
+A "step" is one pass of the hot path over one batch of synthetic keys:
+  * N == 1: BASELINE.json configs[1] -- uint32 inclusive scan of 2^28 random keys with the
+    default CSDL kernel, out of place (1 GiB in + 1 GiB out, both far larger than the
+    126 MB L2, so no flush is needed between iterations);
+  * N  > 1: the sharded scan -- every rank holds a contiguous slice of 2^28 keys of one
+    global array (weak scaling: N * 2^28 keys in total; --log2-total 33 gives the 2^33-key
+    case), pass 1 reduce + publish totals over NVLink P2P, pass 2 scan with the carry
+    folded into tile 0's look-back.  No NCCL call inside the step in the default mode.
+`value` is whole-job Gkeys/s with inputs resident in HBM; `e2e` is the same metric
+through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed
+region).  `--impl reference` times the CPU oracle restatement of the reference's serial
+scan on all host threads (the reference's CUDA directory has no CPU implementation and
+its kernels are the GPU baselines reported by tests/test_compare_baselines.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "uint32 inclusive scan throughput"
+UNIT = "Gkeys/s"
+LOG2_KEYS_PER_GPU = 28
+BYTES_PER_KEY = 8  # algorithmic: 4 B read + 4 B written
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--algo", default="csdl", help="csdl | csdl_reg | csdl_tma | rts | csdl_fallback")
+    ap.add_argument("--log2-keys-per-gpu", type=int, default=LOG2_KEYS_PER_GPU)
+    ap.add_argument("--log2-total", type=int, default=0, help="N>1: total keys = 2^this (strong-scaling point)")
+    ap.add_argument("--carry", default="p2p", choices=["p2p", "nccl"], help="N>1 carry exchange")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(algo_key: str):
+    """dram bytes per launch from the committed ncu capture (profiles/roofline_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(algo_key)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.out = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.gpu_index)], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        # samples under load: the upper half (idle samples before/after the region clock down)
+        under_load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(under_load) if under_load else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_serial(oracle, log2n: int) -> dict:
+    """The oracle's serial scan (restating the reference's single-thread validation loop,
+    Utility.hlsl:99-111) on 1 host core: bounded sample, best of 5 passes over 2^log2n keys."""
+    import numpy as np
+
+    n = 1 << log2n
+    x = oracle.random_u32(n, seed=1)
+    out = np.empty_like(x)
+    best = float("inf")
+    for _ in range(5):
+        t0 = time.perf_counter()
+        oracle.scan_u32_mt(x, out, False, 0, 1)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": n / best / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"2^{log2n} random uint32 keys, inclusive, best of 5 passes, 1 of {os.cpu_count()} host threads",
+            "host_threads_available": os.cpu_count()}
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm: CPU oracle on all host threads
+# ---------------------------------------------------------------------------------------
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    from tests import oracle_lib
+
+    oracle = oracle_lib.load()
+    threads = os.cpu_count() or 1
+    n = 1 << args.log2_keys_per_gpu  # bounded sample: one GPU's share of the workload per step
+    x = oracle.random_u32(n, seed=1)
+    out = np.empty_like(x)
+    steps = min(args.steps, 40)  # keep the whole run within a few minutes on any host
+    warm = min(args.warmup, 3)
+    for _ in range(warm):
+        oracle.scan_u32_mt(x, out, False, 0, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.scan_u32_mt(x, out, False, 0, threads)
+    dt = (time.perf_counter() - t0) / steps
+    assert oracle.check_u32(x[: 1 << 20], out[: 1 << 20])[0] == 0
+    value = n / dt / 1e9
+    sample = (f"oracle port of the reference's serial scan, chunked over {threads} host threads; "
+              f"{steps} steps of 2^{args.log2_keys_per_gpu} random uint32 keys (one GPU's share per step)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args, args.gpus), "keys_per_step": n, "host_threads": threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, n_gpus: int) -> str:
+    if n_gpus == 1:
+        return f"uint32 inclusive scan, 2^{args.log2_keys_per_gpu} random keys, 1 B200, {args.algo} (BASELINE configs[1])"
+    return (f"sharded uint32 inclusive scan, {n_gpus} x 2^{args.log2_keys_per_gpu} random keys, contiguous slices, "
+            f"carry over {'NVLink P2P stores' if args.carry == 'p2p' else 'NCCL all_gather'} (BASELINE configs[4] shape)")
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import gpuprefixsums_b200 as gps  # raises if the CUDA library is missing: no fallback
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    if world > 1 and args.log2_total:
+        n_total = 1 << args.log2_total
+    else:
+        n_total = world << args.log2_keys_per_gpu
+    lo, hi = gps.slice_bounds(n_total, world, rank)
+    n_local = hi - lo
+
+    x = torch.empty(n_local, dtype=torch.int32, device=dev)
+    out = torch.empty_like(x)
+    gps.init_random(x, seed=1, first_index=lo)  # counter-based: the host never holds the array
+
+    if world == 1:
+        ps = gps.PrefixSum(n_local, dev)
+        step = lambda: ps.scan(x, out, algo=args.algo)  # noqa: E731
+        launches_per_step = 3 if args.algo == "rts" else 1
+        checker = ps
+    else:
+        sh = gps.ShardedScan(n_local, mode=args.carry)
+        step = lambda: sh.scan(x, out, algo=args.algo)  # noqa: E731
+        launches_per_step = (2 + (3 if args.algo == "rts" else 1)) + (1 if args.carry == "nccl" else 0)
+        checker = sh.ps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    checker.check()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    checker.check()
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n_total / (ms_per_step * 1e-3) / 1e9
+
+    # quick correctness guard on what was just timed: out[i]-out[i-1] == x[i], first key
+    assert torch.equal(out[1:1 << 20] - out[:(1 << 20) - 1], x[1:1 << 20]), "scan output failed the difference check"
+
+    # ---- end to end through the host-buffer call ----------------------------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    h_in = torch.empty(n_local, dtype=torch.int32).pin_memory()
+    h_in.copy_(x)
+    h_out = torch.empty(n_local, dtype=torch.int32).pin_memory()
+    if world == 1:
+        e2e_step = lambda: ps.scan_host(h_in, h_out, algo=args.algo)  # noqa: E731
+    else:
+        def e2e_step():
+            x.copy_(h_in, non_blocking=True)
+            sh.scan(x, out, algo=args.algo)
+            h_out.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = n_total / (e2e_s / e2e_steps) / 1e9
+    assert torch.equal(h_out[: 1 << 20], out[: 1 << 20].cpu()), "host-buffer path disagrees with the device path"
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        # dominant kernel: the scan kernel.  N == 1 with CSDL: one launch per step, so the
+        # event time per step IS the kernel's average launch duration.
+        achieved = BYTES_PER_KEY * n_local / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(args.algo if world == 1 else "sharded"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": BYTES_PER_KEY * n_local,
+                    "note": ("per GPU; the sharded step moves 12 B/key (reduce 4 + scan 8) for 8 useful B/key"
+                             if world > 1 else "8 B/key x 2^%d keys per launch" % args.log2_keys_per_gpu)}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from tests import oracle_lib  # checker only: the CPU baseline leg
+
+            cpu = cpu_baseline_serial(oracle_lib.load(), args.log2_keys_per_gpu)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if (world > 1 and args.log2_total) else "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "keys_total": n_total, "keys_per_gpu": n_local,
+                       "algo": args.algo, "in_place": False,
+                       "l2": "inputs (1 GiB in + 1 GiB out per GPU) far exceed the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_total,
+                    "d2h_bytes_per_step": 4 * n_total, "steps": e2e_steps,
+                    "path": "gps_scan_host (pinned host buffers, chunked H2D/scan/D2H pipeline)" if world == 1
+                    else "pinned H2D copy + sharded scan + D2H copy per rank"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        sh.close()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

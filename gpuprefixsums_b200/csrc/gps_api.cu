@@ -1,0 +1,819 @@
+// gps_api.cu -- the C ABI of libgps_b200.so (include/gps_b200.h): context, dispatch,
+// harness helpers, host-buffer pipeline, IPC, single-process sharded scan.
+//
+// Host-side mirror of the reference's private dispatch methods
+// (ChainedScanDecoupledLookbackDispatcher.cuh:166-211, ReduceThenScanDispatcher.cuh:158-204,
+// EmulatedDeadlockingDispatcher.cuh:140-174): grid arithmetic, scratch management,
+// kernel launch, validation -- but over caller-owned buffers, with checked errors and
+// without per-launch scratch clears.  There is no CPU path in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/gps_b200.h"
+#include "gps_config.h"
+#include "gps_launch.cuh"
+#include "gps_util_kernels.cuh"
+
+using namespace gps;
+
+// ---------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------
+namespace {
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define GPS_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(GPS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                             \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr uint32_t kMinTileKeys = 4096;  // smallest tile of any compiled CSDL variant
+constexpr uint32_t kHostChunkKeysDefault = 1u << 24;  // 64 MiB per pipeline chunk
+constexpr int kHostBufs = 3;
+static_assert(GPS_REG_NT * GPS_REG_V * 4 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
+static_assert(GPS_TMA_NT * 16 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
+}  // namespace
+
+struct gps_ctx {
+    int device = 0;
+    uint64_t max_n = 0;
+    Scratch s;                      // descriptors, claim counter, status word, partials
+    // options
+    int csdl_variant = 0;           // 0 auto, 1 reg, 2 tma
+    uint64_t host_chunk_keys = kHostChunkKeysDefault;
+    // cached launch geometry
+    int tma_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [dtype][kind]
+    int rts_ctas_per_sm[2] = {0, 0};               // [dtype]
+    // host pipeline (lazy)
+    cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
+    void* stage[kHostBufs] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_h2d[kHostBufs] = {}, ev_cmp[kHostBufs] = {}, ev_d2h[kHostBufs] = {};
+    uint64_t* chain_slots = nullptr;  // 2 tagged slots chaining chunk totals
+    uint32_t chain_tag = 0;
+    void* chain_total = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+constexpr int dt_index() { return std::is_same<T, float>::value ? 1 : 0; }
+
+template <typename T, bool INCL>
+int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n,
+                     const CarrySpec& cs, cudaStream_t st)
+{
+    cudaError_t e;
+    if (n == 0) {
+        e = launch_carry_only<T>(c->s, cs, st);
+    } else {
+        if (algo == GPS_ALGO_CSDL) {
+            const int v = c->csdl_variant ? c->csdl_variant : GPS_CSDL_DEFAULT_VARIANT;
+            algo = v == 2 ? GPS_ALGO_CSDL_TMA : GPS_ALGO_CSDL_REG;
+        }
+        switch (algo) {
+            case GPS_ALGO_CSDL_REG:
+                e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL>(c->s, in, out, n, cs, st);
+                break;
+            case GPS_ALGO_CSDL_TMA:
+                e = launch_csdl_tma<T, GPS_TMA_NT, GPS_TMA_STAGES, INCL>(
+                    c->s, in, out, n, cs, c->tma_ctas_per_sm[dt_index<T>()][INCL ? 0 : 1],
+                    GPS_TMA_MAX_CTAS_PER_SM, st);
+                break;
+            case GPS_ALGO_CSDL_FALLBACK: {
+                FallbackParams f{kNoStall, GPS_FALLBACK_DEFAULT_SPIN, nullptr};
+                e = launch_csdl_fallback<T, GPS_REG_NT, GPS_REG_V, INCL>(c->s, in, out, n, cs, f, st);
+                break;
+            }
+            case GPS_ALGO_RTS:
+                e = launch_rts<T, GPS_RTS_NT, GPS_RTS_V, INCL>(c->s, in, out, n, cs,
+                                                                c->rts_ctas_per_sm[dt_index<T>()], st);
+                break;
+            default:
+                return fail(GPS_ERR_INVALID, "unknown algo %d", algo);
+        }
+    }
+    if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+    return GPS_OK;
+}
+
+int check_scan_args(gps_ctx* c, int kind, int dtype, const void* in, void* out, uint64_t n)
+{
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    if (kind != GPS_INCLUSIVE && kind != GPS_EXCLUSIVE) return fail(GPS_ERR_INVALID, "bad kind %d", kind);
+    if (dtype != GPS_U32 && dtype != GPS_F32) return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
+    if (n > c->max_n) return fail(GPS_ERR_INVALID, "n=%llu exceeds ctx capacity %llu",
+                                  (unsigned long long)n, (unsigned long long)c->max_n);
+    if (n && (!in || !out)) return fail(GPS_ERR_INVALID, "null data pointer");
+    if (!aligned16(in) || !aligned16(out)) return fail(GPS_ERR_ALIGNMENT, "data pointers must be 16-byte aligned");
+    if (n && in != out) {
+        const char* a = static_cast<const char*>(in);
+        const char* b = static_cast<const char*>(out);
+        if (a < b + n * 4 && b < a + n * 4)
+            return fail(GPS_ERR_INVALID, "d_in and d_out partially overlap");
+    }
+    return GPS_OK;
+}
+
+int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, void* out, uint64_t n,
+                  const CarrySpec& cs, cudaStream_t st)
+{
+    int rc = check_scan_args(c, kind, dtype, in, out, n);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    if (dtype == GPS_U32)
+        return kind == GPS_INCLUSIVE ? dispatch_scan_tk<uint32_t, true>(c, algo, in, out, n, cs, st)
+                                     : dispatch_scan_tk<uint32_t, false>(c, algo, in, out, n, cs, st);
+    return kind == GPS_INCLUSIVE ? dispatch_scan_tk<float, true>(c, algo, in, out, n, cs, st)
+                                 : dispatch_scan_tk<float, false>(c, algo, in, out, n, cs, st);
+}
+
+int fill_publish(PublishList& pl, uint64_t* const* dst, uint32_t n_dst, uint32_t tag)
+{
+    if (n_dst > (uint32_t)kMaxPublish)
+        return fail(GPS_ERR_INVALID, "at most %d publish destinations", kMaxPublish);
+    pl.n = n_dst;
+    pl.tag = tag;
+    for (uint32_t i = 0; i < n_dst; ++i) pl.dst[i] = dst[i];
+    return GPS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------
+// library / device
+// ---------------------------------------------------------------------------------
+extern "C" {
+
+int gps_abi_version(void) { return GPS_ABI_VERSION; }
+const char* gps_last_error(void) { return g_err; }
+
+int gps_device_count(int* count)
+{
+    if (!count) return fail(GPS_ERR_INVALID, "null count");
+    *count = 0;
+    GPS_CUDA(cudaGetDeviceCount(count));
+    return GPS_OK;
+}
+
+int gps_device_info(int device, char* name, int* sm_count, uint64_t* l2_bytes, uint64_t* mem_bytes)
+{
+    cudaDeviceProp prop;
+    GPS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (name) {
+        strncpy(name, prop.name, 255);
+        name[255] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = (uint64_t)prop.l2CacheSize;
+    if (mem_bytes) *mem_bytes = (uint64_t)prop.totalGlobalMem;
+    return GPS_OK;
+}
+
+int gps_set_device(int device)
+{
+    GPS_CUDA(cudaSetDevice(device));
+    return GPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------
+int gps_create(gps_ctx** out, int device, uint64_t max_n)
+{
+    if (!out) return fail(GPS_ERR_INVALID, "null ctx out");
+    *out = nullptr;
+    int count = 0;
+    GPS_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(GPS_ERR_INVALID, "device %d of %d", device, count);
+    if (div_up(max_n, kMinTileKeys) >= (1ull << 31))
+        return fail(GPS_ERR_INVALID, "max_n too large");
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    GPS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(GPS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    gps_ctx* c = new gps_ctx();
+    c->device = device;
+    c->max_n = max_n;
+    c->s.sm_count = prop.multiProcessorCount;
+    c->s.desc_tiles = (uint32_t)std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
+    cudaError_t e = cudaMalloc(&c->s.desc, (size_t)c->s.desc_tiles * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&c->s.counter, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&c->s.partials, (size_t)kMaxParts * 4);
+    if (e == cudaSuccess) e = cudaMemset(c->s.desc, 0, (size_t)c->s.desc_tiles * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemset(c->s.counter, 0, 64);
+    if (e != cudaSuccess) {
+        gps_destroy(c);
+        return fail(GPS_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(e));
+    }
+    c->s.status = c->s.counter + 1;
+    *out = c;
+    return GPS_OK;
+}
+
+void gps_destroy(gps_ctx* c)
+{
+    if (!c) return;
+    DeviceGuard g(c->device);
+    cudaFree(c->s.desc);
+    cudaFree(c->s.counter);
+    cudaFree(c->s.partials);
+    for (int i = 0; i < kHostBufs; ++i) {
+        if (c->stage[i]) cudaFree(c->stage[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_cmp[i]) cudaEventDestroy(c->ev_cmp[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+    }
+    if (c->chain_slots) cudaFree(c->chain_slots);
+    if (c->chain_total) cudaFree(c->chain_total);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+int gps_check(gps_ctx* c, void* stream)
+{
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    DeviceGuard g(c->device);
+    GPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    uint32_t st = 0;
+    GPS_CUDA(cudaMemcpy(&st, c->s.status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st) {
+        GPS_CUDA(cudaMemset(c->s.status, 0, sizeof(uint32_t)));
+        return fail(GPS_ERR_WATCHDOG, "look-back poll budget exceeded (status 0x%x): results invalid", st);
+    }
+    return GPS_OK;
+}
+
+int gps_set_option(gps_ctx* c, const char* key, int64_t value)
+{
+    if (!c || !key) return fail(GPS_ERR_INVALID, "null argument");
+    if (!strcmp(key, "csdl_variant")) {
+        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..2");
+        c->csdl_variant = (int)value;
+    } else if (!strcmp(key, "poll_sleep_ns")) {
+        if (value < 0 || value > 100000) return fail(GPS_ERR_INVALID, "poll_sleep_ns out of range");
+        c->s.poll_sleep_ns = (uint32_t)value;
+    } else if (!strcmp(key, "host_chunk_keys")) {
+        if (value < 4096 || (uint64_t)value > (1ull << 30)) return fail(GPS_ERR_INVALID, "host_chunk_keys out of range");
+        if (c->stage[0]) return fail(GPS_ERR_INVALID, "host pipeline already initialised");
+        c->host_chunk_keys = (uint64_t)value & ~3ull;
+    } else {
+        return fail(GPS_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return GPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// scans
+// ---------------------------------------------------------------------------------
+int gps_scan(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
+             uint32_t carry_in_bits, void* d_total_out, void* stream)
+{
+    CarrySpec cs;
+    cs.carry_bits = carry_in_bits;
+    cs.total_out = d_total_out;
+    return dispatch_scan(c, algo, kind, dtype, d_in, d_out, n, cs, (cudaStream_t)stream);
+}
+
+int gps_scan_carry_slots(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out,
+                         uint64_t n, const uint64_t* d_slots, uint32_t n_slots, uint32_t n_carry,
+                         uint32_t tag, void* d_total_out, void* stream)
+{
+    if (n_slots && !d_slots) return fail(GPS_ERR_INVALID, "null slots");
+    if (n_carry > n_slots) return fail(GPS_ERR_INVALID, "n_carry > n_slots");
+    CarrySpec cs;
+    cs.slots = d_slots;
+    cs.n_slots = n_slots;
+    cs.n_carry = n_carry;
+    cs.tag = tag;
+    cs.total_out = d_total_out;
+    return dispatch_scan(c, algo, kind, dtype, d_in, d_out, n, cs, (cudaStream_t)stream);
+}
+
+int gps_reduce_publish(gps_ctx* c, int dtype, const void* d_in, uint64_t n,
+                       uint64_t* const* h_dst_slots, uint32_t n_dst, uint32_t tag,
+                       void* d_total_out, void* stream)
+{
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    if (dtype != GPS_U32 && dtype != GPS_F32) return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
+    if (n > c->max_n) return fail(GPS_ERR_INVALID, "n exceeds ctx capacity");
+    if (n && !d_in) return fail(GPS_ERR_INVALID, "null data pointer");
+    if (!aligned16(d_in)) return fail(GPS_ERR_ALIGNMENT, "data pointer must be 16-byte aligned");
+    if (n_dst && !h_dst_slots) return fail(GPS_ERR_INVALID, "null destination list");
+    PublishList pl{};
+    int rc = fill_publish(pl, h_dst_slots, n_dst, tag);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const cudaError_t e =
+        dtype == GPS_U32
+            ? launch_reduce<uint32_t, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, c->rts_ctas_per_sm[0], st)
+            : launch_reduce<float, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, c->rts_ctas_per_sm[1], st);
+    if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
+    return GPS_OK;
+}
+
+int gps_reduce(gps_ctx* c, int dtype, const void* d_in, uint64_t n, void* d_total_out, void* stream)
+{
+    if (!d_total_out) return fail(GPS_ERR_INVALID, "null total_out");
+    return gps_reduce_publish(c, dtype, d_in, n, nullptr, 0, 0, d_total_out, stream);
+}
+
+int gps_scan_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void* d_in, void* d_out,
+                               uint64_t n, uint32_t stall_mask, uint32_t max_spin,
+                               uint32_t* d_stats, void* stream)
+{
+    int rc = check_scan_args(c, kind, dtype, d_in, d_out, n);
+    if (rc) return rc;
+    if (stall_mask == 0)
+        return fail(GPS_ERR_INVALID, "stall_mask 0 would stall every tile: nobody left to fall back");
+    if (max_spin == 0) return fail(GPS_ERR_INVALID, "max_spin must be >= 1");
+    if (n == 0) return GPS_OK;
+    DeviceGuard g(c->device);
+    CarrySpec cs;
+    FallbackParams f{stall_mask, max_spin, d_stats};
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (dtype == GPS_U32)
+        e = kind == GPS_INCLUSIVE
+                ? launch_csdl_fallback<uint32_t, GPS_REG_NT, GPS_REG_V, true>(c->s, d_in, d_out, n, cs, f, st)
+                : launch_csdl_fallback<uint32_t, GPS_REG_NT, GPS_REG_V, false>(c->s, d_in, d_out, n, cs, f, st);
+    else
+        e = kind == GPS_INCLUSIVE
+                ? launch_csdl_fallback<float, GPS_REG_NT, GPS_REG_V, true>(c->s, d_in, d_out, n, cs, f, st)
+                : launch_csdl_fallback<float, GPS_REG_NT, GPS_REG_V, false>(c->s, d_in, d_out, n, cs, f, st);
+    if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "fallback scan launch failed: %s", cudaGetErrorString(e));
+    return GPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// host-buffer pipeline: H2D(c+1) || scan(c) || D2H(c-1), chunk totals chained on device
+// ---------------------------------------------------------------------------------
+static int host_pipeline_init(gps_ctx* c)
+{
+    if (c->stage[0]) return GPS_OK;
+    GPS_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    GPS_CUDA(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking));
+    GPS_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    const uint64_t chunk = std::min<uint64_t>(c->host_chunk_keys, std::max<uint64_t>(c->max_n, 4096));
+    for (int i = 0; i < kHostBufs; ++i) {
+        GPS_CUDA(cudaMalloc(&c->stage[i], (chunk + 4) * 4));
+        GPS_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        GPS_CUDA(cudaEventCreateWithFlags(&c->ev_cmp[i], cudaEventDisableTiming));
+        GPS_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+    }
+    GPS_CUDA(cudaMalloc(&c->chain_slots, 2 * sizeof(uint64_t)));
+    GPS_CUDA(cudaMemset(c->chain_slots, 0, 2 * sizeof(uint64_t)));
+    GPS_CUDA(cudaMalloc(&c->chain_total, 16));
+    return GPS_OK;
+}
+
+int gps_scan_host(gps_ctx* c, int algo, int kind, int dtype, const void* h_in, void* h_out,
+                  uint64_t n, uint32_t carry_in_bits, void* h_total_out)
+{
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    if (n && (!h_in || !h_out)) return fail(GPS_ERR_INVALID, "null host pointer");
+    if (n > c->max_n) return fail(GPS_ERR_INVALID, "n exceeds ctx capacity");
+    DeviceGuard g(c->device);
+    int rc = host_pipeline_init(c);
+    if (rc) return rc;
+    const uint64_t chunk = std::min<uint64_t>(c->host_chunk_keys, std::max<uint64_t>(c->max_n, 4096));
+    const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n, chunk));
+    const char* src = static_cast<const char*>(h_in);
+    char* dst = static_cast<char*>(h_out);
+    uint32_t prev_tag = 0;
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const int b = (int)(k % kHostBufs);
+        const uint64_t off = k * chunk;
+        const uint64_t len = std::min<uint64_t>(chunk, n - off);
+        // the staging buffer is free once its previous contents went back to the host
+        if (k >= (uint64_t)kHostBufs) GPS_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));
+        if (len) GPS_CUDA(cudaMemcpyAsync(c->stage[b], src + off * 4, len * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        GPS_CUDA(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+        GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_h2d[b], 0));
+        CarrySpec cs;
+        if (++c->chain_tag == 0) ++c->chain_tag;  // 0 is the "never written" tag
+        const uint32_t tag = c->chain_tag;
+        if (k == 0) {
+            cs.carry_bits = carry_in_bits;
+        } else {  // carry = tagged total published by the previous chunk's last tile
+            cs.slots = c->chain_slots + ((k - 1) & 1);
+            cs.n_slots = cs.n_carry = 1;
+            cs.tag = prev_tag;
+        }
+        prev_tag = tag;
+        cs.publish.n = 1;
+        cs.publish.dst[0] = c->chain_slots + (k & 1);
+        cs.publish.tag = tag;
+        if (k + 1 == n_chunks) cs.total_out = c->chain_total;
+        rc = dispatch_scan(c, algo, kind, dtype, c->stage[b], c->stage[b], len, cs, c->s_cmp);
+        if (rc) return rc;
+        GPS_CUDA(cudaEventRecord(c->ev_cmp[b], c->s_cmp));
+        GPS_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_cmp[b], 0));
+        if (len) GPS_CUDA(cudaMemcpyAsync(dst + off * 4, c->stage[b], len * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        GPS_CUDA(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
+    }
+    if (h_total_out) {
+        GPS_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_cmp[(n_chunks - 1) % kHostBufs], 0));
+        GPS_CUDA(cudaMemcpyAsync(h_total_out, c->chain_total, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    GPS_CUDA(cudaStreamSynchronize(c->s_d2h));
+    GPS_CUDA(cudaStreamSynchronize(c->s_cmp));
+    return GPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// harness kernels
+// ---------------------------------------------------------------------------------
+static inline int util_grid(uint64_t n)
+{
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(div_up(n, 256 * 8), 148 * 16));
+}
+
+int gps_init_ones(void* d, uint64_t n, int dtype, void* stream)
+{
+    if (n && !d) return fail(GPS_ERR_INVALID, "null pointer");
+    if (!n) return GPS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GPS_U32)
+        init_ones_kernel<uint32_t><<<util_grid(n), 256, 0, st>>>(static_cast<uint32_t*>(d), n);
+    else if (dtype == GPS_F32)
+        init_ones_kernel<float><<<util_grid(n), 256, 0, st>>>(static_cast<float*>(d), n);
+    else
+        return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
+    GPS_CUDA(cudaGetLastError());
+    return GPS_OK;
+}
+
+int gps_init_random(void* d, uint64_t n, int dtype, uint64_t seed, uint32_t mask, uint64_t first_index,
+                    void* stream)
+{
+    if (n && !d) return fail(GPS_ERR_INVALID, "null pointer");
+    if (!n) return GPS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == GPS_U32)
+        init_random_u32_kernel<<<util_grid(n), 256, 0, st>>>(static_cast<uint32_t*>(d), n, seed, mask, first_index);
+    else if (dtype == GPS_F32)
+        init_random_f32_kernel<<<util_grid(n), 256, 0, st>>>(static_cast<float*>(d), n, seed, first_index);
+    else
+        return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
+    GPS_CUDA(cudaGetLastError());
+    return GPS_OK;
+}
+
+int gps_validate_ones(const void* d, uint64_t n, int kind, uint32_t first_value, uint64_t* h_errs)
+{
+    if (!h_errs || (n && !d)) return fail(GPS_ERR_INVALID, "null pointer");
+    unsigned long long* d_err = nullptr;
+    GPS_CUDA(cudaMalloc(&d_err, sizeof(unsigned long long)));
+    GPS_CUDA(cudaMemset(d_err, 0, sizeof(unsigned long long)));
+    if (n)
+        validate_ones_kernel<<<util_grid(n), 256>>>(static_cast<const uint32_t*>(d), n, first_value,
+                                                    kind == GPS_INCLUSIVE ? 1u : 0u, d_err);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d_err, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_err);
+    GPS_CUDA(e);
+    *h_errs = h;
+    return GPS_OK;
+}
+
+int gps_compare_u32(const void* d_a, const void* d_b, uint64_t n, uint64_t* h_errs, uint64_t* h_first_bad)
+{
+    if (!h_errs || (n && (!d_a || !d_b))) return fail(GPS_ERR_INVALID, "null pointer");
+    unsigned long long* d_err = nullptr;
+    unsigned long long init[2] = {0ull, ~0ull};
+    GPS_CUDA(cudaMalloc(&d_err, sizeof(init)));
+    GPS_CUDA(cudaMemcpy(d_err, init, sizeof(init), cudaMemcpyHostToDevice));
+    if (n)
+        compare_u32_kernel<<<util_grid(n), 256>>>(static_cast<const uint32_t*>(d_a),
+                                                  static_cast<const uint32_t*>(d_b), n, d_err);
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(h, d_err, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_err);
+    GPS_CUDA(e);
+    *h_errs = h[0];
+    if (h_first_bad) *h_first_bad = h[0] ? h[1] : n;
+    return GPS_OK;
+}
+
+int gps_compare_f32(const void* d_a, const void* d_b, const void* d_bound, uint64_t n, float rtol,
+                    float atol, uint64_t* h_errs, float* h_max_abs_diff)
+{
+    if (!h_errs || (n && (!d_a || !d_b))) return fail(GPS_ERR_INVALID, "null pointer");
+    unsigned long long* d_err = nullptr;
+    GPS_CUDA(cudaMalloc(&d_err, 16));
+    GPS_CUDA(cudaMemset(d_err, 0, 16));
+    if (n)
+        compare_f32_kernel<<<util_grid(n), 256>>>(static_cast<const float*>(d_a),
+                                                  static_cast<const float*>(d_b),
+                                                  static_cast<const float*>(d_bound), n, rtol, atol,
+                                                  d_err, reinterpret_cast<uint32_t*>(d_err + 1));
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(h, d_err, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_err);
+    GPS_CUDA(e);
+    *h_errs = h[0];
+    if (h_max_abs_diff) {
+        uint32_t bits = (uint32_t)h[1];
+        memcpy(h_max_abs_diff, &bits, 4);
+    }
+    return GPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// memory / stream / timing helpers
+// ---------------------------------------------------------------------------------
+int gps_malloc(void** d_ptr, uint64_t bytes)
+{
+    if (!d_ptr) return fail(GPS_ERR_INVALID, "null pointer");
+    GPS_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return GPS_OK;
+}
+int gps_free(void* d_ptr)
+{
+    GPS_CUDA(cudaFree(d_ptr));
+    return GPS_OK;
+}
+int gps_malloc_host(void** h_ptr, uint64_t bytes)
+{
+    if (!h_ptr) return fail(GPS_ERR_INVALID, "null pointer");
+    GPS_CUDA(cudaMallocHost(h_ptr, bytes ? bytes : 16));
+    return GPS_OK;
+}
+int gps_free_host(void* h_ptr)
+{
+    GPS_CUDA(cudaFreeHost(h_ptr));
+    return GPS_OK;
+}
+int gps_memcpy_h2d(void* d, const void* h, uint64_t bytes, void* stream)
+{
+    GPS_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return GPS_OK;
+}
+int gps_memcpy_d2h(void* h, const void* d, uint64_t bytes, void* stream)
+{
+    GPS_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return GPS_OK;
+}
+int gps_memcpy_d2d(void* dst, const void* src, uint64_t bytes, void* stream)
+{
+    GPS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GPS_OK;
+}
+int gps_memset(void* d, int byte, uint64_t bytes, void* stream)
+{
+    GPS_CUDA(cudaMemsetAsync(d, byte, bytes, (cudaStream_t)stream));
+    return GPS_OK;
+}
+int gps_stream_sync(void* stream)
+{
+    GPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return GPS_OK;
+}
+int gps_device_sync(void)
+{
+    GPS_CUDA(cudaDeviceSynchronize());
+    return GPS_OK;
+}
+int gps_event_create(void** ev)
+{
+    if (!ev) return fail(GPS_ERR_INVALID, "null pointer");
+    cudaEvent_t e;
+    GPS_CUDA(cudaEventCreate(&e));
+    *ev = e;
+    return GPS_OK;
+}
+int gps_event_destroy(void* ev)
+{
+    GPS_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+    return GPS_OK;
+}
+int gps_event_record(void* ev, void* stream)
+{
+    GPS_CUDA(cudaEventRecord((cudaEvent_t)ev, (cudaStream_t)stream));
+    return GPS_OK;
+}
+int gps_event_elapsed_ms(void* start, void* stop, float* ms)
+{
+    if (!ms) return fail(GPS_ERR_INVALID, "null pointer");
+    GPS_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    GPS_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return GPS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// CUDA IPC
+// ---------------------------------------------------------------------------------
+int gps_ipc_export(void* d_ptr, unsigned char handle[GPS_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == GPS_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    GPS_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, sizeof(h));
+    return GPS_OK;
+}
+int gps_ipc_open(const unsigned char handle[GPS_IPC_HANDLE_BYTES], void** d_ptr)
+{
+    if (!d_ptr) return fail(GPS_ERR_INVALID, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    GPS_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GPS_OK;
+}
+int gps_ipc_close(void* d_ptr)
+{
+    GPS_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return GPS_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------
+// single-process sharded scan
+// ---------------------------------------------------------------------------------
+struct gps_shard_group {
+    int n = 0;
+    std::vector<int> devices;
+    std::vector<gps_ctx*> ctx;
+    std::vector<cudaStream_t> stream;
+    std::vector<uint64_t*> slots;   // per GPU: 2 parities x n slots
+    std::vector<cudaEvent_t> ev0, ev1;
+    uint32_t tag = 0;
+};
+
+extern "C" {
+
+int gps_sharded_create(gps_shard_group** out, int n_gpus, const int* devices, uint64_t max_n_per_gpu)
+{
+    if (!out || !devices || n_gpus < 1 || n_gpus > kMaxPublish)
+        return fail(GPS_ERR_INVALID, "bad sharded_create arguments");
+    *out = nullptr;
+    gps_shard_group* g = new gps_shard_group();
+    g->n = n_gpus;
+    g->devices.assign(devices, devices + n_gpus);
+    g->ctx.assign(n_gpus, nullptr);
+    g->stream.assign(n_gpus, nullptr);
+    g->slots.assign(n_gpus, nullptr);
+    g->ev0.assign(n_gpus, nullptr);
+    g->ev1.assign(n_gpus, nullptr);
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = GPS_OK;
+    for (int i = 0; i < n_gpus && rc == GPS_OK; ++i) {
+        rc = gps_create(&g->ctx[i], devices[i], max_n_per_gpu);
+        if (rc) break;
+        cudaError_t e = cudaSetDevice(devices[i]);
+        for (int j = 0; j < n_gpus && e == cudaSuccess; ++j) {
+            if (devices[j] == devices[i]) continue;
+            int can = 0;
+            e = cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+            if (e == cudaSuccess && !can) {
+                rc = fail(GPS_ERR_UNSUPPORTED, "no peer access %d -> %d", devices[i], devices[j]);
+                break;
+            }
+            if (e == cudaSuccess) {
+                e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                    e = cudaSuccess;
+                    cudaGetLastError();
+                }
+            }
+        }
+        if (rc) break;
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc(&g->slots[i], 2 * kMaxPublish * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMemset(g->slots[i], 0, 2 * kMaxPublish * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaEventCreate(&g->ev0[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&g->ev1[i]);
+        if (e != cudaSuccess) rc = fail(GPS_ERR_CUDA, "sharded setup on device %d: %s", devices[i], cudaGetErrorString(e));
+    }
+    cudaSetDevice(prev);
+    if (rc) {
+        gps_sharded_destroy(g);
+        return rc;
+    }
+    *out = g;
+    return GPS_OK;
+}
+
+void gps_sharded_destroy(gps_shard_group* g)
+{
+    if (!g) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int i = 0; i < g->n; ++i) {
+        cudaSetDevice(g->devices[i]);
+        if (g->stream[i]) cudaStreamDestroy(g->stream[i]);
+        if (g->slots[i]) cudaFree(g->slots[i]);
+        if (g->ev0[i]) cudaEventDestroy(g->ev0[i]);
+        if (g->ev1[i]) cudaEventDestroy(g->ev1[i]);
+        if (g->ctx[i]) gps_destroy(g->ctx[i]);
+    }
+    cudaSetDevice(prev);
+    delete g;
+}
+
+int gps_sharded_scan(gps_shard_group* g, int algo, int kind, int dtype, const void* const* d_in,
+                     void* const* d_out, const uint64_t* n_per_gpu, int carry_mode, float* h_ms)
+{
+    if (!g || !d_in || !d_out || !n_per_gpu) return fail(GPS_ERR_INVALID, "null argument");
+    if (carry_mode != 0 && carry_mode != 1) return fail(GPS_ERR_INVALID, "bad carry_mode");
+    const int G = g->n;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    const uint32_t tag = ++g->tag ? g->tag : ++g->tag;
+    const uint32_t par = tag & 1u;
+    int rc = GPS_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    // pass 1: reduce every slice; publish its tagged total into slot [par][i] of EVERY
+    // GPU (P2P stores over NVLink).  Every GPU later polls all G slots, so nobody can
+    // run a whole step ahead and overwrite a slot that is still being read.
+    std::vector<void*> totals(G, nullptr);
+    for (int i = 0; i < G && !rc; ++i) {
+        cudaSetDevice(g->devices[i]);
+        cudaEventRecord(g->ev0[i], g->stream[i]);
+        uint64_t* dst[kMaxPublish];
+        uint32_t n_dst = 0;
+        if (carry_mode == 0)
+            for (int j = 0; j < G; ++j) dst[n_dst++] = g->slots[j] + par * kMaxPublish + i;
+        else
+            dst[n_dst++] = g->slots[i] + par * kMaxPublish + i;
+        rc = gps_reduce_publish(g->ctx[i], dtype, d_in[i], n_per_gpu[i], dst, n_dst, tag, nullptr, g->stream[i]);
+    }
+    if (!rc && carry_mode == 1) {  // host-staged exchange (debug / no-P2P boxes)
+        std::vector<uint64_t> words(G, 0);
+        for (int i = 0; i < G; ++i) {
+            cudaSetDevice(g->devices[i]);
+            cudaStreamSynchronize(g->stream[i]);
+            cudaMemcpy(&words[i], g->slots[i] + par * kMaxPublish + i, 8, cudaMemcpyDeviceToHost);
+        }
+        for (int i = 0; i < G; ++i) {
+            cudaSetDevice(g->devices[i]);
+            cudaMemcpyAsync(g->slots[i] + par * kMaxPublish, words.data(), 8 * G, cudaMemcpyHostToDevice, g->stream[i]);
+            cudaStreamSynchronize(g->stream[i]);
+        }
+    }
+    // pass 2: scan with the carry folded into tile 0's look-back
+    for (int i = 0; i < G && !rc; ++i) {
+        cudaSetDevice(g->devices[i]);
+        rc = gps_scan_carry_slots(g->ctx[i], algo, kind, dtype, d_in[i], d_out[i], n_per_gpu[i],
+                                  g->slots[i] + par * kMaxPublish, (uint32_t)G, (uint32_t)i, tag,
+                                  nullptr, g->stream[i]);
+        cudaEventRecord(g->ev1[i], g->stream[i]);
+    }
+    float worst = 0.f;
+    for (int i = 0; i < G; ++i) {
+        cudaSetDevice(g->devices[i]);
+        cudaError_t e = cudaStreamSynchronize(g->stream[i]);
+        if (e != cudaSuccess && !rc) rc = fail(GPS_ERR_CUDA, "device %d: %s", g->devices[i], cudaGetErrorString(e));
+        float ms = 0.f;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, g->ev0[i], g->ev1[i]) == cudaSuccess)
+            worst = std::max(worst, ms);
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    (void)t0;
+    (void)t1;
+    if (h_ms) *h_ms = worst;
+    cudaSetDevice(prev);
+    return rc;
+}
+
+}  // extern "C"

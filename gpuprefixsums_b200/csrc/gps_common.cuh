@@ -1,0 +1,410 @@
+// gps_common.cuh -- device primitives shared by all sm_100a scan kernels.
+//
+// Replaces the reference's L0 layer (paths relative to /root/reference/GPUPrefixSumsCUDA):
+//   Utils.cuh:22-71   lane id, InclusiveWarpScan, InclusiveWarpScanCircularShift,
+//                     WarpReduceSum, uint4 helpers
+//   ChainedScanDecoupledLookback.cuh:19-23,50-77   flag encoding + LookbackWarp
+// Differences that matter on B200:
+//   * tile descriptor is ONE 64-bit word {value:32 | epoch:30 | status:2} written with
+//     st.release.gpu / read with ld.acquire.gpu, so the aggregate is a full 32-bit
+//     value (the reference packs 30 bits next to the flag and silently truncates
+//     totals >= 2^30) and float32 bit patterns travel unchanged;
+//   * the epoch tag makes descriptors of earlier launches read as NOT_READY, so no
+//     cudaMemset per launch (reference: ...Dispatcher.cuh:172-175);
+//   * polls are gpu-scope acquire loads, not `volatile` (.SYS) loads, and only the
+//     publishing lane orders its store -- no block-wide __threadfence().
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+namespace gps {
+
+// ---------------------------------------------------------------------------------
+// kernel parameter block (passed by value as a __grid_constant__)
+// ---------------------------------------------------------------------------------
+// Destinations of a tagged total {value:32 | tag:32}: carry slots of downstream
+// consumers (peer GPUs over NVLink, or the next chunk of the host pipeline).
+constexpr int kMaxPublish = 16;
+struct PublishList {
+    uint64_t* dst[kMaxPublish];
+    uint32_t n;
+    uint32_t tag;
+};
+
+struct ScanParams {
+    const void* in;
+    void* out;
+    uint64_t n;               // keys
+    uint64_t* desc;           // one 64-bit descriptor per tile
+    uint32_t* counter;        // monotonically increasing tile-claim counter
+    uint32_t counter_base;    // value of *counter when this launch starts
+    uint32_t epoch;           // 1 .. 2^30-1, unique per launch within a ctx
+    uint32_t num_tiles;
+    uint32_t carry_bits;      // immediate carry (uint32 or float bits)
+    const uint64_t* slots;    // optional carry slots {value:32 | tag:32}
+    uint32_t n_slots;         // slots polled until their tag == slot_tag
+    uint32_t n_carry;         // the first n_carry of them are summed into the carry
+    uint32_t slot_tag;
+    void* total_out;          // optional: carry + sum of all keys
+    PublishList publish;      // optional: tagged total for downstream consumers
+    uint32_t* status;         // watchdog / error word (bit 0 = poll budget exceeded)
+    uint32_t poll_sleep_ns;
+    uint32_t flags;           // PF_* bits
+};
+enum : uint32_t { PF_DESC_RELAXED = 1u };  // tuning: relaxed instead of release/acquire
+
+enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
+enum : uint32_t { STATUS_WATCHDOG = 1u };
+constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+constexpr uint32_t kWatchdogPolls = 1u << 22;  // * ~0.5 us per poll => seconds, then bail out
+
+// ---------------------------------------------------------------------------------
+// bit casts
+// ---------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ uint32_t to_bits(T v)
+{
+    if constexpr (std::is_same<T, float>::value)
+        return __float_as_uint(v);
+    else
+        return (uint32_t)v;
+}
+template <typename T>
+__device__ __forceinline__ T from_bits(uint32_t b)
+{
+    if constexpr (std::is_same<T, float>::value)
+        return __uint_as_float(b);
+    else
+        return (T)b;
+}
+
+__device__ __forceinline__ uint64_t pack_desc(uint32_t value_bits, uint32_t epoch, uint32_t status)
+{
+    return ((uint64_t)((epoch << 2) | status) << 32) | (uint64_t)value_bits;
+}
+__device__ __forceinline__ uint32_t desc_value(uint64_t d) { return (uint32_t)d; }
+__device__ __forceinline__ uint32_t desc_status(uint64_t d) { return (uint32_t)(d >> 32) & ST_MASK; }
+__device__ __forceinline__ bool desc_valid(uint64_t d, uint32_t epoch)
+{
+    return ((uint32_t)(d >> 34)) == epoch;
+}
+
+// ---------------------------------------------------------------------------------
+// PTX: scoped loads / stores for descriptors and carry slots
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t ld_acquire_gpu(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_gpu(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Descriptor publish / poll: st.release.gpu / ld.acquire.gpu.  The payload rides in the
+// same 64-bit word as the flag, so plain CSDL would also be correct with relaxed
+// accesses; PF_DESC_RELAXED (a warp-uniform runtime flag used by the tuning harness)
+// selects them to measure what the release/acquire qualifiers cost.
+__device__ __forceinline__ void desc_publish(const ScanParams& p, uint64_t* ptr, uint64_t v)
+{
+    if (p.flags & PF_DESC_RELAXED)
+        st_relaxed_gpu(ptr, v);
+    else
+        st_release_gpu(ptr, v);
+}
+__device__ __forceinline__ uint64_t desc_poll(const ScanParams& p, const uint64_t* ptr)
+{
+    return (p.flags & PF_DESC_RELAXED) ? ld_relaxed_gpu(ptr) : ld_acquire_gpu(ptr);
+}
+
+// ---------------------------------------------------------------------------------
+// PTX: streaming 128-bit global access (data is touched exactly once: keep it out of
+// L1).  Not .nc: the scan may run in place.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// PTX: mbarrier + TMA bulk copies (cp.async.bulk -> SASS UBLKCP)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared::cta, completion signalled on an mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                          uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_addr(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+// shared::cta -> global, tracked by the per-thread bulk async-group
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_addr(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (TMA store)
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// warp primitives (Utils.cuh:22-59), generic over uint32_t / float
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id()
+{
+    uint32_t l;
+    asm("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_inclusive_scan(T v, uint32_t lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const T t = __shfl_up_sync(kFullMask, v, d);
+        if (lane >= (uint32_t)d) v += t;
+    }
+    return v;
+}
+
+// exclusive prefix of a lane given the inclusive scan `inc` of `raw`
+template <typename T>
+__device__ __forceinline__ T warp_exclusive_of(T inc, T raw, uint32_t lane)
+{
+    if constexpr (std::is_same<T, float>::value) {
+        const T t = __shfl_up_sync(kFullMask, inc, 1);
+        return lane ? t : T(0);
+    } else {
+        (void)lane;
+        return inc - raw;  // exact mod 2^32
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_reduce(T v)
+{
+#pragma unroll
+    for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(kFullMask, v, m);
+    return v;
+}
+
+// Block-level exclusive scan of the per-warp totals held in s_warp[NW] (NW <= 32):
+// every warp redundantly scans the NW totals with shuffles.  Must be called by all
+// threads of the warp after the __syncthreads that follows the s_warp writes.
+template <typename T, int NW>
+__device__ __forceinline__ void block_scan_warp_totals(const T* s_warp, uint32_t warp,
+                                                       uint32_t lane, T& warp_prefix, T& aggregate)
+{
+    static_assert(NW <= 32, "at most 32 warps per block");
+    const T raw = lane < (uint32_t)NW ? s_warp[lane] : T(0);
+    const T inc = warp_inclusive_scan(raw, lane);
+    const T exc = warp_exclusive_of(inc, raw, lane);
+    warp_prefix = __shfl_sync(kFullMask, exc, (int)warp);
+    aggregate = __shfl_sync(kFullMask, inc, NW - 1);
+}
+
+// ---------------------------------------------------------------------------------
+// watchdog: a spin that exceeds kWatchdogPolls sets bit 0 of *status and gives up
+// (the result is then wrong, gps_check() reports GPS_ERR_WATCHDOG) instead of
+// hanging the GPU.  Pollers also bail out early once another tile tripped it.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool watchdog_tick(uint32_t& polls, uint32_t* status)
+{
+    ++polls;
+    if ((polls & 1023u) == 0u) {
+        if (polls >= kWatchdogPolls) {
+            atomicOr(status, STATUS_WATCHDOG);
+            return true;
+        }
+        if (ld_relaxed_gpu_u32(status) & STATUS_WATCHDOG) return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------
+// carry acquisition (tile 0 / spine): immediate carry + sum of the tagged carry slots.
+// Called by a full warp.  Slots may live in this GPU's memory and be written by peer
+// GPUs over NVLink (st.release.sys), hence system scope.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T acquire_carry(const ScanParams& p, uint32_t lane)
+{
+    T carry = from_bits<T>(p.carry_bits);
+    for (uint32_t base = 0; base < p.n_slots; base += 32) {
+        const uint32_t i = base + lane;
+        T v = T(0);
+        if (i < p.n_slots) {
+            uint32_t polls = 0;
+            uint64_t s = ld_acquire_sys(p.slots + i);
+            while ((uint32_t)(s >> 32) != p.slot_tag) {
+                if (watchdog_tick(polls, p.status)) break;
+                __nanosleep(64);
+                s = ld_acquire_sys(p.slots + i);
+            }
+            if (i < p.n_carry) v = from_bits<T>((uint32_t)s);
+        }
+        carry += warp_reduce(v);
+    }
+    return carry;
+}
+
+// tagged total -> every destination slot (called by ONE thread)
+template <typename T>
+__device__ __forceinline__ void publish_total(const PublishList& pl, T total)
+{
+    const uint64_t word = ((uint64_t)pl.tag << 32) | (uint64_t)to_bits(total);
+#pragma unroll 1
+    for (uint32_t i = 0; i < pl.n; ++i) st_release_sys(pl.dst[i], word);
+}
+
+// grand total of a launch: plain value + tagged copies for downstream consumers
+template <typename T>
+__device__ __forceinline__ void write_total(const ScanParams& p, T total)
+{
+    if (p.total_out) *reinterpret_cast<T*>(p.total_out) = total;
+    publish_total<T>(p.publish, total);
+}
+
+// claim the next tile index; the counter is never reset (host advances counter_base)
+__device__ __forceinline__ uint32_t claim_tile(const ScanParams& p)
+{
+    return atomicAdd(p.counter, 1u) - p.counter_base;
+}
+
+// ---------------------------------------------------------------------------------
+// warp-parallel decoupled look-back (ChainedScanDecoupledLookback.cuh:50-77).
+// Lane l polls the descriptor of tile (top - l); lanes that fall below tile 0 see a
+// virtual INCLUSIVE/0 entry (they are never the nearest INCLUSIVE because tile 0
+// itself always publishes INCLUSIVE).  Returns the exclusive prefix of `tile`.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, uint32_t lane)
+{
+    T prefix = T(0);
+    int64_t top = (int64_t)tile - 1;
+    uint32_t polls = 0;
+    while (true) {
+        const int64_t idx = top - (int64_t)lane;
+        uint64_t d = pack_desc(0u, p.epoch, ST_INCLUSIVE);
+        bool ready = true;
+        if (idx >= 0) {
+            d = desc_poll(p, p.desc + idx);
+            ready = desc_valid(d, p.epoch);
+        }
+        if (!__all_sync(kFullMask, ready)) {
+            const bool bail = watchdog_tick(polls, p.status);
+            if (__any_sync(kFullMask, bail)) return prefix;  // warp-uniform exit
+            if (p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
+            continue;
+        }
+        const T v = from_bits<T>(desc_value(d));
+        const uint32_t incl = __ballot_sync(kFullMask, desc_status(d) == ST_INCLUSIVE);
+        if (incl) {
+            const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
+            prefix += warp_reduce(lane <= nearest ? v : T(0));
+            return prefix;
+        }
+        prefix += warp_reduce(v);
+        top -= 32;
+    }
+}
+
+}  // namespace gps

@@ -1,0 +1,285 @@
+// gps_csdl_reg.cuh -- Chained Scan with Decoupled Lookback, register path, plus the
+// Decoupled-Fallback / emulated-deadlock variant.
+//
+// Replaces ChainedScanDecoupledLookback.cuh:79-153 (CSDL, CSDLInclusive/Exclusive) and
+// EmulatedDeadlocking.cuh:26-168 (EmulatedDeadlock) of the reference.  One CTA per
+// tile; tile order = order of the atomic claim (CSDL.cuh:90-94), which is what makes
+// spinning on predecessors deadlock-free.
+#pragma once
+#include "gps_tile_reg.cuh"
+
+namespace gps {
+
+// ---------------------------------------------------------------------------------
+// CSDL, register path
+// ---------------------------------------------------------------------------------
+template <typename T, int NT, int V, bool INCLUSIVE>
+__global__ void __launch_bounds__(NT) csdl_reg_kernel(const __grid_constant__ ScanParams p)
+{
+    using Tile = RegTile<T, NT, V>;
+    constexpr int NW = Tile::NW;
+    __shared__ T s_warp[NW];
+    __shared__ T s_prefix;
+    __shared__ uint32_t s_tile;
+
+    const uint32_t lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) s_tile = claim_tile(p);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
+    const uint64_t vbase = Tile::vec_base(tile, warp, lane);
+
+    Tile t;
+    if (full)
+        t.load_full(p.in, vbase);
+    else
+        t.load_partial(p.in, vbase, p.n);
+    t.scan_warp(lane);
+    if (lane == 0) s_warp[warp] = t.warp_total;
+    __syncthreads();
+
+    T warp_prefix, aggregate;
+    block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, aggregate);
+
+    if (warp == 0) {
+        T prefix;
+        if (tile == 0) {
+            prefix = acquire_carry<T>(p, lane);
+        } else {
+            if (lane == 0)
+                desc_publish(p, p.desc + tile, pack_desc(to_bits(aggregate), p.epoch, ST_AGGREGATE));
+            prefix = lookback_warp<T>(p, tile, lane);
+        }
+        if (lane == 0) {
+            const T inclusive = prefix + aggregate;
+            desc_publish(p, p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
+            s_prefix = prefix;
+            if (tile == p.num_tiles - 1) write_total<T>(p, inclusive);
+        }
+    }
+    __syncthreads();
+
+    const T prefix = s_prefix + warp_prefix;
+    if (full)
+        t.template store_full<INCLUSIVE>(p.out, vbase, prefix);
+    else
+        t.template store_partial<INCLUSIVE>(p.out, vbase, p.n, prefix);
+}
+
+// ---------------------------------------------------------------------------------
+// CSDL + Decoupled Fallback, with optional emulated stalls
+// ---------------------------------------------------------------------------------
+struct FallbackParams {
+    uint32_t stall_mask;   // tiles with (tile & mask) == 0 stall; 0xFFFFFFFF = none
+    uint32_t max_spin;     // unsuccessful polls of a window before falling back
+    uint32_t* stats;       // nullable: {spins, fallbacks, insertions, lookback windows}
+};
+constexpr uint32_t kNoStall = 0xFFFFFFFFu;
+
+enum : uint32_t { LB_DONE = 0, LB_FALLBACK = 1 };
+
+template <typename T, int NT, int V, bool INCLUSIVE>
+__global__ void __launch_bounds__(NT)
+    csdl_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
+{
+    using Tile = RegTile<T, NT, V>;
+    constexpr int NW = Tile::NW;
+    __shared__ T s_warp[NW];
+    __shared__ T s_red[NW];
+    __shared__ T s_prefix;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_state;     // LB_DONE / LB_FALLBACK
+    __shared__ uint32_t s_fb_tile;   // tile to recompute
+
+    const uint32_t lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) s_tile = claim_tile(p);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
+    const uint64_t vbase = Tile::vec_base(tile, warp, lane);
+
+    Tile t;
+    if (full)
+        t.load_full(p.in, vbase);
+    else
+        t.load_partial(p.in, vbase, p.n);
+    t.scan_warp(lane);
+    if (lane == 0) s_warp[warp] = t.warp_total;
+    __syncthreads();
+
+    T warp_prefix, aggregate;
+    block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, aggregate);
+
+    // Stall emulation (EmulatedDeadlocking.cuh:63-72): the tile refuses to publish until
+    // some successor's fallback has published for it.  The last tile never stalls: it
+    // has no successor to rescue it (the reference hangs there).
+    const bool stalled = f.stall_mask != kNoStall && (tile & f.stall_mask) == 0u &&
+                         p.num_tiles > 1u && tile != p.num_tiles - 1u;
+    T carry = T(0);
+    if (warp == 0) {
+        if (tile == 0) carry = acquire_carry<T>(p, lane);
+        if (lane == 0) {
+            if (stalled) {
+                uint32_t polls = 0;
+                while (!desc_valid(ld_acquire_gpu(p.desc + tile), p.epoch)) {
+                    if (watchdog_tick(polls, p.status)) break;
+                }
+            }
+            // overwrite (same value for uint32; for float32 the recomputed aggregate may
+            // differ in the last bits -- both are within the stated tolerance)
+            const T v = tile ? aggregate : carry + aggregate;
+            st_release_gpu(p.desc + tile,
+                           pack_desc(to_bits(v), p.epoch, tile ? ST_AGGREGATE : ST_INCLUSIVE));
+            // In-place safety of the fallback: a successor may be re-reading this tile's
+            // INPUT right now.  The descriptor must be visible before any thread of this
+            // CTA overwrites the input with outputs, so that successor's CAS then fails
+            // and it discards what it read.  (fence + the __syncthreads below.)
+            __threadfence();
+        }
+    }
+    __syncthreads();  // holds the whole block while stalled ("purely for emulation")
+
+    uint32_t n_spins = 0, n_fallbacks = 0, n_inserts = 0, n_windows = 0;
+    T prefix = carry;  // tile 0: done
+    if (tile != 0) {
+        // warp 0 runs the warp-parallel look-back with a spin budget; when the budget is
+        // exhausted the whole CTA recomputes the aggregate of the nearest not-ready tile
+        int64_t top = (int64_t)tile - 1;
+        prefix = T(0);
+        while (true) {
+            if (warp == 0) {
+                uint32_t state = LB_DONE, spins = 0, polls = 0;
+                uint32_t fb = 0;
+                while (true) {
+                    const int64_t idx = top - (int64_t)lane;
+                    uint64_t d = pack_desc(0u, p.epoch, ST_INCLUSIVE);
+                    bool ready = true;
+                    if (idx >= 0) {
+                        d = ld_acquire_gpu(p.desc + idx);
+                        ready = desc_valid(d, p.epoch);
+                    }
+                    ++n_windows;
+                    const uint32_t not_ready = __ballot_sync(kFullMask, !ready);
+                    const uint32_t first_nr = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
+                    const uint32_t below = first_nr >= 32u ? kFullMask : ((1u << first_nr) - 1u);
+                    const uint32_t incl =
+                        __ballot_sync(kFullMask, ready && desc_status(d) == ST_INCLUSIVE) & below;
+                    const T v = from_bits<T>(desc_value(d));
+                    if (incl) {
+                        const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
+                        prefix += warp_reduce(lane <= nearest ? v : T(0));
+                        state = LB_DONE;
+                        break;
+                    }
+                    if (first_nr == 32u) {  // whole window ready, none inclusive
+                        prefix += warp_reduce(v);
+                        top -= 32;
+                        spins = 0;
+                        continue;
+                    }
+                    ++n_spins;
+                    const bool bail = watchdog_tick(polls, p.status);
+                    if (__any_sync(kFullMask, bail)) {
+                        state = LB_DONE;
+                        break;
+                    }
+                    if (++spins < f.max_spin) {
+                        if (p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
+                        continue;
+                    }
+                    // budget exhausted: consume the ready tiles nearer than the blocker and
+                    // fall back on the blocker itself
+                    prefix += warp_reduce(lane < first_nr ? v : T(0));
+                    fb = (uint32_t)(top - (int64_t)first_nr);
+                    top = (int64_t)fb - 1;
+                    state = LB_FALLBACK;
+                    break;
+                }
+                if (lane == 0) {
+                    s_state = state;
+                    s_fb_tile = fb;
+                }
+            }
+            __syncthreads();
+            if (s_state == LB_DONE) break;
+
+            // ---- Decoupled Fallback (EmulatedDeadlocking.cuh:112-151): every thread
+            // helps to re-reduce tile fb from the INPUT array
+            const uint32_t fb = s_fb_tile;
+            ++n_fallbacks;
+            {
+                Tile ft;  // a fallback target is never the last tile => always full
+                ft.load_full(p.in, Tile::vec_base(fb, warp, lane));
+                const T ws = warp_reduce(ft.thread_sum());
+                if (lane == 0) s_red[warp] = ws;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                T red = warp_reduce(lane < (uint32_t)NW ? s_red[lane] : T(0));
+                if (fb == 0) red += acquire_carry<T>(p, lane);  // tile 0 is INCLUSIVE incl. carry
+                uint32_t done = 0;
+                if (lane == 0) {
+                    const uint32_t st = fb ? ST_AGGREGATE : ST_INCLUSIVE;
+                    const uint64_t mine = pack_desc(to_bits(red), p.epoch, st);
+                    // CAS from the stale (earlier-epoch) word we observe to ours
+                    uint64_t seen = ld_acquire_gpu(p.desc + fb);
+                    T use = red;
+                    uint32_t use_st = st;
+                    bool inserted = false;
+                    while (!desc_valid(seen, p.epoch)) {
+                        const uint64_t old =
+                            atomicCAS(reinterpret_cast<unsigned long long*>(p.desc + fb),
+                                      (unsigned long long)seen, (unsigned long long)mine);
+                        if (old == seen) {
+                            inserted = true;
+                            break;
+                        }
+                        seen = old;
+                    }
+                    if (!inserted) {  // the owner (or another rescuer) got there first
+                        use = from_bits<T>(desc_value(seen));
+                        use_st = desc_status(seen);
+                    } else {
+                        ++n_inserts;
+                    }
+                    prefix += use;
+                    done = (use_st == ST_INCLUSIVE || fb == 0) ? 1u : 0u;
+                }
+                // lane 0 carries the running prefix; broadcast so warp_reduce adds stay uniform
+                prefix = __shfl_sync(kFullMask, prefix, 0);
+                done = __shfl_sync(kFullMask, done, 0);
+                if (lane == 0) s_state = done ? LB_DONE : LB_FALLBACK;
+            }
+            __syncthreads();
+            if (s_state == LB_DONE) break;
+            __syncthreads();  // s_state is rewritten by the next look-back round
+        }
+    }
+
+    if (warp == 0 && lane == 0) {
+        const T inclusive = prefix + aggregate;
+        if (tile != 0)
+            st_release_gpu(p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
+        s_prefix = prefix;
+        if (tile == p.num_tiles - 1) write_total<T>(p, inclusive);
+        if (f.stats) {
+            if (n_spins) atomicAdd(f.stats + 0, n_spins);
+            if (n_inserts) atomicAdd(f.stats + 2, n_inserts);
+            if (n_windows) atomicAdd(f.stats + 3, n_windows);
+        }
+    }
+    if (threadIdx.x == 0 && f.stats && n_fallbacks) atomicAdd(f.stats + 1, n_fallbacks);
+    __syncthreads();
+
+    const T out_prefix = s_prefix + warp_prefix;
+    if (full)
+        t.template store_full<INCLUSIVE>(p.out, vbase, out_prefix);
+    else
+        t.template store_partial<INCLUSIVE>(p.out, vbase, p.n, out_prefix);
+}
+
+}  // namespace gps

@@ -1,0 +1,209 @@
+// gps_launch.cuh -- host-side launch helpers shared by the library (gps_api.cu) and
+// the tuning harness (tools/gps_tune.cu): scratch bookkeeping (epoch tags, claim
+// counter base), grid arithmetic and the <<< >>> calls, templated on the kernel
+// configuration.  Mirrors the private Dispatch* methods of the reference dispatchers
+// (ChainedScanDecoupledLookbackDispatcher.cuh:166-195, ReduceThenScanDispatcher.cuh:158-187)
+// minus the per-launch cudaMemsets.
+#pragma once
+#include <algorithm>
+
+#include "gps_csdl_reg.cuh"
+#include "gps_csdl_tma.cuh"
+#include "gps_rts.cuh"
+
+namespace gps {
+
+inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// device scratch of one context + the host-side counters that replace memsets
+struct Scratch {
+    uint64_t* desc = nullptr;     // tile descriptors (zero-initialised once)
+    uint32_t desc_tiles = 0;
+    uint32_t* counter = nullptr;  // tile-claim counter, never reset
+    uint32_t* status = nullptr;   // watchdog word
+    void* partials = nullptr;     // kMaxParts key-sized values
+    uint32_t counter_base = 0;
+    uint32_t epoch = 0;
+    int sm_count = 148;
+    uint32_t poll_sleep_ns = 0;
+    uint32_t flags = 0;
+};
+
+// everything a scan launch needs besides the buffers
+struct CarrySpec {
+    uint32_t carry_bits = 0;
+    const uint64_t* slots = nullptr;
+    uint32_t n_slots = 0, n_carry = 0, tag = 0;
+    void* total_out = nullptr;
+    PublishList publish{};
+};
+
+inline uint32_t next_epoch(Scratch& s, cudaStream_t st)
+{
+    if (++s.epoch >= (1u << 30)) {  // wrap: epoch values would alias -> clear once
+        cudaMemsetAsync(s.desc, 0, (size_t)s.desc_tiles * sizeof(uint64_t), st);
+        s.epoch = 1;
+    }
+    return s.epoch;
+}
+
+inline ScanParams make_scan_params(Scratch& s, const void* in, void* out, uint64_t n,
+                                   uint32_t tile_keys, const CarrySpec& cs, cudaStream_t st)
+{
+    ScanParams p{};
+    p.in = in;
+    p.out = out;
+    p.n = n;
+    p.desc = s.desc;
+    p.counter = s.counter;
+    p.counter_base = s.counter_base;
+    p.epoch = next_epoch(s, st);
+    p.num_tiles = (uint32_t)div_up(n, tile_keys);
+    p.carry_bits = cs.carry_bits;
+    p.slots = cs.slots;
+    p.n_slots = cs.n_slots;
+    p.n_carry = cs.n_carry;
+    p.slot_tag = cs.tag;
+    p.total_out = cs.total_out;
+    p.publish = cs.publish;
+    p.status = s.status;
+    p.poll_sleep_ns = s.poll_sleep_ns;
+    p.flags = s.flags;
+    return p;
+}
+
+// ---- n == 0: only the carry travels ------------------------------------------------
+template <typename T>
+__global__ void carry_only_kernel(const __grid_constant__ ScanParams p)
+{
+    const T c = acquire_carry<T>(p, lane_id());
+    if (threadIdx.x == 0) write_total<T>(p, c);
+}
+
+template <typename T>
+cudaError_t launch_carry_only(Scratch& s, const CarrySpec& cs, cudaStream_t st)
+{
+    ScanParams p = make_scan_params(s, nullptr, nullptr, 0, 4096, cs, st);
+    carry_only_kernel<T><<<1, 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- CSDL register path --------------------------------------------------------------
+template <typename T, int NT, int V, bool INCL>
+cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                            cudaStream_t st)
+{
+    using Tile = RegTile<T, NT, V>;
+    ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
+    csdl_reg_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p);
+    s.counter_base += p.num_tiles;  // one claim per CTA
+    return cudaGetLastError();
+}
+
+// ---- CSDL TMA path -------------------------------------------------------------------
+// ctas_per_sm: in/out cache (0 = query occupancy and opt in to the dynamic smem size);
+// max_ctas_per_sm: 0 = as many as fit
+template <typename T, int NT, int STAGES, bool INCL>
+cudaError_t launch_csdl_tma(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                            int& ctas_per_sm, int max_ctas_per_sm, cudaStream_t st)
+{
+    using Cfg = TmaCfg<NT, STAGES>;
+    auto kern = csdl_tma_kernel<T, NT, STAGES, INCL>;
+    if (ctas_per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::RING_BYTES);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, Cfg::RING_BYTES);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        ctas_per_sm = occ;
+    }
+    int occ = ctas_per_sm;
+    if (max_ctas_per_sm > 0) occ = std::min(occ, max_ctas_per_sm);
+    ScanParams p = make_scan_params(s, in, out, n, Cfg::TILE_KEYS, cs, st);
+    const uint32_t grid = std::min<uint32_t>(p.num_tiles, (uint32_t)(occ * s.sm_count));
+    kern<<<grid, NT, Cfg::RING_BYTES, st>>>(p);
+    // every CTA claims STAGES-1 tiles up front and one more per tile it processes
+    s.counter_base += grid * (STAGES - 1) + p.num_tiles;
+    return cudaGetLastError();
+}
+
+// ---- CSDL + Decoupled Fallback ---------------------------------------------------------
+template <typename T, int NT, int V, bool INCL>
+cudaError_t launch_csdl_fallback(Scratch& s, const void* in, void* out, uint64_t n,
+                                 const CarrySpec& cs, const FallbackParams& f, cudaStream_t st)
+{
+    using Tile = RegTile<T, NT, V>;
+    ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
+    csdl_fallback_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p, f);
+    s.counter_base += p.num_tiles;
+    return cudaGetLastError();
+}
+
+// ---- RTS -----------------------------------------------------------------------------
+// ctas_per_sm: in/out cache of the propagate kernel's occupancy (0 = query)
+template <typename T, int NT, int V>
+cudaError_t rts_geometry(Scratch& s, uint64_t n, int& ctas_per_sm, RtsParams& p)
+{
+    using Tile = RegTile<T, NT, V>;
+    if (ctas_per_sm == 0) {
+        int occ = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, rts_propagate_kernel<T, NT, V, true>, NT, 0);
+        if (e != cudaSuccess) return e;
+        ctas_per_sm = std::max(1, occ);
+    }
+    p.n = n;
+    p.num_tiles = (uint32_t)div_up(n, Tile::TILE_KEYS);
+    p.partials = s.partials;
+    p.status = s.status;
+    if (p.num_tiles == 0) {
+        p.tiles_per_part = p.num_parts = 0;
+        return cudaSuccess;
+    }
+    uint32_t parts = std::min<uint32_t>((uint32_t)(ctas_per_sm * s.sm_count), kMaxParts);
+    parts = std::max<uint32_t>(1u, std::min(parts, p.num_tiles));
+    p.tiles_per_part = (uint32_t)div_up(p.num_tiles, parts);
+    p.num_parts = (uint32_t)div_up(p.num_tiles, p.tiles_per_part);
+    return cudaSuccess;
+}
+
+template <typename T, int NT, int V, bool INCL>
+cudaError_t launch_rts(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                       int& ctas_per_sm, cudaStream_t st)
+{
+    RtsParams p{};
+    cudaError_t e = rts_geometry<T, NT, V>(s, n, ctas_per_sm, p);
+    if (e != cudaSuccess) return e;
+    p.in = in;
+    p.out = out;
+    p.carry_bits = cs.carry_bits;
+    p.slots = cs.slots;
+    p.n_slots = cs.n_slots;
+    p.n_carry = cs.n_carry;
+    p.slot_tag = cs.tag;
+    p.total_out = cs.total_out;
+    p.publish = cs.publish;
+    rts_reduce_kernel<T, NT, V><<<p.num_parts, NT, 0, st>>>(p);
+    rts_spine_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
+    rts_propagate_kernel<T, NT, V, INCL><<<p.num_parts, NT, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename T, int NT, int V>
+cudaError_t launch_reduce(Scratch& s, const void* in, uint64_t n, void* total_out,
+                          const PublishList& pl, int& ctas_per_sm, cudaStream_t st)
+{
+    RtsParams p{};
+    cudaError_t e = rts_geometry<T, NT, V>(s, n, ctas_per_sm, p);
+    if (e != cudaSuccess) return e;
+    p.in = in;
+    p.total_out = total_out;
+    p.publish = pl;
+    if (p.num_parts) rts_reduce_kernel<T, NT, V><<<p.num_parts, NT, 0, st>>>(p);
+    rts_fold_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace gps

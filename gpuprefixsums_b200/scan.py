@@ -1,0 +1,187 @@
+"""Host-side Python surface over the C ABI: a context object working on torch tensors.
+
+PyTorch is plumbing here (device memory, streams); every scan runs in
+``lib/libgps_b200.so``.  The C++ dispatcher classes with the reference's names live in
+``host/*.hpp``; ``dispatchers.py`` mirrors them for the Python tests.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _capi as capi
+from ._capi import check, lib
+
+_DTYPES = {torch.int32: capi.U32, torch.uint32: capi.U32, torch.float32: capi.F32}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype}: uint32/int32 (bit pattern) or float32") from None
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream], device: torch.device) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream(device)
+    return s.cuda_stream
+
+
+def _algo(algo) -> int:
+    return capi.ALGO_NAMES[algo] if isinstance(algo, str) else int(algo)
+
+
+def _kind(exclusive: bool) -> int:
+    return capi.EXCLUSIVE if exclusive else capi.INCLUSIVE
+
+
+def carry_bits(value, dtype: torch.dtype) -> int:
+    """uint32 value, or the bit pattern of a float32."""
+    if dtype == torch.float32:
+        return int(torch.tensor([float(value)], dtype=torch.float32).view(torch.int32).item()) & 0xFFFFFFFF
+    return int(value) & 0xFFFFFFFF
+
+
+class PrefixSum:
+    """One ``gps_ctx``: scratch for scans of up to ``max_n`` keys on ``device``.
+
+    Use one instance per stream; calls are asynchronous on the current torch stream.
+    """
+
+    def __init__(self, max_n: int, device: int | torch.device | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("gpuprefixsums_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.max_n = int(max_n)
+        self._ctx = C.c_void_p()
+        check(lib.gps_create(C.byref(self._ctx), self.device.index, self.max_n))
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            lib.gps_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- options -------------------------------------------------------------------
+    def set_option(self, key: str, value: int) -> None:
+        check(lib.gps_set_option(self._ctx, key.encode(), int(value)))
+
+    def check(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Synchronise and raise if a look-back watchdog tripped since the last check."""
+        check(lib.gps_check(self._ctx, _stream_ptr(stream, self.device)))
+
+    # ---- scans ---------------------------------------------------------------------
+    def _prep(self, inp: torch.Tensor, out: Optional[torch.Tensor]):
+        if not inp.is_cuda or inp.device != self.device:
+            raise ValueError(f"input must live on {self.device}")
+        if not inp.is_contiguous():
+            raise ValueError("input must be contiguous")
+        if out is None:
+            out = torch.empty_like(inp)
+        if out.dtype != inp.dtype or out.numel() != inp.numel() or not out.is_contiguous() or out.device != inp.device:
+            raise ValueError("output must match the input's dtype, size and device and be contiguous")
+        return inp, out
+
+    def scan(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, algo="csdl",
+             exclusive: bool = False, carry=0, total_out: Optional[torch.Tensor] = None,
+             stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        inp, out = self._prep(inp, out)
+        check(lib.gps_scan(self._ctx, _algo(algo), _kind(exclusive), _dtype_code(inp), inp.data_ptr(),
+                           out.data_ptr(), inp.numel(), carry_bits(carry, inp.dtype),
+                           total_out.data_ptr() if total_out is not None else None,
+                           _stream_ptr(stream, self.device)))
+        return out
+
+    def scan_carry_slots(self, inp: torch.Tensor, out: Optional[torch.Tensor], slots_ptr: int, n_slots: int,
+                         n_carry: int, tag: int, *, algo="csdl", exclusive: bool = False,
+                         total_out: Optional[torch.Tensor] = None,
+                         stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        inp, out = self._prep(inp, out)
+        check(lib.gps_scan_carry_slots(self._ctx, _algo(algo), _kind(exclusive), _dtype_code(inp),
+                                       inp.data_ptr(), out.data_ptr(), inp.numel(), slots_ptr, n_slots,
+                                       n_carry, tag & 0xFFFFFFFF,
+                                       total_out.data_ptr() if total_out is not None else None,
+                                       _stream_ptr(stream, self.device)))
+        return out
+
+    def reduce(self, inp: torch.Tensor, total_out: Optional[torch.Tensor] = None,
+               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        if total_out is None:
+            total_out = torch.empty(1, dtype=inp.dtype, device=inp.device)
+        check(lib.gps_reduce(self._ctx, _dtype_code(inp), inp.data_ptr(), inp.numel(), total_out.data_ptr(),
+                             _stream_ptr(stream, self.device)))
+        return total_out
+
+    def reduce_publish(self, inp: torch.Tensor, dst_slot_ptrs: list[int], tag: int,
+                       total_out: Optional[torch.Tensor] = None,
+                       stream: Optional[torch.cuda.Stream] = None) -> None:
+        arr = (C.c_void_p * max(1, len(dst_slot_ptrs)))(*dst_slot_ptrs)
+        check(lib.gps_reduce_publish(self._ctx, _dtype_code(inp), inp.data_ptr(), inp.numel(), arr,
+                                     len(dst_slot_ptrs), tag & 0xFFFFFFFF,
+                                     total_out.data_ptr() if total_out is not None else None,
+                                     _stream_ptr(stream, self.device)))
+
+    def scan_emulated_deadlock(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *,
+                               exclusive: bool = False, stall_mask: int = 7, max_spin: int = 4,
+                               stats: Optional[torch.Tensor] = None,
+                               stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        inp, out = self._prep(inp, out)
+        check(lib.gps_scan_emulated_deadlock(self._ctx, _kind(exclusive), _dtype_code(inp), inp.data_ptr(),
+                                             out.data_ptr(), inp.numel(), stall_mask & 0xFFFFFFFF, max_spin,
+                                             stats.data_ptr() if stats is not None else None,
+                                             _stream_ptr(stream, self.device)))
+        return out
+
+    def scan_host(self, h_in: torch.Tensor, h_out: Optional[torch.Tensor] = None, *, algo="csdl",
+                  exclusive: bool = False, carry=0) -> torch.Tensor:
+        """Host buffers in, host buffers out (pinned recommended); synchronous."""
+        if h_in.is_cuda or not h_in.is_contiguous():
+            raise ValueError("scan_host takes contiguous CPU tensors")
+        if h_out is None:
+            h_out = torch.empty_like(h_in, pin_memory=h_in.is_pinned())
+        check(lib.gps_scan_host(self._ctx, _algo(algo), _kind(exclusive), _dtype_code(h_in), h_in.data_ptr(),
+                                h_out.data_ptr(), h_in.numel(), carry_bits(carry, h_in.dtype), None))
+        return h_out
+
+
+# ---- harness helpers (UtilityKernels.cuh:15-38 equivalents) --------------------------
+def init_ones(t: torch.Tensor) -> None:
+    check(lib.gps_init_ones(t.data_ptr(), t.numel(), _dtype_code(t), _stream_ptr(None, t.device)))
+
+
+def init_random(t: torch.Tensor, seed: int, mask: int = 0xFFFFFFFF, first_index: int = 0) -> None:
+    check(lib.gps_init_random(t.data_ptr(), t.numel(), _dtype_code(t), seed, mask, first_index,
+                              _stream_ptr(None, t.device)))
+
+
+def validate_ones(t: torch.Tensor, exclusive: bool, first_value: int = 0) -> int:
+    torch.cuda.current_stream(t.device).synchronize()
+    errs = C.c_uint64(0)
+    check(lib.gps_validate_ones(t.data_ptr(), t.numel(), _kind(exclusive), first_value, C.byref(errs)))
+    return errs.value
+
+
+def compare_u32(a: torch.Tensor, b: torch.Tensor) -> tuple[int, int]:
+    torch.cuda.current_stream(a.device).synchronize()
+    errs, first = C.c_uint64(0), C.c_uint64(0)
+    check(lib.gps_compare_u32(a.data_ptr(), b.data_ptr(), a.numel(), C.byref(errs), C.byref(first)))
+    return errs.value, first.value
+
+
+def cub_scan(inp: torch.Tensor, out: torch.Tensor, exclusive: bool = False) -> torch.Tensor:
+    """cub::DeviceScan baseline (libgps_cub.so) on the current stream."""
+    rc = capi.cub_lib().gps_cub_scan(int(exclusive), _dtype_code(inp), inp.data_ptr(), out.data_ptr(),
+                                     inp.numel(), _stream_ptr(None, inp.device))
+    if rc != 0:
+        raise RuntimeError("cub::DeviceScan failed")
+    return out

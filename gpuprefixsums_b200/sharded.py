@@ -1,0 +1,141 @@
+"""Sharded scan across GPUs, one process per GPU (``torch.distributed``).
+
+New capability (the reference is single-GPU).  Rank g holds the
+contiguous keys [g*n/G, (g+1)*n/G).  Per call:
+
+  pass 1  ``gps_reduce_publish``    reduce the slice (4 B/key) and publish the tagged
+                                    total to every rank's carry slots
+  pass 2  ``gps_scan_carry_slots``  scan the slice (8 B/key); tile 0 (CSDL) or the spine
+                                    (RTS) polls all G slots and seeds itself with the sum
+                                    of the first `rank` totals -- the carry is applied in
+                                    the same pass, no extra sweep over HBM
+
+Carry exchange:
+  * ``"p2p"``  the fold kernel stores {total|tag} straight into every peer's slot array
+               over NVLink (peer memory mapped once with CUDA IPC); no host
+               synchronisation and no collective call per step;
+  * ``"nccl"`` a G-element ``all_gather`` of the tagged word (also used on the gloo/CPU
+               test path for the host logic).
+Slots are double-buffered by tag parity; since every rank polls ALL G slots, no rank can
+finish step k before every rank has published step k, so a slot is never overwritten
+while a peer still waits for its previous value.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+MAX_RANKS = 16  # gps::kMaxPublish
+
+
+def carry_from_totals(totals_bits: list[int], rank: int, dtype: torch.dtype = torch.int32):
+    """Host restatement of what tile 0 computes from the slots: the exclusive carry of
+    `rank` (uint32 wraparound, or float32 summed in slot order).  Used by the CPU
+    (gloo) tests of the multi-rank logic and by the host-staged debug mode."""
+    if dtype == torch.float32:
+        vals = torch.tensor(totals_bits[:rank], dtype=torch.int64).to(torch.int32).view(torch.float32)
+        return float(vals.sum(dtype=torch.float32)) if rank else 0.0
+    acc = 0
+    for v in totals_bits[:rank]:
+        acc = (acc + (v & 0xFFFFFFFF)) & 0xFFFFFFFF
+    return acc
+
+
+def pack_slot(value_bits: int, tag: int) -> int:
+    return ((tag & 0xFFFFFFFF) << 32) | (value_bits & 0xFFFFFFFF)
+
+
+def unpack_slot(word: int) -> tuple[int, int]:
+    word &= 0xFFFFFFFFFFFFFFFF
+    return word & 0xFFFFFFFF, word >> 32
+
+
+def slice_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous slice of rank: sizes differ by at most one 4-key vector; every slice
+    start is a multiple of 4 keys so device buffers stay 16-byte aligned."""
+    vec = (n_total + 3) // 4
+    base, rem = divmod(vec, world)
+    start_vec = rank * base + min(rank, rem)
+    end_vec = start_vec + base + (1 if rank < rem else 0)
+    return min(start_vec * 4, n_total), min(end_vec * 4, n_total)
+
+
+class ShardedScan:
+    """Collective sharded scan; construct on every rank of ``group``."""
+
+    def __init__(self, max_n_local: int, mode: str = "p2p", group=None):
+        from . import _capi as capi
+        from .scan import PrefixSum
+
+        if mode not in ("p2p", "nccl"):
+            raise ValueError("mode must be 'p2p' or 'nccl'")
+        self.capi = capi
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > MAX_RANKS:
+            raise ValueError(f"at most {MAX_RANKS} ranks")
+        self.mode = mode
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.ps = PrefixSum(max_n_local, self.device)
+        self.tag = 0
+        # 2 parities x MAX_RANKS tagged 64-bit slots, allocated with cudaMalloc so it can
+        # be exported over CUDA IPC
+        self._slots = C.c_void_p()
+        capi.check(capi.lib.gps_malloc(C.byref(self._slots), 2 * MAX_RANKS * 8))
+        capi.check(capi.lib.gps_memset(self._slots, 0, 2 * MAX_RANKS * 8, None))
+        capi.check(capi.lib.gps_device_sync())
+        self._peer_slots: list[int] = [0] * self.world
+        self._opened: list[int] = []
+        self._word = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._gathered = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        if mode == "p2p":
+            self._exchange_ipc()
+
+    def _exchange_ipc(self) -> None:
+        capi = self.capi
+        handle = C.create_string_buffer(capi.IPC_HANDLE_BYTES)
+        capi.check(capi.lib.gps_ipc_export(self._slots, handle))
+        every: list = [None] * self.world
+        dist.all_gather_object(every, bytes(handle.raw), group=self.group)  # works on nccl and gloo
+        for r in range(self.world):
+            if r == self.rank:
+                self._peer_slots[r] = self._slots.value
+                continue
+            ptr = C.c_void_p()
+            capi.check(capi.lib.gps_ipc_open(every[r], C.byref(ptr)))
+            self._peer_slots[r] = ptr.value
+            self._opened.append(ptr.value)
+        dist.barrier(group=self.group)
+
+    def close(self) -> None:
+        capi = self.capi
+        for p in self._opened:
+            capi.lib.gps_ipc_close(p)
+        self._opened = []
+        if self._slots.value:
+            capi.lib.gps_free(self._slots)
+            self._slots = C.c_void_p()
+        self.ps.close()
+
+    def scan(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, algo="csdl",
+             exclusive: bool = False) -> torch.Tensor:
+        """Scan this rank's slice in the context of the global array."""
+        self.tag = (self.tag % 0xFFFFFFFE) + 1  # 1 .. 2^32-2, never 0
+        tag, par = self.tag, self.tag & 1
+        base = self._slots.value + par * MAX_RANKS * 8
+        if self.mode == "p2p":
+            dst = [self._peer_slots[r] + (par * MAX_RANKS + self.rank) * 8 for r in range(self.world)]
+            self.ps.reduce_publish(inp, dst, tag)
+        else:
+            # publish into my own staging word, all_gather the words, then copy them into
+            # the slot array the scan kernel polls
+            self.ps.reduce_publish(inp, [self._word.data_ptr()], tag)
+            dist.all_gather_into_tensor(self._gathered, self._word, group=self.group)
+            self.capi.check(self.capi.lib.gps_memcpy_d2d(base, self._gathered.data_ptr(), self.world * 8,
+                                                         torch.cuda.current_stream().cuda_stream))
+        return self.ps.scan_carry_slots(inp, out, base, self.world, self.rank, tag, algo=algo,
+                                        exclusive=exclusive)

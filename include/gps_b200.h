@@ -1,0 +1,197 @@
+/*
+ * gps_b200.h -- C ABI of the B200-native device-wide prefix-sum library
+ * (libgps_b200.so).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * The reference (b0nes164/GPUPrefixSums, CUDA port) has no FFI layer: its operator
+ * surface is four header-defined C++ dispatcher classes that launch kernels with
+ * <<< >>> directly.  Every entry point below replaces one of those private launch /
+ * harness methods; the C++ classes with the reference's names live in
+ * gpuprefixsums_b200/host/*.hpp and call only this ABI.  File:line citations are
+ * relative to /root/reference/GPUPrefixSumsCUDA/.
+ *
+ * Conventions
+ *   - all data pointers named d_* are DEVICE pointers owned by the caller and must be
+ *     16-byte aligned; h_* are host pointers.  n counts keys (4 bytes each), 64-bit.
+ *   - d_out may equal d_in (the reference scans in place) but must not partially
+ *     overlap it.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     Calls are asynchronous on that stream unless stated otherwise.
+ *   - a gps_ctx owns the scratch (tile descriptors, tile counter, partials, status
+ *     word) for one device; use one ctx per host thread / stream.  Scratch is
+ *     epoch-tagged: no per-launch memset (the reference clears its descriptors inside
+ *     the timed region, ChainedScanDecoupledLookbackDispatcher.cuh:172-175).
+ *   - every function returns GPS_OK (0) or a negative gps_status; gps_last_error()
+ *     gives a thread-local message.  There is NO CPU fallback: without a usable CUDA
+ *     device every compute entry point fails with GPS_ERR_CUDA.
+ */
+#ifndef GPS_B200_H_
+#define GPS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPS_ABI_VERSION 1
+
+typedef struct gps_ctx gps_ctx;
+typedef struct gps_shard_group gps_shard_group;
+
+enum gps_status {
+    GPS_OK = 0,
+    GPS_ERR_INVALID = -1,   /* bad enum / null pointer / n > ctx capacity            */
+    GPS_ERR_ALIGNMENT = -2, /* device pointer not 16-byte aligned                    */
+    GPS_ERR_CUDA = -3,      /* a CUDA runtime call failed (message in last_error)    */
+    GPS_ERR_WATCHDOG = -4,  /* a look-back spin exceeded its poll budget (reported by */
+                            /* gps_check; the kernel bails out instead of hanging)   */
+    GPS_ERR_MISMATCH = -5,  /* validation helper found wrong results                 */
+    GPS_ERR_UNSUPPORTED = -6
+};
+
+enum gps_algo {
+    GPS_ALGO_CSDL = 0,          /* Chained Scan w/ Decoupled Lookback, tuned default  */
+    GPS_ALGO_CSDL_REG = 1,      /*   register path: 128-bit coalesced LDG/STG          */
+    GPS_ALGO_CSDL_TMA = 2,      /*   TMA bulk copies into a shared-memory ring        */
+    GPS_ALGO_CSDL_FALLBACK = 3, /* CSDL + Decoupled Fallback (no emulated stalls)     */
+    GPS_ALGO_RTS = 4            /* three-kernel Reduce-then-Scan                      */
+};
+enum gps_kind { GPS_INCLUSIVE = 0, GPS_EXCLUSIVE = 1 };
+enum gps_dtype { GPS_U32 = 0, GPS_F32 = 1 };
+
+/* ---- library / device ------------------------------------------------------- */
+int gps_abi_version(void);
+const char* gps_last_error(void);
+int gps_device_count(int* count);
+/* name (<=255 chars), SM count, L2 bytes, total memory of `device` */
+int gps_device_info(int device, char* name, int* sm_count, uint64_t* l2_bytes,
+                    uint64_t* mem_bytes);
+
+/* ---- context: replaces the dispatcher constructors/destructors --------------
+ * ChainedScanDecoupledLookbackDispatcher.cuh:28-34,158-163 (m_index,
+ * m_threadBlockReduction), ReduceThenScanDispatcher.cuh:27-33,152-156.  Unlike the
+ * reference the ctx does not own the data buffer. */
+int gps_create(gps_ctx** ctx, int device, uint64_t max_n);
+void gps_destroy(gps_ctx* ctx);
+/* Synchronises `stream` and reports GPS_ERR_WATCHDOG if any launch since the last
+ * check tripped the look-back watchdog (then clears the flag). */
+int gps_check(gps_ctx* ctx, void* stream);
+/* Tuning knobs (key/value); unknown keys return GPS_ERR_INVALID.  Keys:
+ *   "csdl_variant"  0 = auto, 1 = register path, 2 = TMA ring
+ *   "poll_sleep_ns" nanosleep between unsuccessful descriptor polls (default 0)
+ *   "host_chunk_keys" chunk size of gps_scan_host (default 2^24; before first use) */
+int gps_set_option(gps_ctx* ctx, const char* key, int64_t value);
+
+/* ---- scans -------------------------------------------------------------------
+ * gps_scan replaces DispatchKernelsInclusive / DispatchKernelsExclusive of
+ *   ChainedScanDecoupledLookbackDispatcher.cuh:177-195 (algo CSDL*) and
+ *   ReduceThenScanDispatcher.cuh:165-187               (algo RTS).
+ * carry_in_bits: value (uint32, or float32 bit pattern) added to every output -- the
+ * prefix seeded into tile 0; 0 reproduces the reference.  d_total_out (nullable)
+ * receives carry + sum of all n keys (one key-sized value).  n == 0 is a no-op that
+ * still writes d_total_out. */
+int gps_scan(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void* d_out,
+             uint64_t n, uint32_t carry_in_bits, void* d_total_out, void* stream);
+
+/* Same, with the carry read ON THE DEVICE by tile 0 from 64-bit carry slots
+ * {value bits : 32 | tag : 32} (low word = value).  Tile 0 polls all `n_slots` slots
+ * with ld.acquire.sys until their tag equals `tag`, sums the values of the first
+ * `n_carry` (<= n_slots) of them and seeds the look-back chain -- the multi-GPU carry
+ * "folded into the look-back" (slots may be written by peer GPUs over NVLink, see
+ * gps_reduce_publish).  Polling more slots than are summed (all G ranks, not only the
+ * upstream ones) is the flow control that lets the slots be reused every other call.
+ * New capability; the reference is single-GPU. */
+int gps_scan_carry_slots(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in,
+                         void* d_out, uint64_t n, const uint64_t* d_slots, uint32_t n_slots,
+                         uint32_t n_carry, uint32_t tag, void* d_total_out, void* stream);
+
+/* Sum of n keys -> *d_total_out (key-sized).  The Reduce pass of
+ * ReduceThenScan.cuh:15-53 followed by a one-block fold of the partials. */
+int gps_reduce(gps_ctx* ctx, int dtype, const void* d_in, uint64_t n, void* d_total_out,
+               void* stream);
+
+/* Reduce + publish: writes {total bits | tag<<32} with st.release.sys to each of the
+ * `n_dst` device addresses in h_dst_slots (host array of device pointers; may point
+ * into peer-GPU memory mapped with gps_ipc_open / peer access). */
+int gps_reduce_publish(gps_ctx* ctx, int dtype, const void* d_in, uint64_t n,
+                       uint64_t* const* h_dst_slots, uint32_t n_dst, uint32_t tag,
+                       void* d_total_out, void* stream);
+
+/* Emulated-deadlock harness kernel: replaces
+ * EmulatedDeadlockingDispatcher.cuh:152-158 -> EmulatedDeadlocking.cuh:26-168.
+ * Tiles with (tile & stall_mask) == 0 stall until a successor's Decoupled Fallback
+ * has published their aggregate (atomic CAS); the LAST tile never stalls (the
+ * reference hangs there).  stall_mask = 0xFFFFFFFF disables stalling
+ * (pure Decoupled Fallback).  max_spin = unsuccessful polls before a fallback (the
+ * reference's MAX_SPIN_COUNT 4, EmulatedDeadlocking.cuh:15).  d_stats (nullable)
+ * accumulates {total spins, fallbacks initiated, successful insertions, lookbacks}
+ * (GPUPrefixSumsWebGPUapis/SharedShaders/TestVariants/csdldf_stats.wgsl). */
+int gps_scan_emulated_deadlock(gps_ctx* ctx, int kind, int dtype, const void* d_in,
+                               void* d_out, uint64_t n, uint32_t stall_mask,
+                               uint32_t max_spin, uint32_t* d_stats, void* stream);
+
+/* The reference-facing call with HOST buffers: pipelined H2D -> scan -> D2H in
+ * chunks on internal streams, chunk totals chained on the device.  Synchronous.
+ * h_in / h_out should be pinned for full PCIe bandwidth (pageable works). */
+int gps_scan_host(gps_ctx* ctx, int algo, int kind, int dtype, const void* h_in,
+                  void* h_out, uint64_t n, uint32_t carry_in_bits, void* h_total_out);
+
+/* ---- harness kernels: UtilityKernels.cuh:15-38 -------------------------------- */
+int gps_init_ones(void* d, uint64_t n, int dtype, void* stream);               /* InitOne  */
+/* key(i) = hash(seed, first_index + i) & mask (uint32) or uniform [0,1) (float32);
+ * same generator as oracle_init_random_* so host and device agree */
+int gps_init_random(void* d, uint64_t n, int dtype, uint64_t seed, uint32_t mask,
+                    uint64_t first_index, void* stream);
+/* ValidateInclusive / ValidateExclusive: counts d[i] != first_value + i (+1 if
+ * inclusive) on uint32; synchronous, *h_errs receives the count */
+int gps_validate_ones(const void* d, uint64_t n, int kind, uint32_t first_value,
+                      uint64_t* h_errs);
+/* word-for-word compare of two device arrays (uint32), synchronous */
+int gps_compare_u32(const void* d_a, const void* d_b, uint64_t n, uint64_t* h_errs,
+                    uint64_t* h_first_bad);
+/* float32: counts |a-b| > rtol*|d_bound[i]| + atol (d_bound nullable -> |b|) */
+int gps_compare_f32(const void* d_a, const void* d_b, const void* d_bound, uint64_t n,
+                    float rtol, float atol, uint64_t* h_errs, float* h_max_abs_diff);
+
+/* ---- memory / stream / timing helpers so host code needs no CUDA headers ------ */
+int gps_set_device(int device);
+int gps_malloc(void** d_ptr, uint64_t bytes);
+int gps_free(void* d_ptr);
+int gps_malloc_host(void** h_ptr, uint64_t bytes); /* pinned */
+int gps_free_host(void* h_ptr);
+int gps_memcpy_h2d(void* d_dst, const void* h_src, uint64_t bytes, void* stream);
+int gps_memcpy_d2h(void* h_dst, const void* d_src, uint64_t bytes, void* stream);
+int gps_memcpy_d2d(void* d_dst, const void* d_src, uint64_t bytes, void* stream);
+int gps_memset(void* d, int byte, uint64_t bytes, void* stream);
+int gps_stream_sync(void* stream);
+int gps_device_sync(void);
+int gps_event_create(void** ev);
+int gps_event_destroy(void* ev);
+int gps_event_record(void* ev, void* stream);
+int gps_event_elapsed_ms(void* start, void* stop, float* ms); /* syncs on stop */
+
+/* ---- CUDA IPC for the cross-process NVLink carry (one process per GPU) -------- */
+#define GPS_IPC_HANDLE_BYTES 64
+int gps_ipc_export(void* d_ptr, unsigned char handle[GPS_IPC_HANDLE_BYTES]);
+int gps_ipc_open(const unsigned char handle[GPS_IPC_HANDLE_BYTES], void** d_ptr);
+int gps_ipc_close(void* d_ptr);
+
+/* ---- single-process sharded scan over several GPUs (C++ hosts) ---------------
+ * New capability.  GPU g holds keys [g*n/G, (g+1)*n/G) in
+ * d_in[g]/d_out[g].  Pass 1 reduces each slice and stores its total into every
+ * downstream GPU's carry slots over NVLink (peer access); pass 2 scans each slice
+ * with the carry folded into tile 0's look-back.  carry_mode: 0 = P2P stores,
+ * 1 = host-staged exchange (debug).  Synchronous.  h_ms (nullable) receives the
+ * max-over-GPUs device time. */
+int gps_sharded_create(gps_shard_group** grp, int n_gpus, const int* devices,
+                       uint64_t max_n_per_gpu);
+void gps_sharded_destroy(gps_shard_group* grp);
+int gps_sharded_scan(gps_shard_group* grp, int algo, int kind, int dtype,
+                     const void* const* d_in, void* const* d_out, const uint64_t* n_per_gpu,
+                     int carry_mode, float* h_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPS_B200_H_ */

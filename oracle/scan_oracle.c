@@ -1,0 +1,243 @@
+/*
+ * oracle/scan_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the reference's serial prefix-sum validation loops.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product path (gpuprefixsums_b200/) never does.
+ *
+ * What it restates (paths relative to /root/reference):
+ *   - inclusive serial scan: GPUPrefixSumsD3D12/Shaders/Utility.hlsl:99-111
+ *     (ValidateRandomInclusive: `sum += in[i]; expect out[i] == sum`) and
+ *     GPUPrefixSumsD3D12/Shaders/Survey.hlsl:49-54 (SerialInclusive).
+ *   - exclusive serial scan: Utility.hlsl:113-125 (ValidateRandomExclusive:
+ *     `expect out[i] == sum; sum += in[i]`) and Survey.hlsl:56-67.
+ *   - all-ones closed form: GPUPrefixSumsCUDA/UtilityKernels.cuh:22-38
+ *     (ValidateInclusive: scan[i] == i + 1, ValidateExclusive: scan[i] == i).
+ *   - random test input: Utility.hlsl:33-66 (InitRandom, Hybrid Tausworthe,
+ *     values & 1023, one RNG draw per "thread", 65536 threads, grid-stride).
+ * All uint32 arithmetic wraps mod 2^32, exactly as the reference's `uint`.
+ *
+ * The CUDA directory of the reference has no host (CPU) scan at all, and no
+ * float32 scan anywhere; the float32 oracle below is new: it accumulates in
+ * float64 (a float32 serial sum stagnates above 2^25).
+ *
+ * Parity pinning: tests/test_oracle.py checks this file against (a) the
+ * closed-form all-ones identity for the reference's own test sizes and (b)
+ * tests/golden/ref_cuda_*.npz, outputs of the reference's own CUDA kernels
+ * (oracle/_ref/libref_shim.so) run on a B200 (generator: oracle/gen_golden.py).
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- serial scans (Utility.hlsl:99-125, Survey.hlsl:49-67) ------------------- */
+
+/* returns the grand total (wraps mod 2^32); carry seeds the running sum */
+uint32_t oracle_scan_u32(const uint32_t *in, uint32_t *out, uint64_t n, int exclusive,
+                         uint32_t carry)
+{
+    uint32_t sum = carry;
+    if (exclusive) {
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t t = in[i];
+            out[i] = sum;
+            sum += t;
+        }
+    } else {
+        for (uint64_t i = 0; i < n; ++i) {
+            sum += in[i];
+            out[i] = sum;
+        }
+    }
+    return sum;
+}
+
+/* float32 input, float64 accumulation and float64 output (the comparison is done
+ * in float64 against rtol * running sum of |x|, written to out_abs if non-NULL) */
+double oracle_scan_f32_f64(const float *in, double *out, double *out_abs, uint64_t n,
+                           int exclusive, double carry)
+{
+    double sum = carry, asum = carry < 0 ? -carry : carry;
+    for (uint64_t i = 0; i < n; ++i) {
+        const double t = (double)in[i];
+        if (exclusive) {
+            out[i] = sum;
+            if (out_abs) out_abs[i] = asum;
+        }
+        sum += t;
+        asum += t < 0 ? -t : t;
+        if (!exclusive) {
+            out[i] = sum;
+            if (out_abs) out_abs[i] = asum;
+        }
+    }
+    return sum;
+}
+
+/* Checks a candidate float32 scan against the float64 serial scan of `in`:
+ * counts positions with |cand - ref| > rtol * (carry + sum_{j<=i}|x_j|) + atol.
+ * max_rel_out receives the largest observed |cand-ref| / max(sum|x|, tiny). */
+uint64_t oracle_check_f32(const float *in, const float *cand, uint64_t n, int exclusive,
+                          double carry, double rtol, double atol, double *max_rel_out)
+{
+    double sum = carry, asum = carry < 0 ? -carry : carry, max_rel = 0.0;
+    uint64_t errs = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const double t = (double)in[i];
+        if (!exclusive) {
+            sum += t;
+            asum += t < 0 ? -t : t;
+        }
+        double d = (double)cand[i] - sum;
+        if (d < 0) d = -d;
+        if (!(d <= rtol * asum + atol)) ++errs; /* also catches NaN */
+        const double rel = d / (asum > 1e-30 ? asum : 1e-30);
+        if (rel > max_rel) max_rel = rel;
+        if (exclusive) {
+            sum += t;
+            asum += t < 0 ? -t : t;
+        }
+    }
+    if (max_rel_out) *max_rel_out = max_rel;
+    return errs;
+}
+
+/* Word-for-word comparison of a candidate uint32 scan with the serial scan of
+ * `in` (Utility.hlsl:99-125 run as a checker).  Returns the mismatch count and the
+ * index of the first mismatch (or n). */
+uint64_t oracle_check_u32(const uint32_t *in, const uint32_t *cand, uint64_t n, int exclusive,
+                          uint32_t carry, uint64_t *first_bad)
+{
+    uint32_t sum = carry;
+    uint64_t errs = 0, first = n;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!exclusive) sum += in[i];
+        if (cand[i] != sum) {
+            if (!errs) first = i;
+            ++errs;
+        }
+        if (exclusive) sum += in[i];
+    }
+    if (first_bad) *first_bad = first;
+    return errs;
+}
+
+/* ---- all-ones closed form (UtilityKernels.cuh:22-38) ------------------------- */
+uint64_t oracle_validate_ones(const uint32_t *scan, uint64_t n, int exclusive)
+{
+    uint64_t errs = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        errs += scan[i] != (uint32_t)(exclusive ? i : i + 1);
+    return errs;
+}
+
+/* ---- reference random test input (Utility.hlsl:38-66) ------------------------ */
+/* One Hybrid-Tausworthe draw per dispatch thread id (65536 threads = 256 groups x
+ * 256), computed once outside the grid-stride loop exactly as the shader does, so
+ * element i receives the value of thread (i mod 65536). */
+void oracle_init_random_d3d12(uint32_t *out, uint64_t n, uint32_t seed)
+{
+    const uint32_t inc = 256u * 256u;
+    for (uint32_t id = 0; id < inc && id < n; ++id) {
+        uint32_t z1 = (id << 2) * seed;
+        uint32_t z2 = ((id << 2) + 1) * seed;
+        uint32_t z3 = ((id << 2) + 2) * seed;
+        uint32_t z4 = ((id << 2) + 3) * seed;
+        z1 = ((z1 & 4294967294U) << 12) ^ (((z1 << 13) ^ z1) >> 19);
+        z2 = ((z2 & 4294967288U) << 4) ^ (((z2 << 2) ^ z2) >> 25);
+        z3 = ((z3 & 4294967280U) << 17) ^ (((z3 << 3) ^ z3) >> 11);
+        z4 = z4 * 1664525u + 1013904223U;
+        const uint32_t t = (z1 ^ z2 ^ z3 ^ z4) & 1023u;
+        for (uint64_t i = id; i < n; i += inc) out[i] = t;
+    }
+}
+
+/* ---- seeded test input shared with the CUDA side ----------------------------- */
+/* Counter-based: key(i) = mix64(seed + i * golden) -- identical to
+ * gps::random_key() in gpuprefixsums_b200/csrc/gps_util_kernels.cuh, so host and
+ * device can generate the same array independently (needed for the 2^33 sharded
+ * case where the host never materialises the input). */
+static inline uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+uint32_t oracle_random_key(uint64_t seed, uint64_t i, uint32_t mask)
+{
+    return (uint32_t)(mix64(seed + (i + 1) * 0x9E3779B97F4A7C15ULL) >> 32) & mask;
+}
+
+void oracle_init_random_u32(uint32_t *out, uint64_t n, uint64_t seed, uint32_t mask,
+                            uint64_t first_index)
+{
+    for (uint64_t i = 0; i < n; ++i) out[i] = oracle_random_key(seed, first_index + i, mask);
+}
+
+/* float32 uniform in [0,1): top 24 bits of the same hash */
+void oracle_init_random_f32(float *out, uint64_t n, uint64_t seed, uint64_t first_index)
+{
+    for (uint64_t i = 0; i < n; ++i)
+        out[i] = (float)(oracle_random_key(seed, first_index + i, 0xFFFFFFFFu) >> 8) *
+                 (1.0f / 16777216.0f);
+}
+
+/* ---- multi-threaded host scan (CPU baseline "with all the host threads") ----- */
+/* Chunked two-pass restatement: each thread runs the serial loop above on a
+ * contiguous chunk (pass 1: chunk totals, pass 2: serial scan seeded with the sum of
+ * the preceding chunk totals).  Bit-identical to oracle_scan_u32 for uint32. */
+typedef struct {
+    const uint32_t *in;
+    uint32_t *out;
+    uint64_t begin, end;
+    int exclusive;
+    uint32_t total, carry;
+} chunk_job;
+
+static void *chunk_reduce(void *arg)
+{
+    chunk_job *j = (chunk_job *)arg;
+    uint32_t s = 0;
+    for (uint64_t i = j->begin; i < j->end; ++i) s += j->in[i];
+    j->total = s;
+    return NULL;
+}
+
+static void *chunk_scan(void *arg)
+{
+    chunk_job *j = (chunk_job *)arg;
+    oracle_scan_u32(j->in + j->begin, j->out + j->begin, j->end - j->begin, j->exclusive,
+                    j->carry);
+    return NULL;
+}
+
+uint32_t oracle_scan_u32_mt(const uint32_t *in, uint32_t *out, uint64_t n, int exclusive,
+                            uint32_t carry, int threads)
+{
+    if (threads <= 1 || n < (uint64_t)threads * 4096)
+        return oracle_scan_u32(in, out, n, exclusive, carry);
+    chunk_job *jobs = (chunk_job *)calloc((size_t)threads, sizeof(chunk_job));
+    pthread_t *tids = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    const uint64_t per = (n + (uint64_t)threads - 1) / (uint64_t)threads;
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].in = in;
+        jobs[t].out = out;
+        jobs[t].begin = per * (uint64_t)t < n ? per * (uint64_t)t : n;
+        jobs[t].end = per * (uint64_t)(t + 1) < n ? per * (uint64_t)(t + 1) : n;
+        jobs[t].exclusive = exclusive;
+    }
+    for (int t = 0; t < threads; ++t) pthread_create(&tids[t], NULL, chunk_reduce, &jobs[t]);
+    for (int t = 0; t < threads; ++t) pthread_join(tids[t], NULL);
+    uint32_t run = carry;
+    for (int t = 0; t < threads; ++t) {
+        jobs[t].carry = run;
+        run += jobs[t].total;
+    }
+    for (int t = 0; t < threads; ++t) pthread_create(&tids[t], NULL, chunk_scan, &jobs[t]);
+    for (int t = 0; t < threads; ++t) pthread_join(tids[t], NULL);
+    free(jobs);
+    free(tids);
+    return run;
+}

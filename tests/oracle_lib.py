@@ -1,0 +1,137 @@
+"""Loader for the CPU oracle (oracle/scan_oracle.c) and the reference CUDA shim.
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs import this.  The oracle is compiled on demand with gcc (seconds)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "liboracle_scan.so")
+REF_SHIM_SO = os.path.join(ORACLE_DIR, "_ref", "libref_shim.so")
+
+_u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(ORACLE_DIR, "scan_oracle.c")
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
+    return ORACLE_SO
+
+
+class Oracle:
+    def __init__(self, lib: C.CDLL):
+        self.lib = lib
+        lib.oracle_scan_u32.restype = C.c_uint32
+        lib.oracle_scan_u32.argtypes = [_u32p, _u32p, C.c_uint64, C.c_int, C.c_uint32]
+        lib.oracle_scan_u32_mt.restype = C.c_uint32
+        lib.oracle_scan_u32_mt.argtypes = [_u32p, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.c_int]
+        lib.oracle_scan_f32_f64.restype = C.c_double
+        lib.oracle_scan_f32_f64.argtypes = [_f32p, _f64p, C.c_void_p, C.c_uint64, C.c_int, C.c_double]
+        lib.oracle_check_f32.restype = C.c_uint64
+        lib.oracle_check_f32.argtypes = [_f32p, _f32p, C.c_uint64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                         C.POINTER(C.c_double)]
+        lib.oracle_check_u32.restype = C.c_uint64
+        lib.oracle_check_u32.argtypes = [_u32p, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(C.c_uint64)]
+        lib.oracle_validate_ones.restype = C.c_uint64
+        lib.oracle_validate_ones.argtypes = [_u32p, C.c_uint64, C.c_int]
+        lib.oracle_init_random_d3d12.restype = None
+        lib.oracle_init_random_d3d12.argtypes = [_u32p, C.c_uint64, C.c_uint32]
+        lib.oracle_init_random_u32.restype = None
+        lib.oracle_init_random_u32.argtypes = [_u32p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64]
+        lib.oracle_init_random_f32.restype = None
+        lib.oracle_init_random_f32.argtypes = [_f32p, C.c_uint64, C.c_uint64, C.c_uint64]
+
+    # --- scans -------------------------------------------------------------------
+    def scan_u32(self, x: np.ndarray, exclusive: bool = False, carry: int = 0):
+        x = np.ascontiguousarray(x, dtype=np.uint32)
+        out = np.empty_like(x)
+        total = self.lib.oracle_scan_u32(x, out, x.size, int(exclusive), carry & 0xFFFFFFFF)
+        return out, total
+
+    def scan_u32_mt(self, x: np.ndarray, out: np.ndarray, exclusive: bool, carry: int, threads: int) -> int:
+        return self.lib.oracle_scan_u32_mt(x, out, x.size, int(exclusive), carry & 0xFFFFFFFF, threads)
+
+    def scan_f32(self, x: np.ndarray, exclusive: bool = False, carry: float = 0.0):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty(x.size, dtype=np.float64)
+        total = self.lib.oracle_scan_f32_f64(x, out, None, x.size, int(exclusive), float(carry))
+        return out, total
+
+    def check_f32(self, x: np.ndarray, cand: np.ndarray, exclusive: bool = False, carry: float = 0.0,
+                  rtol: float = 2e-5, atol: float = 1e-6):
+        """(errors, max relative error) of a float32 candidate vs the float64 serial scan."""
+        mx = C.c_double(0.0)
+        errs = self.lib.oracle_check_f32(np.ascontiguousarray(x, dtype=np.float32),
+                                         np.ascontiguousarray(cand, dtype=np.float32), x.size, int(exclusive),
+                                         float(carry), rtol, atol, C.byref(mx))
+        return errs, mx.value
+
+    def check_u32(self, x: np.ndarray, cand: np.ndarray, exclusive: bool = False, carry: int = 0):
+        first = C.c_uint64(0)
+        errs = self.lib.oracle_check_u32(np.ascontiguousarray(x, dtype=np.uint32),
+                                         np.ascontiguousarray(cand, dtype=np.uint32), x.size, int(exclusive),
+                                         carry & 0xFFFFFFFF, C.byref(first))
+        return errs, first.value
+
+    def validate_ones(self, scan: np.ndarray, exclusive: bool) -> int:
+        return self.lib.oracle_validate_ones(np.ascontiguousarray(scan, dtype=np.uint32), scan.size, int(exclusive))
+
+    # --- inputs ------------------------------------------------------------------
+    def random_u32(self, n: int, seed: int, mask: int = 0xFFFFFFFF, first_index: int = 0) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint32)
+        self.lib.oracle_init_random_u32(out, n, seed, mask, first_index)
+        return out
+
+    def random_f32(self, n: int, seed: int, first_index: int = 0) -> np.ndarray:
+        out = np.empty(n, dtype=np.float32)
+        self.lib.oracle_init_random_f32(out, n, seed, first_index)
+        return out
+
+    def random_d3d12(self, n: int, seed: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint32)
+        self.lib.oracle_init_random_d3d12(out, n, seed)
+        return out
+
+
+def load() -> Oracle:
+    return Oracle(C.CDLL(build()))
+
+
+class RefShim:
+    """oracle/_ref/libref_shim.so: the reference's unmodified CUDA kernels on caller buffers."""
+
+    CSDL, RTS, EMULATED_DEADLOCK, CUB = 0, 1, 2, 3
+
+    def __init__(self, lib: C.CDLL):
+        self.lib = lib
+        lib.ref_scan_u32.restype = C.c_int
+        lib.ref_scan_u32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_uint32]
+        lib.ref_cub_scan_f32.restype = C.c_int
+        lib.ref_cub_scan_f32.argtypes = [C.c_int, C.c_void_p, C.c_uint32]
+        lib.ref_init_one.restype = None
+        lib.ref_init_one.argtypes = [C.c_void_p, C.c_uint32]
+        lib.ref_validate.restype = C.c_uint32
+        lib.ref_validate.argtypes = [C.c_int, C.c_void_p, C.c_uint32]
+        lib.ref_time_u32.restype = C.c_double
+        lib.ref_time_u32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+
+    def scan_u32(self, algo: int, exclusive: bool, d_ptr: int, size: int) -> int:
+        return self.lib.ref_scan_u32(algo, int(exclusive), d_ptr, size)
+
+    def time_u32(self, algo: int, exclusive: bool, d_ptr: int, d_src: int | None, size: int, batch: int) -> float:
+        return self.lib.ref_time_u32(algo, int(exclusive), d_ptr, d_src, size, batch)
+
+
+def load_ref_shim() -> RefShim | None:
+    if not os.path.exists(REF_SHIM_SO):
+        return None
+    return RefShim(C.CDLL(REF_SHIM_SO))

@@ -1,0 +1,425 @@
+// tools/gps_tune.cu -- tuning / comparison harness (developer tool, not the product).
+// Sweeps kernel configurations of the register and TMA CSDL paths, RTS, copy
+// ceilings (cudaMemcpy D2D, LDG/STG copy kernel, TMA bulk copy kernel) and
+// cub::DeviceScan on one GPU; verifies every variant against CUB's output word for word
+// and prints one JSON object per variant.
+//   gps_tune [--log2n 28] [--n N] [--iters 50] [--filter substr] [--float] [--exclusive]
+#include <cub/device/device_scan.cuh>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../gpuprefixsums_b200/csrc/gps_launch.cuh"
+#include "../gpuprefixsums_b200/csrc/gps_util_kernels.cuh"
+
+using namespace gps;
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(2);                                                                  \
+        }                                                                             \
+    } while (0)
+
+// ---- copy ceilings ----------------------------------------------------------------
+template <int NT, int V>
+__global__ void __launch_bounds__(NT) copy_ldg_kernel(const uint4* in, uint4* out, uint64_t nvec)
+{
+    const uint64_t base = (uint64_t)blockIdx.x * (NT * V) + (threadIdx.x >> 5) * (32 * V) + (threadIdx.x & 31);
+    uint4 r[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+        if (base + 32 * k < nvec) r[k] = ldg_stream(in + base + 32 * k);
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+        if (base + 32 * k < nvec) stg_stream(out + base + 32 * k, r[k]);
+}
+
+// persistent TMA bulk copy: global -> smem ring -> global, one thread drives it
+template <int TILE_BYTES, int STAGES>
+__global__ void __launch_bounds__(32) copy_tma_kernel(const unsigned char* in, unsigned char* out,
+                                                      uint32_t num_tiles, uint32_t* counter,
+                                                      uint32_t counter_base)
+{
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) uint64_t s_full[STAGES];
+    if (threadIdx.x != 0) return;
+    for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+    fence_mbar_init();
+    uint32_t tiles[STAGES];
+    auto produce = [&](int stage) {
+        const uint32_t t = atomicAdd(counter, 1u) - counter_base;
+        tiles[stage] = t;
+        if (t < num_tiles) {
+            mbar_arrive_expect_tx(&s_full[stage], TILE_BYTES);
+            bulk_load(ring + (size_t)stage * TILE_BYTES, in + (uint64_t)t * TILE_BYTES, TILE_BYTES, &s_full[stage]);
+        }
+    };
+    // static register indexing is not needed here (one thread, local array is fine)
+    for (int s = 0; s < STAGES - 1; ++s) produce(s);
+    for (uint32_t it = 0;; ++it) {
+        const int stage = it % STAGES;
+        const uint32_t tile = tiles[stage];
+        if (tile >= num_tiles) break;
+        mbar_wait(&s_full[stage], (it / STAGES) & 1u);
+        bulk_store(out + (uint64_t)tile * TILE_BYTES, ring + (size_t)stage * TILE_BYTES, TILE_BYTES);
+        bulk_commit();
+        bulk_wait_read<1>();
+        produce((it + STAGES - 1) % STAGES);
+    }
+    bulk_wait<0>();
+}
+
+// ---- harness ------------------------------------------------------------------------
+struct Env {
+    uint64_t n = 1ull << 28;
+    int iters = 50;
+    bool is_float = false;
+    bool exclusive = false;
+    void *in = nullptr, *out = nullptr, *ref = nullptr, *work = nullptr;
+    Scratch s;
+    uint32_t* tma_copy_counter = nullptr;
+    uint32_t tma_copy_base = 0;
+    cudaEvent_t e0, e1;
+    double copy_gbs = 0;
+};
+
+struct Result {
+    double ms_mean = 0;
+    uint64_t errs = 0;
+    bool verified = false;
+    bool ok = true;
+};
+
+static uint64_t compare(Env& env, const void* got)
+{
+    unsigned long long* d_err;
+    unsigned long long init[2] = {0ull, ~0ull}, h[2];
+    CK(cudaMalloc(&d_err, sizeof(init)));
+    CK(cudaMemcpy(d_err, init, sizeof(init), cudaMemcpyHostToDevice));
+    if (!env.is_float) {
+        compare_u32_kernel<<<2048, 256>>>((const uint32_t*)got, (const uint32_t*)env.ref, env.n, d_err);
+    } else {
+        // float: tolerance vs CUB (a peer, not an oracle): rtol 1e-4 of the value
+        compare_f32_kernel<<<2048, 256>>>((const float*)got, (const float*)env.ref, nullptr, env.n, 1e-4f, 1e-3f,
+                                          d_err, (uint32_t*)(d_err + 1));
+    }
+    CK(cudaMemcpy(h, d_err, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaFree(d_err));
+    if (h[0] && !env.is_float) fprintf(stderr, "    first mismatch at %llu\n", h[1]);
+    return h[0];
+}
+
+using LaunchFn = std::function<cudaError_t(const void* in, void* out)>;
+
+static Result run_variant(Env& env, const char* name, bool verify, const LaunchFn& fn, double bytes_per_key = 8.0,
+                          bool inplace_too = true)
+{
+    Result r;
+    // correctness: out-of-place once, then in place once
+    CK(cudaMemset(env.out, 0xAB, env.n * 4));
+    cudaError_t e = fn(env.in, env.out);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("{\"variant\": \"%s\", \"error\": \"%s\"}\n", name, cudaGetErrorString(e));
+        fflush(stdout);
+        r.ok = false;
+        return r;
+    }
+    uint32_t status = 0;
+    CK(cudaMemcpy(&status, env.s.status, 4, cudaMemcpyDeviceToHost));
+    if (status) CK(cudaMemset(env.s.status, 0, 4));
+    if (verify) {
+        r.errs = compare(env, env.out);
+        r.verified = true;
+        if (inplace_too) {
+            CK(cudaMemcpy(env.work, env.in, env.n * 4, cudaMemcpyDeviceToDevice));
+            e = fn(env.work, env.work);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) {
+                printf("{\"variant\": \"%s\", \"error\": \"in-place: %s\"}\n", name, cudaGetErrorString(e));
+                r.ok = false;
+                return r;
+            }
+            r.errs += compare(env, env.work);
+        }
+    }
+    // timing: out-of-place, back to back (2 GiB of traffic per launch at 2^28 >> L2)
+    for (int i = 0; i < 3; ++i) fn(env.in, env.out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(env.e0));
+    for (int i = 0; i < env.iters; ++i) fn(env.in, env.out);
+    CK(cudaEventRecord(env.e1));
+    CK(cudaEventSynchronize(env.e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, env.e0, env.e1));
+    r.ms_mean = ms / env.iters;
+    // in place timing
+    double ms_inplace = 0;
+    if (inplace_too) {
+        for (int i = 0; i < 2; ++i) fn(env.work, env.work);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(env.e0));
+        for (int i = 0; i < env.iters; ++i) fn(env.work, env.work);
+        CK(cudaEventRecord(env.e1));
+        CK(cudaEventSynchronize(env.e1));
+        CK(cudaEventElapsedTime(&ms, env.e0, env.e1));
+        ms_inplace = ms / env.iters;
+    }
+    CK(cudaMemcpy(&status, env.s.status, 4, cudaMemcpyDeviceToHost));
+    if (status) CK(cudaMemset(env.s.status, 0, 4));
+    const double gkeys = env.n / (r.ms_mean * 1e-3) / 1e9;
+    const double gbs = gkeys * bytes_per_key;
+    printf("{\"variant\": \"%s\", \"n\": %llu, \"ms\": %.5f, \"gkeys_s\": %.2f, \"gb_s\": %.1f, "
+           "\"ms_inplace\": %.5f, \"gkeys_s_inplace\": %.2f, \"verified\": %s, \"errors\": %llu, \"watchdog\": %u}\n",
+           name, (unsigned long long)env.n, r.ms_mean, gkeys, gbs, ms_inplace,
+           ms_inplace > 0 ? env.n / (ms_inplace * 1e-3) / 1e9 : 0.0, r.verified ? "true" : "false",
+           (unsigned long long)r.errs, status);
+    fflush(stdout);
+    return r;
+}
+
+template <typename T, int NT, int V, bool INCL>
+static void add_reg(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, const char* suffix = "")
+{
+    char name[96];
+    snprintf(name, sizeof(name), "csdl_reg<%d,%d>%s", NT, V, suffix);
+    v.emplace_back(name, [&env](const void* in, void* out) {
+        CarrySpec cs;
+        return launch_csdl_reg<T, NT, V, INCL>(env.s, in, out, env.n, cs, 0);
+    });
+}
+
+template <typename T, int NT, int STAGES, bool INCL>
+static void add_tma(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, int max_ctas)
+{
+    char name[96];
+    snprintf(name, sizeof(name), "csdl_tma<%d,S%d>/cta%d", NT, STAGES, max_ctas);
+    auto occ = std::make_shared<int>(0);
+    v.emplace_back(name, [&env, occ, max_ctas](const void* in, void* out) {
+        CarrySpec cs;
+        return launch_csdl_tma<T, NT, STAGES, INCL>(env.s, in, out, env.n, cs, *occ, max_ctas, 0);
+    });
+}
+
+template <typename T, int NT, int V, bool INCL>
+static void add_rts(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v)
+{
+    char name[96];
+    snprintf(name, sizeof(name), "rts<%d,%d>", NT, V);
+    auto occ = std::make_shared<int>(0);
+    v.emplace_back(name, [&env, occ](const void* in, void* out) {
+        CarrySpec cs;
+        return launch_rts<T, NT, V, INCL>(env.s, in, out, env.n, cs, *occ, 0);
+    });
+}
+
+template <typename T, int NT, int V, bool INCL>
+static void add_fallback(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, uint32_t mask, uint32_t spin)
+{
+    char name[96];
+    snprintf(name, sizeof(name), "csdl_fallback<%d,%d>/mask%x/spin%u", NT, V, mask, spin);
+    v.emplace_back(name, [&env, mask, spin](const void* in, void* out) {
+        CarrySpec cs;
+        FallbackParams f{mask, spin, nullptr};
+        return launch_csdl_fallback<T, NT, V, INCL>(env.s, in, out, env.n, cs, f, 0);
+    });
+}
+
+template <typename T, bool INCL>
+static void build_variants(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v)
+{
+    add_reg<T, 256, 4, INCL>(env, v);
+    add_reg<T, 128, 4, INCL>(env, v);
+    add_reg<T, 128, 8, INCL>(env, v);
+    add_reg<T, 256, 2, INCL>(env, v);
+    add_reg<T, 256, 8, INCL>(env, v);
+    add_reg<T, 512, 4, INCL>(env, v);
+    add_reg<T, 512, 2, INCL>(env, v);
+    add_reg<T, 384, 4, INCL>(env, v);
+    add_reg<T, 1024, 2, INCL>(env, v);
+    add_tma<T, 256, 3, INCL>(env, v, 0);
+    add_tma<T, 256, 4, INCL>(env, v, 0);
+    add_tma<T, 256, 6, INCL>(env, v, 0);
+    add_tma<T, 512, 2, INCL>(env, v, 0);
+    add_tma<T, 512, 3, INCL>(env, v, 0);
+    add_tma<T, 512, 3, INCL>(env, v, 1);
+    add_tma<T, 512, 4, INCL>(env, v, 0);
+    add_tma<T, 1024, 2, INCL>(env, v, 0);
+    add_tma<T, 1024, 3, INCL>(env, v, 0);
+    add_rts<T, 256, 4, INCL>(env, v);
+    add_rts<T, 512, 4, INCL>(env, v);
+    add_fallback<T, 256, 4, INCL>(env, v, kNoStall, 64);
+    add_fallback<T, 256, 4, INCL>(env, v, kNoStall, 4);
+    add_fallback<T, 256, 4, INCL>(env, v, 7, 4);
+    add_fallback<T, 256, 4, INCL>(env, v, 63, 4);
+}
+
+template <typename T, bool INCL>
+static cudaError_t cub_scan(const void* in, void* out, uint64_t n, void*& temp, size_t& temp_bytes)
+{
+    size_t need = 0;
+    if (INCL)
+        cub::DeviceScan::InclusiveSum(nullptr, need, (const T*)in, (T*)out, (int64_t)n);
+    else
+        cub::DeviceScan::ExclusiveSum(nullptr, need, (const T*)in, (T*)out, (int64_t)n);
+    if (need > temp_bytes) {
+        if (temp) cudaFree(temp);
+        cudaMalloc(&temp, need);
+        temp_bytes = need;
+    }
+    if (INCL)
+        return cub::DeviceScan::InclusiveSum(temp, need, (const T*)in, (T*)out, (int64_t)n);
+    return cub::DeviceScan::ExclusiveSum(temp, need, (const T*)in, (T*)out, (int64_t)n);
+}
+
+template <typename T, bool INCL>
+static int run_all(Env& env, const char* filter)
+{
+    static void* cub_temp = nullptr;
+    static size_t cub_temp_bytes = 0;
+    auto wanted = [&](const std::string& name) { return !filter || name.find(filter) != std::string::npos; };
+    const uint64_t nvec = env.n / 4;
+
+    // reference output from CUB
+    CK((cub_scan<T, INCL>(env.in, env.ref, env.n, cub_temp, cub_temp_bytes)));
+    CK(cudaDeviceSynchronize());
+
+    if (wanted("copy_memcpy"))
+        run_variant(env, "copy_memcpy_d2d", false,
+                    [&](const void* in, void* out) { return cudaMemcpyAsync(out, in, env.n * 4, cudaMemcpyDeviceToDevice, 0); },
+                    8.0, false);
+    if (wanted("copy_ldg")) {
+        run_variant(env, "copy_ldg<256,4>", false, [&](const void* in, void* out) {
+            copy_ldg_kernel<256, 4><<<(unsigned)div_up(nvec, 256 * 4), 256>>>((const uint4*)in, (uint4*)out, nvec);
+            return cudaGetLastError();
+        }, 8.0, false);
+        run_variant(env, "copy_ldg<512,4>", false, [&](const void* in, void* out) {
+            copy_ldg_kernel<512, 4><<<(unsigned)div_up(nvec, 512 * 4), 512>>>((const uint4*)in, (uint4*)out, nvec);
+            return cudaGetLastError();
+        }, 8.0, false);
+        run_variant(env, "copy_ldg<256,8>", false, [&](const void* in, void* out) {
+            copy_ldg_kernel<256, 8><<<(unsigned)div_up(nvec, 256 * 8), 256>>>((const uint4*)in, (uint4*)out, nvec);
+            return cudaGetLastError();
+        }, 8.0, false);
+    }
+    if (wanted("copy_tma") && env.n % 8192 == 0) {
+        auto tma_copy = [&](auto kern, int tile_bytes, int stages, int ctas_per_sm, const char* name) {
+            const int smem = tile_bytes * stages;
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const uint32_t tiles = (uint32_t)(env.n * 4 / tile_bytes);
+            const uint32_t grid = 148 * ctas_per_sm;
+            run_variant(env, name, false, [&, kern, tiles, grid, smem, stages](const void* in, void* out) {
+                kern<<<grid, 32, smem>>>((const unsigned char*)in, (unsigned char*)out, tiles, env.tma_copy_counter,
+                                         env.tma_copy_base);
+                env.tma_copy_base += grid * (stages - 1) + tiles;
+                return cudaGetLastError();
+            }, 8.0, false);
+        };
+        tma_copy(copy_tma_kernel<32768, 3>, 32768, 3, 2, "copy_tma<32K,S3>x2");
+        tma_copy(copy_tma_kernel<16384, 4>, 16384, 4, 3, "copy_tma<16K,S4>x3");
+        tma_copy(copy_tma_kernel<32768, 6>, 32768, 6, 1, "copy_tma<32K,S6>x1");
+        tma_copy(copy_tma_kernel<8192, 4>, 8192, 4, 6, "copy_tma<8K,S4>x6");
+    }
+    if (wanted("cub"))
+        run_variant(env, "cub_device_scan", true, [&](const void* in, void* out) {
+            return cub_scan<T, INCL>(in, out, env.n, cub_temp, cub_temp_bytes);
+        });
+
+    std::vector<std::pair<std::string, LaunchFn>> variants;
+    build_variants<T, INCL>(env, variants);
+    int bad = 0;
+    for (auto& kv : variants) {
+        if (!wanted(kv.first)) continue;
+        Result r = run_variant(env, kv.first.c_str(), true, kv.second);
+        if (!r.ok || r.errs) ++bad;
+    }
+    // knobs on the two main candidates
+    if (wanted("knob")) {
+        for (uint32_t sleep_ns : {20u, 100u}) {
+            env.s.poll_sleep_ns = sleep_ns;
+            char name[96];
+            snprintf(name, sizeof(name), "knob/csdl_reg<256,4>/sleep%u", sleep_ns);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
+            });
+            snprintf(name, sizeof(name), "knob/csdl_tma<512,S3>/sleep%u", sleep_ns);
+            static int occ = 0;
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_tma<T, 512, 3, INCL>(env.s, in, out, env.n, cs, occ, 0, 0);
+            });
+        }
+        env.s.poll_sleep_ns = 0;
+        env.s.flags = PF_DESC_RELAXED;
+        run_variant(env, "knob/csdl_reg<256,4>/relaxed", true, [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
+        });
+        static int occ2 = 0;
+        run_variant(env, "knob/csdl_tma<512,S3>/relaxed", true, [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_tma<T, 512, 3, INCL>(env.s, in, out, env.n, cs, occ2, 0, 0);
+        });
+        env.s.flags = 0;
+    }
+    return bad;
+}
+
+int main(int argc, char** argv)
+{
+    Env env;
+    const char* filter = nullptr;
+    for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "--log2n") && i + 1 < argc) env.n = 1ull << atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--n") && i + 1 < argc) env.n = strtoull(argv[++i], nullptr, 10);
+        else if (!strcmp(argv[i], "--iters") && i + 1 < argc) env.iters = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--filter") && i + 1 < argc) filter = argv[++i];
+        else if (!strcmp(argv[i], "--float")) env.is_float = true;
+        else if (!strcmp(argv[i], "--exclusive")) env.exclusive = true;
+        else {
+            fprintf(stderr, "unknown argument %s\n", argv[i]);
+            return 2;
+        }
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    fprintf(stderr, "device: %s, %d SMs, L2 %d MB\n", prop.name, prop.multiProcessorCount, prop.l2CacheSize >> 20);
+    const size_t bytes = env.n * 4 + 64;
+    CK(cudaMalloc(&env.in, bytes));
+    CK(cudaMalloc(&env.out, bytes));
+    CK(cudaMalloc(&env.ref, bytes));
+    CK(cudaMalloc(&env.work, bytes));
+    env.s.sm_count = prop.multiProcessorCount;
+    env.s.desc_tiles = (uint32_t)div_up(env.n, 2048) + 1;
+    CK(cudaMalloc(&env.s.desc, (size_t)env.s.desc_tiles * 8));
+    CK(cudaMemset(env.s.desc, 0, (size_t)env.s.desc_tiles * 8));
+    CK(cudaMalloc(&env.s.counter, 64));
+    CK(cudaMemset(env.s.counter, 0, 64));
+    env.s.status = env.s.counter + 1;
+    env.tma_copy_counter = env.s.counter + 8;
+    CK(cudaMalloc(&env.s.partials, kMaxParts * 4));
+    CK(cudaEventCreate(&env.e0));
+    CK(cudaEventCreate(&env.e1));
+    if (env.is_float)
+        init_random_f32_kernel<<<2048, 256>>>((float*)env.in, env.n, 1234, 0);
+    else
+        init_random_u32_kernel<<<2048, 256>>>((uint32_t*)env.in, env.n, 1234, 0xFFFFFFFFu, 0);
+    CK(cudaDeviceSynchronize());
+
+    int bad;
+    if (env.is_float)
+        bad = env.exclusive ? run_all<float, false>(env, filter) : run_all<float, true>(env, filter);
+    else
+        bad = env.exclusive ? run_all<uint32_t, false>(env, filter) : run_all<uint32_t, true>(env, filter);
+    fprintf(stderr, "variants with errors: %d\n", bad);
+    return bad ? 1 : 0;
+}
