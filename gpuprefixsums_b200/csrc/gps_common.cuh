@@ -52,8 +52,33 @@ struct ScanParams {
     uint32_t* status;         // watchdog / error word (bit 0 = poll budget exceeded)
     uint32_t poll_sleep_ns;
     uint32_t flags;           // PF_* bits
+    unsigned long long* prof; // optional (tuning): kProfSlots x kProfFields counters
 };
-enum : uint32_t { PF_DESC_RELAXED = 1u };  // tuning: relaxed instead of release/acquire
+// profiling counters (per tile, accumulated): SM cycles spent in each phase + look-back effort
+enum : int { PROF_TILES = 0, PROF_CLAIM, PROF_LOAD, PROF_REDUCE, PROF_LOOKBACK, PROF_FINISH,
+             PROF_WINDOWS, PROF_POLLS, kProfFields };
+constexpr int kProfSlots = 64;  // spread over 64 rows to keep the atomics uncontended
+// Descriptor protocol (measured on B200 at 2^28 keys, register path <256,4>):
+//   publish st.release.gpu + poll ld.acquire.gpu : 281 Gkeys/s  (MEMBAR.ALL.GPU before every
+//            store; CCTL.IVALL after every poll; the store itself lingers behind the SM's
+//            streaming data stores before it becomes visible)
+//   publish st.relaxed.gpu + poll ld.relaxed.gpu : 309 Gkeys/s
+//   publish atom.exch.gpu  + poll ld.relaxed.gpu : 426 Gkeys/s  <- default
+// The descriptor carries its payload in the same 64-bit word as the flag, so plain CSDL
+// needs no ordering against other memory; the atomic is used because it is performed at L2
+// immediately instead of waiting in the store path.  The fallback kernel adds the one
+// fence it needs explicitly.
+enum : uint32_t {
+    PF_PUBLISH_ST_RELEASE = 1u,  // publish with st.release.gpu (else atom.exch.relaxed.gpu)
+    PF_SKIP_LOOKBACK = 2u,       // experiment: publish but never look back (WRONG results)
+    PF_FENCE_ALL = 4u,           // experiment: every thread fences after the publish (reference style)
+    PF_LD_ALLOCATE = 8u,         // experiment: plain (L1-allocating) loads/stores
+    PF_STATIC_TILE = 16u,        // tile = blockIdx.x (relies on in-order CTA dispatch, like CUB)
+    PF_POLL_VOLATILE = 32u,      // poll with ld.volatile (SASS LDG.STRONG.SYS, reference style)
+    PF_PUBLISH_ST_RELAXED = 64u, // publish with st.relaxed.gpu
+    PF_DELAY_FIRST = 128u,       // experiment: nanosleep(poll_sleep_ns) once before the first poll
+    PF_POLL_ACQUIRE = 256u,      // poll with ld.acquire.gpu (else ld.relaxed.gpu)
+};
 
 enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
 enum : uint32_t { STATUS_WATCHDOG = 1u };
@@ -131,20 +156,20 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p)
     return v;
 }
 
-// Descriptor publish / poll: st.release.gpu / ld.acquire.gpu.  The payload rides in the
-// same 64-bit word as the flag, so plain CSDL would also be correct with relaxed
-// accesses; PF_DESC_RELAXED (a warp-uniform runtime flag used by the tuning harness)
-// selects them to measure what the release/acquire qualifiers cost.
+// Descriptor publish / poll (protocol selected by warp-uniform flags, see PF_* above).
 __device__ __forceinline__ void desc_publish(const ScanParams& p, uint64_t* ptr, uint64_t v)
 {
-    if (p.flags & PF_DESC_RELAXED)
+    if (p.flags & PF_PUBLISH_ST_RELEASE)
+        st_release_gpu(ptr, v);
+    else if (p.flags & PF_PUBLISH_ST_RELAXED)
         st_relaxed_gpu(ptr, v);
     else
-        st_release_gpu(ptr, v);
+        asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(v) : "memory");
 }
 __device__ __forceinline__ uint64_t desc_poll(const ScanParams& p, const uint64_t* ptr)
 {
-    return (p.flags & PF_DESC_RELAXED) ? ld_relaxed_gpu(ptr) : ld_acquire_gpu(ptr);
+    if (p.flags & PF_POLL_VOLATILE) return *reinterpret_cast<const volatile uint64_t*>(ptr);
+    return (p.flags & PF_POLL_ACQUIRE) ? ld_acquire_gpu(ptr) : ld_relaxed_gpu(ptr);
 }
 
 // ---------------------------------------------------------------------------------
@@ -209,6 +234,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {
     }
+}
+// bounded variant: false if the phase did not complete within ~2^22 try_waits (each of
+// which suspends the thread for a HW-defined interval) -- a TMA that never lands must not
+// hang the GPU
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity)
+{
+    for (uint32_t i = 0; i < (1u << 22); ++i)
+        if (mbar_try_wait(bar, parity)) return true;
+    return false;
 }
 // global -> shared::cta, completion signalled on an mbarrier (bytes % 16 == 0)
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes,
@@ -375,12 +409,19 @@ __device__ __forceinline__ uint32_t claim_tile(const ScanParams& p)
 // virtual INCLUSIVE/0 entry (they are never the nearest INCLUSIVE because tile 0
 // itself always publishes INCLUSIVE).  Returns the exclusive prefix of `tile`.
 // ---------------------------------------------------------------------------------
+struct LookbackStats {
+    uint32_t windows = 0;  // descriptor windows consumed
+    uint32_t polls = 0;    // polls that found the nearest tile not ready
+};
+
 template <typename T>
-__device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, uint32_t lane)
+__device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, uint32_t lane,
+                                           LookbackStats* stats = nullptr)
 {
     T prefix = T(0);
     int64_t top = (int64_t)tile - 1;
-    uint32_t polls = 0;
+    uint32_t polls = 0, windows = 0;
+    if ((p.flags & PF_DELAY_FIRST) && p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
     while (true) {
         const int64_t idx = top - (int64_t)lane;
         uint64_t d = pack_desc(0u, p.epoch, ST_INCLUSIVE);
@@ -389,22 +430,48 @@ __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, u
             d = desc_poll(p, p.desc + idx);
             ready = desc_valid(d, p.epoch);
         }
-        if (!__all_sync(kFullMask, ready)) {
+        // consume the run of ready descriptors nearest to this tile; an INCLUSIVE one in
+        // that run ends the walk no matter what farther tiles are doing
+        const uint32_t not_ready = __ballot_sync(kFullMask, !ready);
+        const uint32_t run = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
+        if (run == 0u) {
             const bool bail = watchdog_tick(polls, p.status);
-            if (__any_sync(kFullMask, bail)) return prefix;  // warp-uniform exit
+            if (__any_sync(kFullMask, bail)) break;  // warp-uniform exit
             if (p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
             continue;
         }
+        ++windows;
+        const uint32_t in_run = run >= 32u ? kFullMask : ((1u << run) - 1u);
         const T v = from_bits<T>(desc_value(d));
-        const uint32_t incl = __ballot_sync(kFullMask, desc_status(d) == ST_INCLUSIVE);
+        const uint32_t incl = __ballot_sync(kFullMask, ready && desc_status(d) == ST_INCLUSIVE) & in_run;
         if (incl) {
             const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
             prefix += warp_reduce(lane <= nearest ? v : T(0));
-            return prefix;
+            break;
         }
-        prefix += warp_reduce(v);
-        top -= 32;
+        prefix += warp_reduce(lane < run ? v : T(0));
+        top -= (int64_t)run;
     }
+    if (stats) {
+        stats->windows = windows;
+        stats->polls = polls;
+    }
+    return prefix;
+}
+
+// accumulate one tile's profile (called by ONE thread; p.prof != nullptr)
+__device__ __forceinline__ void prof_add(const ScanParams& p, uint32_t tile, const long long (&t)[6],
+                                         const LookbackStats& lb)
+{
+    unsigned long long* row = p.prof + (size_t)(tile % kProfSlots) * kProfFields;
+    atomicAdd(row + PROF_TILES, 1ull);
+    atomicAdd(row + PROF_CLAIM, (unsigned long long)(t[1] - t[0]));
+    atomicAdd(row + PROF_LOAD, (unsigned long long)(t[2] - t[1]));
+    atomicAdd(row + PROF_REDUCE, (unsigned long long)(t[3] - t[2]));
+    atomicAdd(row + PROF_LOOKBACK, (unsigned long long)(t[4] - t[3]));
+    atomicAdd(row + PROF_FINISH, (unsigned long long)(t[5] - t[4]));
+    atomicAdd(row + PROF_WINDOWS, (unsigned long long)lb.windows);
+    atomicAdd(row + PROF_POLLS, (unsigned long long)lb.polls);
 }
 
 }  // namespace gps

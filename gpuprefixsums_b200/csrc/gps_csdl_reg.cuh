@@ -25,21 +25,33 @@ __global__ void __launch_bounds__(NT) csdl_reg_kernel(const __grid_constant__ Sc
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
 
-    if (threadIdx.x == 0) s_tile = claim_tile(p);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    long long tprof[6] = {0, 0, 0, 0, 0, 0};
+    LookbackStats lbs;
+    const bool profiler = p.prof != nullptr && threadIdx.x == 0;
+    if (profiler) tprof[0] = clock64();
+    uint32_t tile;
+    if (p.flags & PF_STATIC_TILE) {
+        tile = blockIdx.x;
+    } else {
+        if (threadIdx.x == 0) s_tile = claim_tile(p);
+        __syncthreads();
+        tile = s_tile;
+    }
     const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
     const uint64_t vbase = Tile::vec_base(tile, warp, lane);
 
+    if (profiler) tprof[1] = clock64();
+    const bool allocate = p.flags & PF_LD_ALLOCATE;
     Tile t;
     if (full)
-        t.load_full(p.in, vbase);
+        t.load_full(p.in, vbase, allocate);
     else
         t.load_partial(p.in, vbase, p.n);
     t.scan_warp(lane);
     if (lane == 0) s_warp[warp] = t.warp_total;
     __syncthreads();
 
+    if (profiler) tprof[2] = clock64();
     T warp_prefix, aggregate;
     block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, aggregate);
 
@@ -47,11 +59,14 @@ __global__ void __launch_bounds__(NT) csdl_reg_kernel(const __grid_constant__ Sc
         T prefix;
         if (tile == 0) {
             prefix = acquire_carry<T>(p, lane);
+            if (profiler) tprof[3] = clock64();
         } else {
             if (lane == 0)
                 desc_publish(p, p.desc + tile, pack_desc(to_bits(aggregate), p.epoch, ST_AGGREGATE));
-            prefix = lookback_warp<T>(p, tile, lane);
+            if (profiler) tprof[3] = clock64();
+            prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T>(p, tile, lane, &lbs);
         }
+        if (profiler) tprof[4] = clock64();
         if (lane == 0) {
             const T inclusive = prefix + aggregate;
             desc_publish(p, p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
@@ -59,13 +74,18 @@ __global__ void __launch_bounds__(NT) csdl_reg_kernel(const __grid_constant__ Sc
             if (tile == p.num_tiles - 1) write_total<T>(p, inclusive);
         }
     }
+    if (p.flags & PF_FENCE_ALL) __threadfence();
     __syncthreads();
 
     const T prefix = s_prefix + warp_prefix;
     if (full)
-        t.template store_full<INCLUSIVE>(p.out, vbase, prefix);
+        t.template store_full<INCLUSIVE>(p.out, vbase, prefix, allocate);
     else
         t.template store_partial<INCLUSIVE>(p.out, vbase, p.n, prefix);
+    if (profiler) {
+        tprof[5] = clock64();
+        prof_add(p, tile, tprof, lbs);
+    }
 }
 
 // ---------------------------------------------------------------------------------

@@ -27,6 +27,7 @@ struct Scratch {
     int sm_count = 148;
     uint32_t poll_sleep_ns = 0;
     uint32_t flags = 0;
+    unsigned long long* prof = nullptr;  // optional profiling counters (tuning harness)
 };
 
 // everything a scan launch needs besides the buffers
@@ -69,6 +70,7 @@ inline ScanParams make_scan_params(Scratch& s, const void* in, void* out, uint64
     p.status = s.status;
     p.poll_sleep_ns = s.poll_sleep_ns;
     p.flags = s.flags;
+    p.prof = s.prof;
     return p;
 }
 
@@ -96,19 +98,26 @@ cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, c
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
     csdl_reg_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p);
-    s.counter_base += p.num_tiles;  // one claim per CTA
+    if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
     return cudaGetLastError();
 }
 
 // ---- CSDL TMA path -------------------------------------------------------------------
 // ctas_per_sm: in/out cache (0 = query occupancy and opt in to the dynamic smem size);
 // max_ctas_per_sm: 0 = as many as fit
-template <typename T, int NT, int STAGES, bool INCL>
+// VER: 1 = tile-at-a-time kernel, 2 = aggregate-ahead software pipeline, 3 = early refill
+template <typename T, int NT, int STAGES, bool INCL, int VER = 2>
 cudaError_t launch_csdl_tma(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
                             int& ctas_per_sm, int max_ctas_per_sm, cudaStream_t st)
 {
     using Cfg = TmaCfg<NT, STAGES>;
-    auto kern = csdl_tma_kernel<T, NT, STAGES, INCL>;
+    void (*kern)(const ScanParams);
+    if constexpr (VER == 1)
+        kern = csdl_tma_kernel<T, NT, STAGES, INCL>;
+    else if constexpr (VER == 3)
+        kern = csdl_tma3_kernel<T, NT, STAGES, INCL>;
+    else
+        kern = csdl_tma2_kernel<T, NT, STAGES, INCL>;
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Cfg::RING_BYTES);

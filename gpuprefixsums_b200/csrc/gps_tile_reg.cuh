@@ -43,12 +43,18 @@ struct RegTile {
     }
 
     // full tile: V back-to-back LDG.128, nothing else between them
-    __device__ __forceinline__ void load_full(const void* in, uint64_t vbase)
+    // `allocate` (experiment switch, warp-uniform): plain L1-allocating accesses
+    __device__ __forceinline__ void load_full(const void* in, uint64_t vbase, bool allocate = false)
     {
         const uint4* in4 = reinterpret_cast<const uint4*>(in);
         uint4 r[V];
+        if (allocate) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) r[k] = ldg_stream(in4 + vbase + 32u * k);
+            for (int k = 0; k < V; ++k) r[k] = in4[vbase + 32u * k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) r[k] = ldg_stream(in4 + vbase + 32u * k);
+        }
 #pragma unroll
         for (int k = 0; k < V; ++k) set_row(k, r[k]);
     }
@@ -128,11 +134,16 @@ struct RegTile {
 
     // prefix = tile prefix + this warp's prefix within the tile
     template <bool INCLUSIVE>
-    __device__ __forceinline__ void store_full(void* out, uint64_t vbase, T prefix) const
+    __device__ __forceinline__ void store_full(void* out, uint64_t vbase, T prefix, bool allocate = false) const
     {
         uint4* out4 = reinterpret_cast<uint4*>(out);
+        if (allocate) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) stg_stream(out4 + vbase + 32u * k, finish_row<INCLUSIVE>(k, prefix));
+            for (int k = 0; k < V; ++k) out4[vbase + 32u * k] = finish_row<INCLUSIVE>(k, prefix);
+        } else {
+#pragma unroll
+            for (int k = 0; k < V; ++k) stg_stream(out4 + vbase + 32u * k, finish_row<INCLUSIVE>(k, prefix));
+        }
     }
 
     template <bool INCLUSIVE>

@@ -89,6 +89,9 @@ struct Env {
     uint32_t tma_copy_base = 0;
     cudaEvent_t e0, e1;
     double copy_gbs = 0;
+    bool prof_enabled = false;
+    unsigned long long* prof_buf = nullptr;
+    double sm_ghz = 1.965;
 };
 
 struct Result {
@@ -173,10 +176,37 @@ static Result run_variant(Env& env, const char* name, bool verify, const LaunchF
         CK(cudaEventElapsedTime(&ms, env.e0, env.e1));
         ms_inplace = ms / env.iters;
     }
-    CK(cudaMemcpy(&status, env.s.status, 4, cudaMemcpyDeviceToHost));
-    if (status) CK(cudaMemset(env.s.status, 0, 4));
+    uint32_t status2 = 0;
+    CK(cudaMemcpy(&status2, env.s.status, 4, cudaMemcpyDeviceToHost));
+    if (status2) CK(cudaMemset(env.s.status, 0, 4));
+    status |= status2;
     const double gkeys = env.n / (r.ms_mean * 1e-3) / 1e9;
     const double gbs = gkeys * bytes_per_key;
+    // one extra launch with the in-kernel profile counters enabled (kernels that support them)
+    double prof_us[kProfFields] = {0};
+    if (env.prof_enabled) {
+        CK(cudaMemset(env.prof_buf, 0, sizeof(unsigned long long) * kProfSlots * kProfFields));
+        env.s.prof = env.prof_buf;
+        fn(env.in, env.out);
+        CK(cudaDeviceSynchronize());
+        env.s.prof = nullptr;
+        std::vector<unsigned long long> h(kProfSlots * kProfFields);
+        CK(cudaMemcpy(h.data(), env.prof_buf, h.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long tot[kProfFields] = {0};
+        for (int r = 0; r < kProfSlots; ++r)
+            for (int f = 0; f < kProfFields; ++f) tot[f] += h[r * kProfFields + f];
+        if (tot[PROF_TILES]) {
+            for (int f = 1; f <= PROF_FINISH; ++f) prof_us[f] = (double)tot[f] / tot[PROF_TILES] / env.sm_ghz / 1e3;
+            prof_us[PROF_WINDOWS] = (double)tot[PROF_WINDOWS] / tot[PROF_TILES];
+            prof_us[PROF_POLLS] = (double)tot[PROF_POLLS] / tot[PROF_TILES];
+            prof_us[PROF_TILES] = (double)tot[PROF_TILES];
+        }
+    }
+    if (prof_us[PROF_TILES] > 0)
+        printf("{\"profile\": \"%s\", \"tiles\": %.0f, \"us_claim\": %.3f, \"us_load\": %.3f, \"us_reduce\": %.3f, "
+               "\"us_lookback\": %.3f, \"us_finish\": %.3f, \"windows\": %.2f, \"polls\": %.2f}\n",
+               name, prof_us[PROF_TILES], prof_us[PROF_CLAIM], prof_us[PROF_LOAD], prof_us[PROF_REDUCE],
+               prof_us[PROF_LOOKBACK], prof_us[PROF_FINISH], prof_us[PROF_WINDOWS], prof_us[PROF_POLLS]);
     printf("{\"variant\": \"%s\", \"n\": %llu, \"ms\": %.5f, \"gkeys_s\": %.2f, \"gb_s\": %.1f, "
            "\"ms_inplace\": %.5f, \"gkeys_s_inplace\": %.2f, \"verified\": %s, \"errors\": %llu, \"watchdog\": %u}\n",
            name, (unsigned long long)env.n, r.ms_mean, gkeys, gbs, ms_inplace,
@@ -197,15 +227,15 @@ static void add_reg(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, 
     });
 }
 
-template <typename T, int NT, int STAGES, bool INCL>
+template <typename T, int NT, int STAGES, bool INCL, int VER = 2>
 static void add_tma(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, int max_ctas)
 {
     char name[96];
-    snprintf(name, sizeof(name), "csdl_tma<%d,S%d>/cta%d", NT, STAGES, max_ctas);
+    snprintf(name, sizeof(name), "csdl_tma%d<%d,S%d>/cta%d", VER, NT, STAGES, max_ctas);
     auto occ = std::make_shared<int>(0);
     v.emplace_back(name, [&env, occ, max_ctas](const void* in, void* out) {
         CarrySpec cs;
-        return launch_csdl_tma<T, NT, STAGES, INCL>(env.s, in, out, env.n, cs, *occ, max_ctas, 0);
+        return launch_csdl_tma<T, NT, STAGES, INCL, VER>(env.s, in, out, env.n, cs, *occ, max_ctas, 0);
     });
 }
 
@@ -245,15 +275,30 @@ static void build_variants(Env& env, std::vector<std::pair<std::string, LaunchFn
     add_reg<T, 512, 2, INCL>(env, v);
     add_reg<T, 384, 4, INCL>(env, v);
     add_reg<T, 1024, 2, INCL>(env, v);
+    add_tma<T, 512, 2, INCL, 1>(env, v, 0);
+    add_tma<T, 512, 3, INCL, 1>(env, v, 0);
+    add_tma<T, 256, 2, INCL, 1>(env, v, 0);
+    add_tma<T, 512, 2, INCL, 3>(env, v, 0);
+    add_tma<T, 512, 3, INCL, 3>(env, v, 0);
+    add_tma<T, 256, 2, INCL, 3>(env, v, 0);
+    add_tma<T, 256, 3, INCL, 3>(env, v, 0);
+    add_tma<T, 256, 4, INCL, 3>(env, v, 0);
+    add_tma<T, 384, 2, INCL, 3>(env, v, 0);
+    add_tma<T, 384, 3, INCL, 3>(env, v, 0);
+    add_tma<T, 1024, 2, INCL, 3>(env, v, 0);
+    add_tma<T, 128, 2, INCL, 3>(env, v, 0);
+    add_tma<T, 128, 3, INCL, 3>(env, v, 0);
     add_tma<T, 256, 3, INCL>(env, v, 0);
     add_tma<T, 256, 4, INCL>(env, v, 0);
+    add_tma<T, 256, 5, INCL>(env, v, 0);
     add_tma<T, 256, 6, INCL>(env, v, 0);
-    add_tma<T, 512, 2, INCL>(env, v, 0);
     add_tma<T, 512, 3, INCL>(env, v, 0);
     add_tma<T, 512, 3, INCL>(env, v, 1);
     add_tma<T, 512, 4, INCL>(env, v, 0);
-    add_tma<T, 1024, 2, INCL>(env, v, 0);
+    add_tma<T, 512, 6, INCL>(env, v, 0);
     add_tma<T, 1024, 3, INCL>(env, v, 0);
+    add_tma<T, 128, 4, INCL>(env, v, 0);
+    add_tma<T, 128, 6, INCL>(env, v, 0);
     add_rts<T, 256, 4, INCL>(env, v);
     add_rts<T, 512, 4, INCL>(env, v);
     add_fallback<T, 256, 4, INCL>(env, v, kNoStall, 64);
@@ -355,21 +400,68 @@ static int run_all(Env& env, const char* filter)
             static int occ = 0;
             run_variant(env, name, true, [&](const void* in, void* out) {
                 CarrySpec cs;
-                return launch_csdl_tma<T, 512, 3, INCL>(env.s, in, out, env.n, cs, occ, 0, 0);
+                return launch_csdl_tma<T, 512, 3, INCL, 2>(env.s, in, out, env.n, cs, occ, 0, 0);
             });
         }
         env.s.poll_sleep_ns = 0;
-        env.s.flags = PF_DESC_RELAXED;
-        run_variant(env, "knob/csdl_reg<256,4>/relaxed", true, [&](const void* in, void* out) {
-            CarrySpec cs;
-            return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
-        });
-        static int occ2 = 0;
-        run_variant(env, "knob/csdl_tma<512,S3>/relaxed", true, [&](const void* in, void* out) {
-            CarrySpec cs;
-            return launch_csdl_tma<T, 512, 3, INCL>(env.s, in, out, env.n, cs, occ2, 0, 0);
-        });
+        struct { const char* name; uint32_t flags; } protos[] = {
+            {"st_release+ld_acquire", PF_PUBLISH_ST_RELEASE | PF_POLL_ACQUIRE},
+            {"st_relaxed+ld_relaxed", PF_PUBLISH_ST_RELAXED},
+            {"atom_exch+ld_acquire", PF_POLL_ACQUIRE},
+            {"atom_exch+ld_volatile", PF_POLL_VOLATILE},
+            {"atom_exch+ld_relaxed", 0},
+        };
+        static int occ2 = 0, occ3 = 0;
+        for (auto& pr : protos) {
+            env.s.flags = pr.flags;
+            char name[96];
+            snprintf(name, sizeof(name), "knob/csdl_reg<256,4>/%s", pr.name);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
+            });
+            snprintf(name, sizeof(name), "knob/csdl_tma2<512,S3>/%s", pr.name);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_tma<T, 512, 3, INCL, 2>(env.s, in, out, env.n, cs, occ2, 0, 0);
+            });
+            snprintf(name, sizeof(name), "knob/csdl_tma2<256,S3>/%s", pr.name);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_tma<T, 256, 3, INCL, 2>(env.s, in, out, env.n, cs, occ3, 0, 0);
+            });
+        }
         env.s.flags = 0;
+    }
+    // experiments on the register path (some produce WRONG results on purpose: not verified)
+    if (wanted("exp")) {
+        struct { const char* name; uint32_t flags; bool verify; } exps[] = {
+            {"exp/reg<256,4>/static_tile", PF_STATIC_TILE, true},
+            {"exp/reg<256,4>/skip_lookback", PF_SKIP_LOOKBACK, false},
+            {"exp/reg<256,4>/static_tile+skip_lookback", PF_STATIC_TILE | PF_SKIP_LOOKBACK, false},
+            {"exp/reg<256,4>/fence_all", PF_FENCE_ALL, true},
+            {"exp/reg<256,4>/ld_allocate", PF_LD_ALLOCATE, true},
+        };
+        for (auto& ex : exps) {
+            env.s.flags = ex.flags;
+            run_variant(env, ex.name, ex.verify, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
+            });
+        }
+        env.s.flags = 0;
+        for (uint32_t ns : {500u, 1000u, 2000u}) {
+            env.s.flags = PF_DELAY_FIRST;
+            env.s.poll_sleep_ns = ns;
+            char name[96];
+            snprintf(name, sizeof(name), "exp/reg<256,4>/delay_first%u", ns);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
+            });
+        }
+        env.s.flags = 0;
+        env.s.poll_sleep_ns = 0;
     }
     return bad;
 }
@@ -384,6 +476,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--iters") && i + 1 < argc) env.iters = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--filter") && i + 1 < argc) filter = argv[++i];
         else if (!strcmp(argv[i], "--float")) env.is_float = true;
+        else if (!strcmp(argv[i], "--prof")) env.prof_enabled = true;
         else if (!strcmp(argv[i], "--exclusive")) env.exclusive = true;
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
@@ -407,6 +500,8 @@ int main(int argc, char** argv)
     env.s.status = env.s.counter + 1;
     env.tma_copy_counter = env.s.counter + 8;
     CK(cudaMalloc(&env.s.partials, kMaxParts * 4));
+    CK(cudaMalloc(&env.prof_buf, sizeof(unsigned long long) * kProfSlots * kProfFields));
+    env.sm_ghz = prop.clockRate / 1e6;
     CK(cudaEventCreate(&env.e0));
     CK(cudaEventCreate(&env.e1));
     if (env.is_float)
