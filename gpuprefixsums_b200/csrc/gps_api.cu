@@ -106,10 +106,10 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
         }
         switch (algo) {
             case GPS_ALGO_CSDL_REG:
-                e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL>(c->s, in, out, n, cs, st);
+                e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 break;
             case GPS_ALGO_CSDL_TMA:
-                e = launch_csdl_tma<T, GPS_TMA_NT, GPS_TMA_STAGES, INCL>(
+                e = launch_csdl_tma<T, GPS_TMA_NT, GPS_TMA_STAGES, INCL, GPS_LOOKBACK_WIN>(
                     c->s, in, out, n, cs, c->tma_ctas_per_sm[dt_index<T>()][INCL ? 0 : 1],
                     GPS_TMA_MAX_CTAS_PER_SM, st);
                 break;
@@ -287,6 +287,19 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     if (!strcmp(key, "csdl_variant")) {
         if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..2");
         c->csdl_variant = (int)value;
+    } else if (!strcmp(key, "tile_order")) {
+        // 0 = atomic ticket (default: provably deadlock-free), 1 = blockIdx.x (what
+        // cub::DeviceScan relies on: CTAs are dispatched in index order); register path only
+        if (value != 0 && value != 1) return fail(GPS_ERR_INVALID, "tile_order must be 0 or 1");
+        c->s.flags = (c->s.flags & ~PF_STATIC_TILE) | (value ? PF_STATIC_TILE : 0u);
+    } else if (!strcmp(key, "desc_protocol")) {
+        // 0 = atom.exch + ld.relaxed (default), 1 = st.release.gpu + ld.acquire.gpu,
+        // 2 = st.relaxed + ld.relaxed  (see gps_common.cuh for the measured cost of each)
+        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "desc_protocol must be 0..2");
+        const uint32_t mask = PF_PUBLISH_ST_RELEASE | PF_PUBLISH_ST_RELAXED | PF_POLL_ACQUIRE;
+        const uint32_t bits = value == 1 ? (PF_PUBLISH_ST_RELEASE | PF_POLL_ACQUIRE)
+                            : value == 2 ? PF_PUBLISH_ST_RELAXED : 0u;
+        c->s.flags = (c->s.flags & ~mask) | bits;
     } else if (!strcmp(key, "poll_sleep_ns")) {
         if (value < 0 || value > 100000) return fail(GPS_ERR_INVALID, "poll_sleep_ns out of range");
         c->s.poll_sleep_ns = (uint32_t)value;

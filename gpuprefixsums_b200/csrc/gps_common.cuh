@@ -78,11 +78,14 @@ enum : uint32_t {
     PF_PUBLISH_ST_RELAXED = 64u, // publish with st.relaxed.gpu
     PF_DELAY_FIRST = 128u,       // experiment: nanosleep(poll_sleep_ns) once before the first poll
     PF_POLL_ACQUIRE = 256u,      // poll with ld.acquire.gpu (else ld.relaxed.gpu)
+    PF_LOOKBACK_WAIT_ALL = 512u, // experiment: consume a window only when all 32 are ready
 };
 
 enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
 enum : uint32_t { STATUS_WATCHDOG = 1u };
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
+// CTAs per SM the scan kernels are compiled for: as many as fit at `regs` registers/thread
+constexpr int min_ctas_per_sm(int nt, int regs = 40) { return 65536 / (nt * regs) > 0 ? 65536 / (nt * regs) : 1; }
 constexpr uint32_t kWatchdogPolls = 1u << 22;  // * ~0.5 us per poll => seconds, then bail out
 
 // ---------------------------------------------------------------------------------
@@ -288,14 +291,42 @@ __device__ __forceinline__ uint32_t lane_id()
     return l;
 }
 
+// One Kogge-Stone step, branch-free: v += (value of lane - d) for lanes >= d.  The add is
+// predicated on the shuffle's own in-range predicate in PTX.  (Written as
+// `t = __shfl_up_sync(..); if (lane >= d) v += t;` nvcc 12.9 turns the condition into a
+// BRANCH around the shuffles and pays WARPSYNC.COLLECTIVE / BRA.DIV sequences for every
+// one of them: 536 SASS instructions per warp on the tile path instead of ~200.)
+__device__ __forceinline__ uint32_t scan_step_up(uint32_t v, int d)
+{
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .u32 t;\n\t.reg .pred q;\n\t"
+        "shfl.sync.up.b32 t|q, %1, %2, 0, 0xffffffff;\n\t"
+        "@q add.u32 t, t, %1;\n\t"
+        "mov.u32 %0, t;\n\t}"
+        : "=r"(r)
+        : "r"(v), "r"(d));
+    return r;
+}
+__device__ __forceinline__ float scan_step_up(float v, int d)
+{
+    float r;
+    asm volatile(
+        "{\n\t.reg .f32 t;\n\t.reg .pred q;\n\t"
+        "shfl.sync.up.b32 t|q, %1, %2, 0, 0xffffffff;\n\t"
+        "@q add.f32 t, t, %1;\n\t"
+        "mov.f32 %0, t;\n\t}"
+        : "=f"(r)
+        : "f"(v), "r"(d));
+    return r;
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_inclusive_scan(T v, uint32_t lane)
 {
+    (void)lane;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const T t = __shfl_up_sync(kFullMask, v, d);
-        if (lane >= (uint32_t)d) v += t;
-    }
+    for (int d = 1; d < 32; d <<= 1) v = scan_step_up(v, d);
     return v;
 }
 
@@ -312,12 +343,17 @@ __device__ __forceinline__ T warp_exclusive_of(T inc, T raw, uint32_t lane)
     }
 }
 
+// warp sum, result in every lane.  uint32: one REDUX.SUM (sm_80+); float: xor butterfly
 template <typename T>
 __device__ __forceinline__ T warp_reduce(T v)
 {
+    if constexpr (std::is_same<T, uint32_t>::value) {
+        return __reduce_add_sync(kFullMask, v);
+    } else {
 #pragma unroll
-    for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(kFullMask, v, m);
-    return v;
+        for (int m = 16; m; m >>= 1) v += __shfl_xor_sync(kFullMask, v, m);
+        return v;
+    }
 }
 
 // Block-level exclusive scan of the per-warp totals held in s_warp[NW] (NW <= 32):
@@ -414,7 +450,9 @@ struct LookbackStats {
     uint32_t polls = 0;    // polls that found the nearest tile not ready
 };
 
-template <typename T>
+// WIN = descriptor windows (of 32 tiles) fetched per round trip: the WIN loads of a lane
+// are issued back to back, so one L2 round trip covers 32*WIN predecessors.
+template <typename T, int WIN = 2>
 __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, uint32_t lane,
                                            LookbackStats* stats = nullptr)
 {
@@ -422,35 +460,54 @@ __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, u
     int64_t top = (int64_t)tile - 1;
     uint32_t polls = 0, windows = 0;
     if ((p.flags & PF_DELAY_FIRST) && p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
+    const bool wait_all = p.flags & PF_LOOKBACK_WAIT_ALL;
     while (true) {
-        const int64_t idx = top - (int64_t)lane;
-        uint64_t d = pack_desc(0u, p.epoch, ST_INCLUSIVE);
-        bool ready = true;
-        if (idx >= 0) {
-            d = desc_poll(p, p.desc + idx);
-            ready = desc_valid(d, p.epoch);
+        uint64_t d[WIN];
+        bool ready[WIN];
+#pragma unroll
+        for (int w = 0; w < WIN; ++w) {
+            const int64_t idx = top - 32 * w - (int64_t)lane;
+            d[w] = pack_desc(0u, p.epoch, ST_INCLUSIVE);  // virtual entry below tile 0
+            ready[w] = true;
+            if (idx >= 0) {
+                d[w] = desc_poll(p, p.desc + idx);
+                ready[w] = desc_valid(d[w], p.epoch);
+            }
         }
         // consume the run of ready descriptors nearest to this tile; an INCLUSIVE one in
         // that run ends the walk no matter what farther tiles are doing
-        const uint32_t not_ready = __ballot_sync(kFullMask, !ready);
-        const uint32_t run = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
-        if (run == 0u) {
+        uint32_t consumed = 0;
+        bool done = false;
+#pragma unroll
+        for (int w = 0; w < WIN; ++w) {
+            const uint32_t not_ready = __ballot_sync(kFullMask, !ready[w]);
+            const uint32_t run = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
+            const uint32_t in_run = run >= 32u ? kFullMask : ((1u << run) - 1u);
+            const uint32_t incl =
+                __ballot_sync(kFullMask, ready[w] && desc_status(d[w]) == ST_INCLUSIVE) & in_run;
+            const T v = from_bits<T>(desc_value(d[w]));
+            if (incl) {
+                const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
+                prefix += warp_reduce(lane <= nearest ? v : T(0));
+                done = true;
+                break;
+            }
+            if (run < 32u && wait_all) break;  // reference behaviour: all 32 or nothing
+            if (run) {
+                prefix += warp_reduce(lane < run ? v : T(0));
+                consumed += run;
+            }
+            if (run < 32u) break;
+        }
+        windows += (consumed + 31u) / 32u + (done ? 1u : 0u);
+        if (done) break;
+        if (consumed == 0u) {
             const bool bail = watchdog_tick(polls, p.status);
             if (__any_sync(kFullMask, bail)) break;  // warp-uniform exit
             if (p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
             continue;
         }
-        ++windows;
-        const uint32_t in_run = run >= 32u ? kFullMask : ((1u << run) - 1u);
-        const T v = from_bits<T>(desc_value(d));
-        const uint32_t incl = __ballot_sync(kFullMask, ready && desc_status(d) == ST_INCLUSIVE) & in_run;
-        if (incl) {
-            const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
-            prefix += warp_reduce(lane <= nearest ? v : T(0));
-            break;
-        }
-        prefix += warp_reduce(lane < run ? v : T(0));
-        top -= (int64_t)run;
+        top -= (int64_t)consumed;
     }
     if (stats) {
         stats->windows = windows;

@@ -4,11 +4,19 @@
 #pragma once
 
 // CSDL register path: NT threads, V uint4 per thread -> tile = NT * V * 4 keys
+// Measured at 2^28 uint32 keys on B200 (profiles/r01_tune_sweep.txt): <128,12> 785-803,
+// <128,10> 796, <64,24> 782-812, <128,16> 782-790, <256,8> 752, <256,4> (the reference's
+// shape) 662 Gkeys/s.  24 KB tiles, 7 CTAs/SM -> 168 KB of loads in flight per SM.
 #ifndef GPS_REG_NT
-#define GPS_REG_NT 256
+#define GPS_REG_NT 128
 #endif
 #ifndef GPS_REG_V
-#define GPS_REG_V 4
+#define GPS_REG_V 12
+#endif
+// look-back windows (32 descriptors each) fetched per L2 round trip: 1 beat 2 and 4
+// (803 / 757 / 530 Gkeys/s on <128,12> resp. <256,4>): the nearest tiles decide
+#ifndef GPS_LOOKBACK_WIN
+#define GPS_LOOKBACK_WIN 1
 #endif
 
 // CSDL TMA path: NT threads x 16 keys per tile, STAGES shared-memory tile buffers
@@ -16,7 +24,7 @@
 #define GPS_TMA_NT 512
 #endif
 #ifndef GPS_TMA_STAGES
-#define GPS_TMA_STAGES 3
+#define GPS_TMA_STAGES 2
 #endif
 // 0 = as many CTAs per SM as fit
 #ifndef GPS_TMA_MAX_CTAS_PER_SM
@@ -28,10 +36,11 @@
 #define GPS_RTS_NT 256
 #endif
 #ifndef GPS_RTS_V
-#define GPS_RTS_V 4
+#define GPS_RTS_V 8
 #endif
 
-// GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA path
+// GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA path.  Chosen by measurement:
+// register path 785-803 Gkeys/s vs TMA ring 659 Gkeys/s at 2^28 keys
 #ifndef GPS_CSDL_DEFAULT_VARIANT
 #define GPS_CSDL_DEFAULT_VARIANT 1
 #endif

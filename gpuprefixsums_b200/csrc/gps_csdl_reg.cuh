@@ -13,8 +13,9 @@ namespace gps {
 // ---------------------------------------------------------------------------------
 // CSDL, register path
 // ---------------------------------------------------------------------------------
-template <typename T, int NT, int V, bool INCLUSIVE>
-__global__ void __launch_bounds__(NT) csdl_reg_kernel(const __grid_constant__ ScanParams p)
+// WIN: look-back windows per round trip; PROF: compile the phase timers in (tuning only)
+template <typename T, int NT, int V, bool INCLUSIVE, int WIN = 2, bool PROF = false>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 24 + 4 * V)) csdl_reg_kernel(const __grid_constant__ ScanParams p)
 {
     using Tile = RegTile<T, NT, V>;
     constexpr int NW = Tile::NW;
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(NT) csdl_reg_kernel(const __grid_constant__ Sc
 
     long long tprof[6] = {0, 0, 0, 0, 0, 0};
     LookbackStats lbs;
-    const bool profiler = p.prof != nullptr && threadIdx.x == 0;
+    const bool profiler = PROF && p.prof != nullptr && threadIdx.x == 0;
     if (profiler) tprof[0] = clock64();
     uint32_t tile;
     if (p.flags & PF_STATIC_TILE) {
@@ -47,25 +48,31 @@ __global__ void __launch_bounds__(NT) csdl_reg_kernel(const __grid_constant__ Sc
         t.load_full(p.in, vbase, allocate);
     else
         t.load_partial(p.in, vbase, p.n);
-    t.scan_warp(lane);
-    if (lane == 0) s_warp[warp] = t.warp_total;
+    // Aggregate first: every tile that is claimed but not yet published is a hole all later
+    // tiles spin on, so the sum takes the shortest path -- thread sums, one REDUX per warp,
+    // one barrier, one REDUX -- and is published BEFORE the V row scans the outputs need.
+    const T wsum = warp_reduce(t.thread_sum());
+    if (lane == 0) s_warp[warp] = wsum;
     __syncthreads();
 
     if (profiler) tprof[2] = clock64();
-    T warp_prefix, aggregate;
-    block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, aggregate);
+    const T wraw = lane < (uint32_t)NW ? s_warp[lane] : T(0);
+    const T aggregate = warp_reduce(wraw);
+    if (warp == 0 && lane == 0 && tile != 0)
+        desc_publish(p, p.desc + tile, pack_desc(to_bits(aggregate), p.epoch, ST_AGGREGATE));
+    if (profiler) tprof[3] = clock64();
+
+    // scan work that does not need the tile prefix
+    const T winc = warp_inclusive_scan(wraw, lane);
+    const T warp_prefix = __shfl_sync(kFullMask, warp_exclusive_of(winc, wraw, lane), (int)warp);
+    t.scan_warp(lane);
 
     if (warp == 0) {
         T prefix;
-        if (tile == 0) {
+        if (tile == 0)
             prefix = acquire_carry<T>(p, lane);
-            if (profiler) tprof[3] = clock64();
-        } else {
-            if (lane == 0)
-                desc_publish(p, p.desc + tile, pack_desc(to_bits(aggregate), p.epoch, ST_AGGREGATE));
-            if (profiler) tprof[3] = clock64();
-            prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T>(p, tile, lane, &lbs);
-        }
+        else
+            prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T, WIN>(p, tile, lane, PROF ? &lbs : nullptr);
         if (profiler) tprof[4] = clock64();
         if (lane == 0) {
             const T inclusive = prefix + aggregate;
@@ -101,7 +108,7 @@ constexpr uint32_t kNoStall = 0xFFFFFFFFu;
 enum : uint32_t { LB_DONE = 0, LB_FALLBACK = 1 };
 
 template <typename T, int NT, int V, bool INCLUSIVE>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
     csdl_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
 {
     using Tile = RegTile<T, NT, V>;
@@ -127,12 +134,14 @@ __global__ void __launch_bounds__(NT)
         t.load_full(p.in, vbase);
     else
         t.load_partial(p.in, vbase, p.n);
-    t.scan_warp(lane);
-    if (lane == 0) s_warp[warp] = t.warp_total;
+    // aggregate first (see csdl_reg_kernel), row scans afterwards
+    const T wsum = warp_reduce(t.thread_sum());
+    if (lane == 0) s_warp[warp] = wsum;
     __syncthreads();
-
-    T warp_prefix, aggregate;
-    block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, aggregate);
+    const T wraw = lane < (uint32_t)NW ? s_warp[lane] : T(0);
+    const T aggregate = warp_reduce(wraw);
+    const T winc = warp_inclusive_scan(wraw, lane);
+    const T warp_prefix = __shfl_sync(kFullMask, warp_exclusive_of(winc, wraw, lane), (int)warp);
 
     // Stall emulation (EmulatedDeadlocking.cuh:63-72): the tile refuses to publish until
     // some successor's fallback has published for it.  The last tile never stalls: it
@@ -152,16 +161,18 @@ __global__ void __launch_bounds__(NT)
             // overwrite (same value for uint32; for float32 the recomputed aggregate may
             // differ in the last bits -- both are within the stated tolerance)
             const T v = tile ? aggregate : carry + aggregate;
-            st_release_gpu(p.desc + tile,
-                           pack_desc(to_bits(v), p.epoch, tile ? ST_AGGREGATE : ST_INCLUSIVE));
+            atomicExch(reinterpret_cast<unsigned long long*>(p.desc + tile),
+                       (unsigned long long)pack_desc(to_bits(v), p.epoch, tile ? ST_AGGREGATE : ST_INCLUSIVE));
             // In-place safety of the fallback: a successor may be re-reading this tile's
-            // INPUT right now.  The descriptor must be visible before any thread of this
-            // CTA overwrites the input with outputs, so that successor's CAS then fails
-            // and it discards what it read.  (fence + the __syncthreads below.)
+            // INPUT right now.  The descriptor must be performed at L2 before any thread of
+            // this CTA overwrites the input with outputs, so that successor's CAS then
+            // fails and it discards what it read.  (fence + the __syncthreads below.)
             __threadfence();
         }
     }
+    if (!stalled) t.scan_warp(lane);  // overlaps thread 0's publish
     __syncthreads();  // holds the whole block while stalled ("purely for emulation")
+    if (stalled) t.scan_warp(lane);
 
     uint32_t n_spins = 0, n_fallbacks = 0, n_inserts = 0, n_windows = 0;
     T prefix = carry;  // tile 0: done
@@ -283,7 +294,8 @@ __global__ void __launch_bounds__(NT)
     if (warp == 0 && lane == 0) {
         const T inclusive = prefix + aggregate;
         if (tile != 0)
-            st_release_gpu(p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
+            atomicExch(reinterpret_cast<unsigned long long*>(p.desc + tile),
+                       (unsigned long long)pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
         s_prefix = prefix;
         if (tile == p.num_tiles - 1) write_total<T>(p, inclusive);
         if (f.stats) {

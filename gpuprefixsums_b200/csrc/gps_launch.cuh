@@ -91,13 +91,13 @@ cudaError_t launch_carry_only(Scratch& s, const CarrySpec& cs, cudaStream_t st)
 }
 
 // ---- CSDL register path --------------------------------------------------------------
-template <typename T, int NT, int V, bool INCL>
+template <typename T, int NT, int V, bool INCL, int WIN = 2, bool PROF = false>
 cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
                             cudaStream_t st)
 {
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
-    csdl_reg_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p);
+    csdl_reg_kernel<T, NT, V, INCL, WIN, PROF><<<p.num_tiles, NT, 0, st>>>(p);
     if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
     return cudaGetLastError();
 }
@@ -105,19 +105,12 @@ cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, c
 // ---- CSDL TMA path -------------------------------------------------------------------
 // ctas_per_sm: in/out cache (0 = query occupancy and opt in to the dynamic smem size);
 // max_ctas_per_sm: 0 = as many as fit
-// VER: 1 = tile-at-a-time kernel, 2 = aggregate-ahead software pipeline, 3 = early refill
-template <typename T, int NT, int STAGES, bool INCL, int VER = 2>
+template <typename T, int NT, int STAGES, bool INCL, int WIN = 2, bool PROF = false>
 cudaError_t launch_csdl_tma(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
                             int& ctas_per_sm, int max_ctas_per_sm, cudaStream_t st)
 {
     using Cfg = TmaCfg<NT, STAGES>;
-    void (*kern)(const ScanParams);
-    if constexpr (VER == 1)
-        kern = csdl_tma_kernel<T, NT, STAGES, INCL>;
-    else if constexpr (VER == 3)
-        kern = csdl_tma3_kernel<T, NT, STAGES, INCL>;
-    else
-        kern = csdl_tma2_kernel<T, NT, STAGES, INCL>;
+    auto kern = csdl_tma_kernel<T, NT, STAGES, INCL, WIN, PROF>;
     if (ctas_per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Cfg::RING_BYTES);

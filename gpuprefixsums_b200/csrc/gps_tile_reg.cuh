@@ -88,10 +88,7 @@ struct RegTile {
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                const T t = __shfl_up_sync(kFullMask, inc[k], d);
-                if (lane >= (uint32_t)d) inc[k] += t;
-            }
+            for (int k = 0; k < V; ++k) inc[k] = scan_step_up(inc[k], d);
         }
         T run = T(0);
 #pragma unroll

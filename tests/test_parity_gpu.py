@@ -203,10 +203,14 @@ def test_2p28_random_vs_cub_and_properties(gps, ps, oracle):
         del exc
 
 
+REF_RTS_MAX_KEYS = 129 * 4096  # largest size the reference RTS gets right, see test_reference_rts_spine_bug
+
+
 def test_reference_cuda_kernels_agree(gps, ps, oracle, ref_shim):
     """The reference's own CUDA scans (unmodified, rebuilt for sm_100a) on the same input.
-    Reference CSDL packs a 30-bit aggregate, so it is only exact while the grand total is
-    below 2^30 (keys in [0,4) at 2^26); RTS and CUB are exact mod 2^32."""
+    Reference CSDL / EmulatedDeadlock pack a 30-bit aggregate, so they are only exact while
+    the grand total is below 2^30 (keys in [0,4) at 2^26); CUB is exact mod 2^32; reference
+    RTS is only correct up to 129 tiles (its SpineScan bug, next test)."""
     n = 1 << 26
     small = torch.empty(n, dtype=torch.int32, device="cuda")
     gps.init_random(small, seed=7, mask=3)
@@ -216,13 +220,13 @@ def test_reference_cuda_kernels_agree(gps, ps, oracle, ref_shim):
         mine_small = ps.scan(small, algo="csdl", exclusive=exclusive)
         mine_full = ps.scan(full, algo="csdl", exclusive=exclusive)
         ps.check()
-        for algo, data, mine in [(ref_shim.CSDL, small, mine_small), (ref_shim.RTS, small, mine_small),
-                                 (ref_shim.RTS, full, mine_full), (ref_shim.CUB, full, mine_full)]:
-            work = data.clone()
+        for algo, data, mine, count in [(ref_shim.CSDL, small, mine_small, n), (ref_shim.CUB, full, mine_full, n),
+                                        (ref_shim.RTS, full, mine_full, REF_RTS_MAX_KEYS)]:
+            work = data[:count].clone()
             torch.cuda.synchronize()
-            assert ref_shim.scan_u32(algo, exclusive, work.data_ptr(), n) == 0
+            assert ref_shim.scan_u32(algo, exclusive, work.data_ptr(), count) == 0
             torch.cuda.synchronize()
-            assert gps.compare_u32(mine, work) == (0, n), (algo, exclusive)
+            assert gps.compare_u32(mine[:count], work) == (0, count), (algo, exclusive)
     # emulated deadlock (inclusive only in the reference)
     work = small.clone()
     torch.cuda.synchronize()
@@ -231,6 +235,33 @@ def test_reference_cuda_kernels_agree(gps, ps, oracle, ref_shim):
     mine = ps.scan_emulated_deadlock(small, stall_mask=7, max_spin=4)
     ps.check()
     assert gps.compare_u32(mine, work) == (0, n)
+
+
+def test_reference_rts_spine_bug(gps, ps, oracle, ref_shim):
+    """Documents a defect of the reference found while pinning the oracle: its RTS SpineScan
+    adds s_red[WARPS - 1] (the total of ALL warps) instead of the preceding warps' total to
+    every warp but the first (ReduceThenScan.cuh:92-93).  Spine entries of tiles >= 128 are
+    therefore wrong (entry 128 is only right when it is the last one), and every key from
+    tile 129 on comes out wrong: ReduceThenScan fails for n > 129 * 4096 = 528,384 keys.  The reference's own tests never see it: its large cases only
+    validate the first 26..28 elements (ReduceThenScanDispatcher.cuh:58-61).  The oracle, the
+    reference CSDL, cub::DeviceScan and every kernel of this repo agree with each other."""
+    n = 131 * 4096
+    x = torch.empty(n, dtype=torch.int32, device="cuda")
+    gps.init_ones(x)
+    work = x.clone()
+    torch.cuda.synchronize()
+    assert ref_shim.scan_u32(ref_shim.RTS, False, work.data_ptr(), n) == 0
+    torch.cuda.synchronize()
+    assert gps.validate_ones(work, False) > 0            # reference RTS: wrong
+    assert gps.validate_ones(work[:REF_RTS_MAX_KEYS], False) == 0
+    mine = ps.scan(x, algo="rts")
+    ps.check()
+    assert gps.validate_ones(mine, False) == 0           # ours: right
+    work = x.clone()
+    torch.cuda.synchronize()
+    assert ref_shim.scan_u32(ref_shim.CSDL, False, work.data_ptr(), n) == 0
+    torch.cuda.synchronize()
+    assert gps.validate_ones(work, False) == 0           # reference CSDL: right
 
 
 def test_float_2p28_tolerance(gps, ps, oracle):

@@ -216,26 +216,30 @@ static Result run_variant(Env& env, const char* name, bool verify, const LaunchF
     return r;
 }
 
-template <typename T, int NT, int V, bool INCL>
+template <typename T, int NT, int V, bool INCL, int WIN = 2>
 static void add_reg(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, const char* suffix = "")
 {
     char name[96];
-    snprintf(name, sizeof(name), "csdl_reg<%d,%d>%s", NT, V, suffix);
+    snprintf(name, sizeof(name), "csdl_reg<%d,%d>/w%d%s", NT, V, WIN, suffix);
     v.emplace_back(name, [&env](const void* in, void* out) {
         CarrySpec cs;
-        return launch_csdl_reg<T, NT, V, INCL>(env.s, in, out, env.n, cs, 0);
+        if (env.s.prof) return launch_csdl_reg<T, NT, V, INCL, WIN, true>(env.s, in, out, env.n, cs, 0);
+        return launch_csdl_reg<T, NT, V, INCL, WIN, false>(env.s, in, out, env.n, cs, 0);
     });
 }
 
-template <typename T, int NT, int STAGES, bool INCL, int VER = 2>
+template <typename T, int NT, int STAGES, bool INCL, int WIN = 2>
 static void add_tma(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, int max_ctas)
 {
     char name[96];
-    snprintf(name, sizeof(name), "csdl_tma%d<%d,S%d>/cta%d", VER, NT, STAGES, max_ctas);
+    snprintf(name, sizeof(name), "csdl_tma<%d,S%d>/w%d/cta%d", NT, STAGES, WIN, max_ctas);
     auto occ = std::make_shared<int>(0);
-    v.emplace_back(name, [&env, occ, max_ctas](const void* in, void* out) {
+    auto occp = std::make_shared<int>(0);
+    v.emplace_back(name, [&env, occ, occp, max_ctas](const void* in, void* out) {
         CarrySpec cs;
-        return launch_csdl_tma<T, NT, STAGES, INCL, VER>(env.s, in, out, env.n, cs, *occ, max_ctas, 0);
+        if (env.s.prof)
+            return launch_csdl_tma<T, NT, STAGES, INCL, WIN, true>(env.s, in, out, env.n, cs, *occp, max_ctas, 0);
+        return launch_csdl_tma<T, NT, STAGES, INCL, WIN, false>(env.s, in, out, env.n, cs, *occ, max_ctas, 0);
     });
 }
 
@@ -266,41 +270,30 @@ static void add_fallback(Env& env, std::vector<std::pair<std::string, LaunchFn>>
 template <typename T, bool INCL>
 static void build_variants(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v)
 {
-    add_reg<T, 256, 4, INCL>(env, v);
-    add_reg<T, 128, 4, INCL>(env, v);
-    add_reg<T, 128, 8, INCL>(env, v);
-    add_reg<T, 256, 2, INCL>(env, v);
-    add_reg<T, 256, 8, INCL>(env, v);
-    add_reg<T, 512, 4, INCL>(env, v);
-    add_reg<T, 512, 2, INCL>(env, v);
-    add_reg<T, 384, 4, INCL>(env, v);
-    add_reg<T, 1024, 2, INCL>(env, v);
+    add_reg<T, 256, 4, INCL, 1>(env, v);
+    add_reg<T, 256, 8, INCL, 1>(env, v);
+    add_reg<T, 128, 10, INCL, 1>(env, v);
+    add_reg<T, 128, 12, INCL, 1>(env, v);
+    add_reg<T, 128, 16, INCL, 1>(env, v);
+    add_reg<T, 96, 16, INCL, 1>(env, v);
+    add_reg<T, 96, 20, INCL, 1>(env, v);
+    add_reg<T, 64, 16, INCL, 1>(env, v);
+    add_reg<T, 64, 20, INCL, 1>(env, v);
+    add_reg<T, 64, 24, INCL, 1>(env, v);
+    add_reg<T, 64, 28, INCL, 1>(env, v);
+    add_reg<T, 64, 32, INCL, 1>(env, v);
+    add_reg<T, 32, 24, INCL, 1>(env, v);
+    add_reg<T, 32, 32, INCL, 1>(env, v);
+    add_reg<T, 32, 40, INCL, 1>(env, v);
     add_tma<T, 512, 2, INCL, 1>(env, v, 0);
-    add_tma<T, 512, 3, INCL, 1>(env, v, 0);
     add_tma<T, 256, 2, INCL, 1>(env, v, 0);
-    add_tma<T, 512, 2, INCL, 3>(env, v, 0);
-    add_tma<T, 512, 3, INCL, 3>(env, v, 0);
-    add_tma<T, 256, 2, INCL, 3>(env, v, 0);
-    add_tma<T, 256, 3, INCL, 3>(env, v, 0);
-    add_tma<T, 256, 4, INCL, 3>(env, v, 0);
-    add_tma<T, 384, 2, INCL, 3>(env, v, 0);
-    add_tma<T, 384, 3, INCL, 3>(env, v, 0);
-    add_tma<T, 1024, 2, INCL, 3>(env, v, 0);
-    add_tma<T, 128, 2, INCL, 3>(env, v, 0);
-    add_tma<T, 128, 3, INCL, 3>(env, v, 0);
-    add_tma<T, 256, 3, INCL>(env, v, 0);
-    add_tma<T, 256, 4, INCL>(env, v, 0);
-    add_tma<T, 256, 5, INCL>(env, v, 0);
-    add_tma<T, 256, 6, INCL>(env, v, 0);
-    add_tma<T, 512, 3, INCL>(env, v, 0);
-    add_tma<T, 512, 3, INCL>(env, v, 1);
-    add_tma<T, 512, 4, INCL>(env, v, 0);
-    add_tma<T, 512, 6, INCL>(env, v, 0);
-    add_tma<T, 1024, 3, INCL>(env, v, 0);
-    add_tma<T, 128, 4, INCL>(env, v, 0);
-    add_tma<T, 128, 6, INCL>(env, v, 0);
+    add_tma<T, 384, 2, INCL, 1>(env, v, 0);
+    add_tma<T, 768, 2, INCL, 1>(env, v, 0);
     add_rts<T, 256, 4, INCL>(env, v);
     add_rts<T, 512, 4, INCL>(env, v);
+    add_rts<T, 256, 8, INCL>(env, v);
+    add_rts<T, 128, 8, INCL>(env, v);
+    add_rts<T, 128, 16, INCL>(env, v);
     add_fallback<T, 256, 4, INCL>(env, v, kNoStall, 64);
     add_fallback<T, 256, 4, INCL>(env, v, kNoStall, 4);
     add_fallback<T, 256, 4, INCL>(env, v, 7, 4);
@@ -396,11 +389,11 @@ static int run_all(Env& env, const char* filter)
                 CarrySpec cs;
                 return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
             });
-            snprintf(name, sizeof(name), "knob/csdl_tma<512,S3>/sleep%u", sleep_ns);
+            snprintf(name, sizeof(name), "knob/csdl_tma<512,S2>/sleep%u", sleep_ns);
             static int occ = 0;
             run_variant(env, name, true, [&](const void* in, void* out) {
                 CarrySpec cs;
-                return launch_csdl_tma<T, 512, 3, INCL, 2>(env.s, in, out, env.n, cs, occ, 0, 0);
+                return launch_csdl_tma<T, 512, 2, INCL>(env.s, in, out, env.n, cs, occ, 0, 0);
             });
         }
         env.s.poll_sleep_ns = 0;
@@ -420,15 +413,15 @@ static int run_all(Env& env, const char* filter)
                 CarrySpec cs;
                 return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
             });
-            snprintf(name, sizeof(name), "knob/csdl_tma2<512,S3>/%s", pr.name);
+            snprintf(name, sizeof(name), "knob/csdl_tma<512,S2>/%s", pr.name);
             run_variant(env, name, true, [&](const void* in, void* out) {
                 CarrySpec cs;
-                return launch_csdl_tma<T, 512, 3, INCL, 2>(env.s, in, out, env.n, cs, occ2, 0, 0);
+                return launch_csdl_tma<T, 512, 2, INCL>(env.s, in, out, env.n, cs, occ2, 0, 0);
             });
-            snprintf(name, sizeof(name), "knob/csdl_tma2<256,S3>/%s", pr.name);
+            snprintf(name, sizeof(name), "knob/csdl_tma<256,S2>/%s", pr.name);
             run_variant(env, name, true, [&](const void* in, void* out) {
                 CarrySpec cs;
-                return launch_csdl_tma<T, 256, 3, INCL, 2>(env.s, in, out, env.n, cs, occ3, 0, 0);
+                return launch_csdl_tma<T, 256, 2, INCL>(env.s, in, out, env.n, cs, occ3, 0, 0);
             });
         }
         env.s.flags = 0;
@@ -436,6 +429,7 @@ static int run_all(Env& env, const char* filter)
     // experiments on the register path (some produce WRONG results on purpose: not verified)
     if (wanted("exp")) {
         struct { const char* name; uint32_t flags; bool verify; } exps[] = {
+            {"exp/reg<256,4>/lookback_wait_all", PF_LOOKBACK_WAIT_ALL, true},
             {"exp/reg<256,4>/static_tile", PF_STATIC_TILE, true},
             {"exp/reg<256,4>/skip_lookback", PF_SKIP_LOOKBACK, false},
             {"exp/reg<256,4>/static_tile+skip_lookback", PF_STATIC_TILE | PF_SKIP_LOOKBACK, false},
@@ -446,7 +440,24 @@ static int run_all(Env& env, const char* filter)
             env.s.flags = ex.flags;
             run_variant(env, ex.name, ex.verify, [&](const void* in, void* out) {
                 CarrySpec cs;
-                return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
+                return launch_csdl_reg<T, 256, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
+            });
+        }
+        for (uint32_t fl : {(uint32_t)PF_STATIC_TILE, (uint32_t)PF_SKIP_LOOKBACK, (uint32_t)PF_LD_ALLOCATE, (uint32_t)PF_LOOKBACK_WAIT_ALL}) {
+            env.s.flags = fl;
+            char name[96];
+            snprintf(name, sizeof(name), "exp/reg<64,24>/w1/flags%u", fl);
+            run_variant(env, name, fl != PF_SKIP_LOOKBACK, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 64, 24, INCL, 1>(env.s, in, out, env.n, cs, 0);
+            });
+        }
+        env.s.flags = PF_LOOKBACK_WAIT_ALL;
+        {
+            static int occw = 0;
+            run_variant(env, "exp/tma<512,S2>/lookback_wait_all", true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_tma<T, 512, 2, INCL>(env.s, in, out, env.n, cs, occw, 0, 0);
             });
         }
         env.s.flags = 0;
