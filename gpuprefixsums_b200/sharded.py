@@ -70,8 +70,10 @@ class ShardedScan:
         from . import _capi as capi
         from .scan import PrefixSum
 
-        if mode not in ("p2p", "nccl"):
-            raise ValueError("mode must be 'p2p' or 'nccl'")
+        if mode not in ("p2p", "nccl", "allgather"):
+            raise ValueError("mode must be 'p2p' or 'nccl' (alias 'allgather')")
+        if mode == "allgather":
+            mode = "nccl"
         self.capi = capi
         self.group = group
         self.rank = dist.get_rank(group)
@@ -134,7 +136,12 @@ class ShardedScan:
             # publish into my own staging word, all_gather the words, then copy them into
             # the slot array the scan kernel polls
             self.ps.reduce_publish(inp, [self._word.data_ptr()], tag)
-            dist.all_gather_into_tensor(self._gathered, self._word, group=self.group)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_gather_into_tensor(self._gathered, self._word, group=self.group)
+            else:  # gloo (tests): stage the G words through the host
+                words = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+                dist.all_gather(words, self._word.cpu(), group=self.group)
+                self._gathered.copy_(torch.cat(words))
             self.capi.check(self.capi.lib.gps_memcpy_d2d(base, self._gathered.data_ptr(), self.world * 8,
                                                          torch.cuda.current_stream().cuda_stream))
         return self.ps.scan_carry_slots(inp, out, base, self.world, self.rank, tag, algo=algo,
