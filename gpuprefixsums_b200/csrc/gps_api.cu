@@ -52,6 +52,7 @@ constexpr uint32_t kHostChunkKeysDefault = 1u << 24;  // 64 MiB per pipeline chu
 constexpr int kHostBufs = 3;
 static_assert(GPS_REG_NT * GPS_REG_V * 4 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
 static_assert(GPS_TMA_NT * 16 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
+static_assert(GPS_RTS_NT * GPS_RTS_V * 4 >= (int)kMinTileKeys, "partials array sized for 4096-key tiles");
 }  // namespace
 
 struct gps_ctx {
@@ -63,7 +64,6 @@ struct gps_ctx {
     uint64_t host_chunk_keys = kHostChunkKeysDefault;
     // cached launch geometry
     int tma_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [dtype][kind]
-    int rts_ctas_per_sm[2] = {0, 0};               // [dtype]
     // host pipeline (lazy)
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
     void* stage[kHostBufs] = {nullptr, nullptr, nullptr};
@@ -106,7 +106,11 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
         }
         switch (algo) {
             case GPS_ALGO_CSDL_REG:
-                e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                // small inputs: 16 KB tiles spread over more SMs (size sweep)
+                if (n <= GPS_REG_SMALL_MAX_N)
+                    e = launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                else
+                    e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 break;
             case GPS_ALGO_CSDL_TMA:
                 e = launch_csdl_tma<T, GPS_TMA_NT, GPS_TMA_STAGES, INCL, GPS_LOOKBACK_WIN>(
@@ -119,8 +123,7 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
                 break;
             }
             case GPS_ALGO_RTS:
-                e = launch_rts<T, GPS_RTS_NT, GPS_RTS_V, INCL>(c->s, in, out, n, cs,
-                                                                c->rts_ctas_per_sm[dt_index<T>()], st);
+                e = launch_rts<T, GPS_RTS_NT, GPS_RTS_V, INCL>(c->s, in, out, n, cs, st);
                 break;
             default:
                 return fail(GPS_ERR_INVALID, "unknown algo %d", algo);
@@ -234,7 +237,8 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
     c->s.desc_tiles = (uint32_t)std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
     cudaError_t e = cudaMalloc(&c->s.desc, (size_t)c->s.desc_tiles * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->s.counter, 64);
-    if (e == cudaSuccess) e = cudaMalloc(&c->s.partials, (size_t)kMaxParts * 4);
+    c->s.partials_capacity = c->s.desc_tiles;
+    if (e == cudaSuccess) e = cudaMalloc(&c->s.partials, (size_t)c->s.partials_capacity * 4);
     if (e == cudaSuccess) e = cudaMemset(c->s.desc, 0, (size_t)c->s.desc_tiles * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemset(c->s.counter, 0, 64);
     if (e != cudaSuccess) {
@@ -357,8 +361,8 @@ int gps_reduce_publish(gps_ctx* c, int dtype, const void* d_in, uint64_t n,
     cudaStream_t st = (cudaStream_t)stream;
     const cudaError_t e =
         dtype == GPS_U32
-            ? launch_reduce<uint32_t, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, c->rts_ctas_per_sm[0], st)
-            : launch_reduce<float, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, c->rts_ctas_per_sm[1], st);
+            ? launch_reduce<uint32_t, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, st)
+            : launch_reduce<float, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, st);
     if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "reduce launch failed: %s", cudaGetErrorString(e));
     return GPS_OK;
 }

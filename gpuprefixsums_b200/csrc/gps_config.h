@@ -13,6 +13,17 @@
 #ifndef GPS_REG_V
 #define GPS_REG_V 12
 #endif
+// below this many keys the scan is launch/latency bound and smaller tiles win
+// (2^20 keys: <256,4> 6.4 us vs <128,12> 8.2 us; equal at 2^21..2^23; <128,12> ahead from 2^24)
+#ifndef GPS_REG_SMALL_MAX_N
+#define GPS_REG_SMALL_MAX_N (1u << 21)
+#endif
+#ifndef GPS_REG_SMALL_NT
+#define GPS_REG_SMALL_NT 256
+#endif
+#ifndef GPS_REG_SMALL_V
+#define GPS_REG_SMALL_V 4
+#endif
 // look-back windows (32 descriptors each) fetched per L2 round trip: 1 beat 2 and 4
 // (803 / 757 / 530 Gkeys/s on <128,12> resp. <256,4>): the nearest tiles decide
 #ifndef GPS_LOOKBACK_WIN
@@ -33,10 +44,10 @@
 
 // Reduce-then-Scan tiles
 #ifndef GPS_RTS_NT
-#define GPS_RTS_NT 256
+#define GPS_RTS_NT 128
 #endif
 #ifndef GPS_RTS_V
-#define GPS_RTS_V 8
+#define GPS_RTS_V 12
 #endif
 
 // GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA path.  Chosen by measurement:

@@ -21,7 +21,8 @@ struct Scratch {
     uint32_t desc_tiles = 0;
     uint32_t* counter = nullptr;  // tile-claim counter, never reset
     uint32_t* status = nullptr;   // watchdog word
-    void* partials = nullptr;     // kMaxParts key-sized values
+    void* partials = nullptr;     // one key-sized value per RTS tile
+    uint32_t partials_capacity = 0;
     uint32_t counter_base = 0;
     uint32_t epoch = 0;
     int sm_count = 148;
@@ -144,39 +145,24 @@ cudaError_t launch_csdl_fallback(Scratch& s, const void* in, void* out, uint64_t
 }
 
 // ---- RTS -----------------------------------------------------------------------------
-// ctas_per_sm: in/out cache of the propagate kernel's occupancy (0 = query)
+// s.partials must hold one key-sized value per tile (s.partials_capacity entries)
 template <typename T, int NT, int V>
-cudaError_t rts_geometry(Scratch& s, uint64_t n, int& ctas_per_sm, RtsParams& p)
+cudaError_t rts_params(Scratch& s, uint64_t n, RtsParams& p)
 {
     using Tile = RegTile<T, NT, V>;
-    if (ctas_per_sm == 0) {
-        int occ = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occ, rts_propagate_kernel<T, NT, V, true>, NT, 0);
-        if (e != cudaSuccess) return e;
-        ctas_per_sm = std::max(1, occ);
-    }
     p.n = n;
     p.num_tiles = (uint32_t)div_up(n, Tile::TILE_KEYS);
     p.partials = s.partials;
     p.status = s.status;
-    if (p.num_tiles == 0) {
-        p.tiles_per_part = p.num_parts = 0;
-        return cudaSuccess;
-    }
-    uint32_t parts = std::min<uint32_t>((uint32_t)(ctas_per_sm * s.sm_count), kMaxParts);
-    parts = std::max<uint32_t>(1u, std::min(parts, p.num_tiles));
-    p.tiles_per_part = (uint32_t)div_up(p.num_tiles, parts);
-    p.num_parts = (uint32_t)div_up(p.num_tiles, p.tiles_per_part);
-    return cudaSuccess;
+    return p.num_tiles <= s.partials_capacity ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 template <typename T, int NT, int V, bool INCL>
 cudaError_t launch_rts(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
-                       int& ctas_per_sm, cudaStream_t st)
+                       cudaStream_t st)
 {
     RtsParams p{};
-    cudaError_t e = rts_geometry<T, NT, V>(s, n, ctas_per_sm, p);
+    cudaError_t e = rts_params<T, NT, V>(s, n, p);
     if (e != cudaSuccess) return e;
     p.in = in;
     p.out = out;
@@ -187,23 +173,23 @@ cudaError_t launch_rts(Scratch& s, const void* in, void* out, uint64_t n, const 
     p.slot_tag = cs.tag;
     p.total_out = cs.total_out;
     p.publish = cs.publish;
-    rts_reduce_kernel<T, NT, V><<<p.num_parts, NT, 0, st>>>(p);
+    rts_reduce_kernel<T, NT, V><<<p.num_tiles, NT, 0, st>>>(p);
     rts_spine_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
-    rts_propagate_kernel<T, NT, V, INCL><<<p.num_parts, NT, 0, st>>>(p);
+    rts_propagate_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p);
     return cudaGetLastError();
 }
 
 template <typename T, int NT, int V>
 cudaError_t launch_reduce(Scratch& s, const void* in, uint64_t n, void* total_out,
-                          const PublishList& pl, int& ctas_per_sm, cudaStream_t st)
+                          const PublishList& pl, cudaStream_t st)
 {
     RtsParams p{};
-    cudaError_t e = rts_geometry<T, NT, V>(s, n, ctas_per_sm, p);
+    cudaError_t e = rts_params<T, NT, V>(s, n, p);
     if (e != cudaSuccess) return e;
     p.in = in;
     p.total_out = total_out;
     p.publish = pl;
-    if (p.num_parts) rts_reduce_kernel<T, NT, V><<<p.num_parts, NT, 0, st>>>(p);
+    if (p.num_tiles) rts_reduce_kernel<T, NT, V><<<p.num_tiles, NT, 0, st>>>(p);
     rts_fold_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
     return cudaGetLastError();
 }

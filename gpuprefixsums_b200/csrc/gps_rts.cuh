@@ -1,15 +1,18 @@
 // gps_rts.cuh -- three-kernel Reduce-then-Scan (second algorithm) and device reduce.
 //
 // Replaces ReduceThenScan.cuh:15-161 of the reference (Reduce, SpineScan,
-// Propagate{In,Ex}clusive).  B200-first restructuring: instead of one partial per
-// 4096-key tile (65,536 partials at 2^28, scanned by a single 1024-thread block in 16
-// serial iterations, ReduceThenScan.cuh:56-104), the input is cut into P contiguous
-// PARTITIONS, P = a multiple of the SM count (one persistent CTA each):
-//   kernel 1  rts_reduce     CTA p streams its partition, one partial per partition
-//   kernel 2  rts_spine      ONE block turns the P partials into exclusive prefixes
-//                            (+ carry), single pass, no loop
-//   kernel 3  rts_propagate  CTA p re-streams its partition tile by tile, carrying the
-//                            running prefix in a register -- no descriptors, no look-back
+// Propagate{In,Ex}clusive):
+//   kernel 1  rts_reduce     one CTA per tile, tile sum -> partials[tile].  Tiles are visited
+//                            BACK TO FRONT, so when the pass ends the front of the array is
+//                            what is left in the 126 MB L2 -- exactly what kernel 3 reads first
+//   kernel 2  rts_spine      ONE block turns the tile sums into exclusive prefixes (+ carry):
+//                            each thread sums a contiguous run of partials, one block scan of
+//                            the 1024 thread sums, prefixes written back -- a single pass, for
+//                            any number of tiles (the reference loops a 4096-wide window with
+//                            one block and gets the cross-warp offset wrong beyond 128 tiles,
+//                            ReduceThenScan.cuh:56-104)
+//   kernel 3  rts_propagate  one CTA per tile: load, block scan, add partials[tile], store --
+//                            the CSDL tile pipeline minus descriptors and look-back
 // Deterministic for float32 (fixed association order).  DRAM traffic 12 B/key.
 #pragma once
 #include "gps_tile_reg.cuh"
@@ -20,10 +23,8 @@ struct RtsParams {
     const void* in;
     void* out;
     uint64_t n;
-    void* partials;            // P key-sized values: sums after kernel 1, exclusive prefixes after kernel 2
+    void* partials;            // one key-sized value per tile: sums, then exclusive prefixes
     uint32_t num_tiles;        // ceil(n / TILE_KEYS)
-    uint32_t tiles_per_part;   // ceil(num_tiles / P)
-    uint32_t num_parts;        // P = gridDim.x of kernels 1 and 3
     uint32_t carry_bits;
     const uint64_t* slots;
     uint32_t n_slots;
@@ -46,37 +47,28 @@ __device__ __forceinline__ T block_reduce(T v, T* s_red, uint32_t warp, uint32_t
     return v;  // valid in every thread
 }
 
-// ---- kernel 1: per-partition sums ------------------------------------------------
+// ---- kernel 1: per-tile sums, back to front ---------------------------------------
 template <typename T, int NT, int V>
-__global__ void __launch_bounds__(NT) rts_reduce_kernel(const __grid_constant__ RtsParams p)
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 16 + 4 * V))
+    rts_reduce_kernel(const __grid_constant__ RtsParams p)
 {
     using Tile = RegTile<T, NT, V>;
     __shared__ T s_red[NT / 32];
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t part = blockIdx.x;
-    const uint32_t first = part * p.tiles_per_part;
-    const uint32_t last = min(first + p.tiles_per_part, p.num_tiles);
-
-    T acc = T(0);
-    for (uint32_t tile = first; tile < last; ++tile) {
-        const uint64_t vbase = Tile::vec_base(tile, warp, lane);
-        Tile t;
-        if (((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n)
-            t.load_full(p.in, vbase);
-        else
-            t.load_partial(p.in, vbase, p.n);
-        acc += t.thread_sum();
-    }
-    acc = block_reduce<T, NT>(acc, s_red, warp, lane);
-    if (threadIdx.x == 0) reinterpret_cast<T*>(p.partials)[part] = acc;
+    const uint32_t tile = p.num_tiles - 1u - blockIdx.x;
+    const uint64_t vbase = Tile::vec_base(tile, warp, lane);
+    Tile t;
+    if (((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n)
+        t.load_full(p.in, vbase);
+    else
+        t.load_partial(p.in, vbase, p.n);
+    const T sum = block_reduce<T, NT>(t.thread_sum(), s_red, warp, lane);
+    if (threadIdx.x == 0) reinterpret_cast<T*>(p.partials)[tile] = sum;
 }
 
-// ---- kernel 2: spine -- exclusive scan of the P partials (+ carry) ----------------
-// One block of 1024 threads, up to kSpineItems partials per thread, single pass.
+// ---- kernel 2: spine -- exclusive scan of the tile sums (+ carry) -------------------
 constexpr int kSpineThreads = 1024;
-constexpr int kSpineItems = 4;
-constexpr uint32_t kMaxParts = kSpineThreads * kSpineItems;
 
 template <typename T>
 __device__ __forceinline__ ScanParams carry_view(const RtsParams& p)
@@ -106,15 +98,13 @@ __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_c
         const T c = acquire_carry<T>(cv, lane);
         if (lane == 0) s_carry = c;
     }
-
-    T v[kSpineItems];
-    const uint32_t base = threadIdx.x * kSpineItems;
+    // contiguous run of this thread (L2-resident: <= a few MB even at 2^32 keys)
+    const uint32_t per = (p.num_tiles + kSpineThreads - 1u) / kSpineThreads;
+    const uint32_t begin = min(threadIdx.x * per, p.num_tiles);
+    const uint32_t end = min(begin + per, p.num_tiles);
     T tsum = T(0);
-#pragma unroll
-    for (int i = 0; i < kSpineItems; ++i) {
-        v[i] = (base + i < p.num_parts) ? partials[base + i] : T(0);
-        tsum += v[i];
-    }
+    for (uint32_t i = begin; i < end; ++i) tsum += partials[i];
+
     const T inc = warp_inclusive_scan(tsum, lane);
     const T lane_excl = warp_exclusive_of(inc, tsum, lane);
     if (lane == 31) s_warp[warp] = inc;
@@ -123,10 +113,10 @@ __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_c
     block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, total);
 
     T run = (s_carry + warp_prefix) + lane_excl;
-#pragma unroll
-    for (int i = 0; i < kSpineItems; ++i) {
-        if (base + i < p.num_parts) partials[base + i] = run;
-        run += v[i];
+    for (uint32_t i = begin; i < end; ++i) {
+        const T v = partials[i];
+        partials[i] = run;
+        run += v;
     }
     if (threadIdx.x == 0) {
         const T grand = s_carry + total;
@@ -135,7 +125,7 @@ __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_c
     }
 }
 
-// Fold of the partials into one total, optionally published to (peer) carry slots with
+// Fold of the tile sums into one total, optionally published to (peer) carry slots with
 // st.release.sys -- the second half of gps_reduce / gps_reduce_publish.
 template <typename T>
 __global__ void __launch_bounds__(kSpineThreads) rts_fold_kernel(const __grid_constant__ RtsParams p)
@@ -145,7 +135,7 @@ __global__ void __launch_bounds__(kSpineThreads) rts_fold_kernel(const __grid_co
     const uint32_t warp = threadIdx.x >> 5;
     const T* partials = reinterpret_cast<const T*>(p.partials);
     T acc = T(0);
-    for (uint32_t i = threadIdx.x; i < p.num_parts; i += kSpineThreads) acc += partials[i];
+    for (uint32_t i = threadIdx.x; i < p.num_tiles; i += kSpineThreads) acc += partials[i];
     acc = block_reduce<T, kSpineThreads>(acc, s_red, warp, lane);
     if (threadIdx.x == 0) {
         if (p.total_out) *reinterpret_cast<T*>(p.total_out) = acc;
@@ -155,39 +145,33 @@ __global__ void __launch_bounds__(kSpineThreads) rts_fold_kernel(const __grid_co
 
 // ---- kernel 3: propagate ----------------------------------------------------------
 template <typename T, int NT, int V, bool INCLUSIVE>
-__global__ void __launch_bounds__(NT) rts_propagate_kernel(const __grid_constant__ RtsParams p)
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 24 + 4 * V))
+    rts_propagate_kernel(const __grid_constant__ RtsParams p)
 {
     using Tile = RegTile<T, NT, V>;
     constexpr int NW = Tile::NW;
-    __shared__ T s_warp[2][NW];
+    __shared__ T s_warp[NW];
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t part = blockIdx.x;
-    const uint32_t first = part * p.tiles_per_part;
-    const uint32_t last = min(first + p.tiles_per_part, p.num_tiles);
-
-    T running = reinterpret_cast<const T*>(p.partials)[part];
-    for (uint32_t tile = first; tile < last; ++tile) {
-        const uint64_t vbase = Tile::vec_base(tile, warp, lane);
-        const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
-        Tile t;
-        if (full)
-            t.load_full(p.in, vbase);
-        else
-            t.load_partial(p.in, vbase, p.n);
-        t.scan_warp(lane);
-        T* sw = s_warp[tile & 1u];  // double-buffered: one barrier per tile
-        if (lane == 0) sw[warp] = t.warp_total;
-        __syncthreads();
-        T warp_prefix, aggregate;
-        block_scan_warp_totals<T, NW>(sw, warp, lane, warp_prefix, aggregate);
-        const T prefix = running + warp_prefix;
-        if (full)
-            t.template store_full<INCLUSIVE>(p.out, vbase, prefix);
-        else
-            t.template store_partial<INCLUSIVE>(p.out, vbase, p.n, prefix);
-        running += aggregate;
-    }
+    const uint32_t tile = blockIdx.x;
+    const uint64_t vbase = Tile::vec_base(tile, warp, lane);
+    const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
+    const T tile_prefix = reinterpret_cast<const T*>(p.partials)[tile];
+    Tile t;
+    if (full)
+        t.load_full(p.in, vbase);
+    else
+        t.load_partial(p.in, vbase, p.n);
+    t.scan_warp(lane);
+    if (lane == 0) s_warp[warp] = t.warp_total;
+    __syncthreads();
+    T warp_prefix, aggregate;
+    block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, aggregate);
+    const T prefix = tile_prefix + warp_prefix;
+    if (full)
+        t.template store_full<INCLUSIVE>(p.out, vbase, prefix);
+    else
+        t.template store_partial<INCLUSIVE>(p.out, vbase, p.n, prefix);
 }
 
 }  // namespace gps

@@ -348,3 +348,25 @@ def test_error_behaviour(gps, ps):
     small.close()
     with pytest.raises(TypeError):
         ps.scan(torch.zeros(8, dtype=torch.float64, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------
+# 64-bit sizes: more than 2^32 keys on one GPU (the 2-GPU shard of the 2^33-key case)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["csdl", "rts", "csdl_tma"])
+def test_more_than_2p32_keys(gps, algo):
+    n = (1 << 32) + 12_345
+    free, _ = torch.cuda.mem_get_info()
+    if free < 2 * 4 * n + (2 << 30):
+        pytest.skip("not enough device memory for 2 x 16 GiB")
+    big = gps.PrefixSum(n)
+    buf = torch.empty(n, dtype=torch.int32, device="cuda")
+    gps.init_ones(buf)
+    total = torch.zeros(1, dtype=torch.int32, device="cuda")
+    big.scan(buf, buf, algo=algo, carry=7, total_out=total)  # in place, 64-bit indexing throughout
+    big.check()
+    assert gps.validate_ones(buf, False, first_value=7) == 0  # scan[i] == 7 + i + 1 (mod 2^32)
+    assert (int(total.item()) & 0xFFFFFFFF) == (7 + n) & 0xFFFFFFFF
+    big.close()
+    del buf
+    torch.cuda.empty_cache()

@@ -248,10 +248,9 @@ static void add_rts(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v)
 {
     char name[96];
     snprintf(name, sizeof(name), "rts<%d,%d>", NT, V);
-    auto occ = std::make_shared<int>(0);
-    v.emplace_back(name, [&env, occ](const void* in, void* out) {
+    v.emplace_back(name, [&env](const void* in, void* out) {
         CarrySpec cs;
-        return launch_rts<T, NT, V, INCL>(env.s, in, out, env.n, cs, *occ, 0);
+        return launch_rts<T, NT, V, INCL>(env.s, in, out, env.n, cs, 0);
     });
 }
 
@@ -271,6 +270,7 @@ template <typename T, bool INCL>
 static void build_variants(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v)
 {
     add_reg<T, 256, 4, INCL, 1>(env, v);
+    add_reg<T, 128, 4, INCL, 1>(env, v);
     add_reg<T, 256, 8, INCL, 1>(env, v);
     add_reg<T, 128, 10, INCL, 1>(env, v);
     add_reg<T, 128, 12, INCL, 1>(env, v);
@@ -292,12 +292,14 @@ static void build_variants(Env& env, std::vector<std::pair<std::string, LaunchFn
     add_rts<T, 256, 4, INCL>(env, v);
     add_rts<T, 512, 4, INCL>(env, v);
     add_rts<T, 256, 8, INCL>(env, v);
-    add_rts<T, 128, 8, INCL>(env, v);
+    add_rts<T, 128, 12, INCL>(env, v);
     add_rts<T, 128, 16, INCL>(env, v);
-    add_fallback<T, 256, 4, INCL>(env, v, kNoStall, 64);
-    add_fallback<T, 256, 4, INCL>(env, v, kNoStall, 4);
+    add_rts<T, 64, 24, INCL>(env, v);
+    add_fallback<T, 128, 12, INCL>(env, v, kNoStall, 64);
+    add_fallback<T, 128, 12, INCL>(env, v, kNoStall, 4);
+    add_fallback<T, 128, 12, INCL>(env, v, 7, 4);
+    add_fallback<T, 128, 12, INCL>(env, v, 63, 4);
     add_fallback<T, 256, 4, INCL>(env, v, 7, 4);
-    add_fallback<T, 256, 4, INCL>(env, v, 63, 4);
 }
 
 template <typename T, bool INCL>
@@ -371,6 +373,39 @@ static int run_all(Env& env, const char* filter)
             return cub_scan<T, INCL>(in, out, env.n, cub_temp, cub_temp_bytes);
         });
 
+    if (filter && !strcmp(filter, "sweep")) {
+        std::vector<std::pair<std::string, LaunchFn>> sv;
+        static int occ_t = 0;
+        sv.emplace_back("sweep/cub_device_scan", [&](const void* in, void* out) {
+            return cub_scan<T, INCL>(in, out, env.n, cub_temp, cub_temp_bytes);
+        });
+        sv.emplace_back("sweep/csdl_reg<128,12>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_reg<T, 128, 12, INCL, 1>(env.s, in, out, env.n, cs, 0);
+        });
+        sv.emplace_back("sweep/csdl_reg<256,4>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_reg<T, 256, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
+        });
+        sv.emplace_back("sweep/csdl_reg<128,4>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_reg<T, 128, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
+        });
+        sv.emplace_back("sweep/csdl_tma<512,S2>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_tma<T, 512, 2, INCL, 1>(env.s, in, out, env.n, cs, occ_t, 0, 0);
+        });
+        sv.emplace_back("sweep/rts<128,12>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_rts<T, 128, 12, INCL>(env.s, in, out, env.n, cs, 0);
+        });
+        int bad = 0;
+        for (auto& kv : sv) {
+            Result r = run_variant(env, kv.first.c_str(), true, kv.second);
+            if (!r.ok || r.errs) ++bad;
+        }
+        return bad;
+    }
     std::vector<std::pair<std::string, LaunchFn>> variants;
     build_variants<T, INCL>(env, variants);
     int bad = 0;
@@ -481,6 +516,8 @@ int main(int argc, char** argv)
 {
     Env env;
     const char* filter = nullptr;
+    bool sweep = false;
+    int max_log2n = 30;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--log2n") && i + 1 < argc) env.n = 1ull << atoi(argv[++i]);
         else if (!strcmp(argv[i], "--n") && i + 1 < argc) env.n = strtoull(argv[++i], nullptr, 10);
@@ -488,6 +525,8 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--filter") && i + 1 < argc) filter = argv[++i];
         else if (!strcmp(argv[i], "--float")) env.is_float = true;
         else if (!strcmp(argv[i], "--prof")) env.prof_enabled = true;
+        else if (!strcmp(argv[i], "--sweep")) sweep = true;
+        else if (!strcmp(argv[i], "--max-log2n") && i + 1 < argc) max_log2n = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--exclusive")) env.exclusive = true;
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
@@ -510,7 +549,8 @@ int main(int argc, char** argv)
     CK(cudaMemset(env.s.counter, 0, 64));
     env.s.status = env.s.counter + 1;
     env.tma_copy_counter = env.s.counter + 8;
-    CK(cudaMalloc(&env.s.partials, kMaxParts * 4));
+    env.s.partials_capacity = env.s.desc_tiles;
+    CK(cudaMalloc(&env.s.partials, (size_t)env.s.partials_capacity * 4));
     CK(cudaMalloc(&env.prof_buf, sizeof(unsigned long long) * kProfSlots * kProfFields));
     env.sm_ghz = prop.clockRate / 1e6;
     CK(cudaEventCreate(&env.e0));
@@ -521,6 +561,19 @@ int main(int argc, char** argv)
         init_random_u32_kernel<<<2048, 256>>>((uint32_t*)env.in, env.n, 1234, 0xFFFFFFFFu, 0);
     CK(cudaDeviceSynchronize());
 
+    if (sweep) {
+        // size sweep (BASELINE configs[3]): 2^10 .. 2^max keys, default kernels + CUB; buffers
+        // were allocated for env.n = 2^max.  n <= 2^23: in + out fit the 126 MB L2 ("L2-resident")
+        const uint64_t n_max = env.n;
+        int bad_total = 0;
+        for (int lg = 10; (1ull << lg) <= n_max; ++lg) {
+            env.n = 1ull << lg;
+            env.iters = lg <= 20 ? 200 : lg <= 24 ? 100 : 30;
+            bad_total += env.is_float ? run_all<float, true>(env, filter ? filter : "sweep")
+                                      : run_all<uint32_t, true>(env, filter ? filter : "sweep");
+        }
+        return bad_total ? 1 : 0;
+    }
     int bad;
     if (env.is_float)
         bad = env.exclusive ? run_all<float, false>(env, filter) : run_all<float, true>(env, filter);

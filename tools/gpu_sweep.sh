@@ -13,5 +13,5 @@ for l in open(sys.argv[1]):
     if 'error' in d: print(d); continue
     if 'profile' in d:
         print("   profile: claim %.2f load %.2f reduce %.2f lookback %.2f finish %.2f us | windows %.2f polls %.1f" % (d['us_claim'], d['us_load'], d['us_reduce'], d['us_lookback'], d['us_finish'], d['windows'], d['polls'])); continue
-    print("%-52s %8.2f Gk/s  inplace %8.2f  errs %d wd %d" % (d["variant"], d["gkeys_s"], d["gkeys_s_inplace"], d["errors"], d["watchdog"]))
+    print("%-44s n=2^%-4.1f %9.2f us %8.2f Gk/s  inplace %8.2f  errs %d wd %d" % (d["variant"], __import__("math").log2(d["n"]), d["ms"]*1e3, d["gkeys_s"], d["gkeys_s_inplace"], d["errors"], d["watchdog"]))
 PY
