@@ -291,6 +291,17 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     if (!strcmp(key, "csdl_variant")) {
         if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..2");
         c->csdl_variant = (int)value;
+    } else if (!strcmp(key, "debug_epoch")) {
+        // test hook: jump the launch epoch (e.g. just below the 2^30 wrap)
+        if (value < 0 || value >= (1ll << 30)) return fail(GPS_ERR_INVALID, "epoch out of range");
+        c->s.epoch = (uint32_t)value;
+    } else if (!strcmp(key, "debug_counter")) {
+        // test hook: jump the never-reset ticket counter (e.g. just below the 2^32 wrap)
+        DeviceGuard g(c->device);
+        const uint32_t v = (uint32_t)value;
+        GPS_CUDA(cudaDeviceSynchronize());
+        GPS_CUDA(cudaMemcpy(c->s.counter, &v, sizeof(v), cudaMemcpyHostToDevice));
+        c->s.counter_base = v;
     } else if (!strcmp(key, "tile_order")) {
         // 0 = atomic ticket (default: provably deadlock-free), 1 = blockIdx.x (what
         // cub::DeviceScan relies on: CTAs are dispatched in index order); register path only

@@ -370,3 +370,42 @@ def test_more_than_2p32_keys(gps, algo):
     big.close()
     del buf
     torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------
+# scratch bookkeeping that replaces the reference's per-launch memsets
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["csdl_reg", "csdl_tma", "csdl_fallback"])
+def test_epoch_and_ticket_counter_wraparound(gps, oracle, algo):
+    """Descriptors are epoch-tagged and the ticket counter is never reset: both must
+    survive their wrap (2^30 launches / 2^32 tickets)."""
+    ps = gps.PrefixSum(1 << 22)
+    n = (1 << 21) + 4099
+    x = oracle.random_u32(n, seed=123)
+    want, _ = oracle.scan_u32(x)
+    d_in = to_dev_u32(x)
+    ps.set_option("debug_epoch", (1 << 30) - 4)
+    ps.set_option("debug_counter", (1 << 32) - 700)  # a launch claims ~350-500 tickets here
+    for i in range(8):
+        out = ps.scan(d_in, algo=algo)
+        ps.check()
+        assert np.array_equal(to_np_u32(out), want), f"launch {i} after the jump"
+    ps.close()
+
+
+@pytest.mark.parametrize("protocol", [0, 1, 2])
+@pytest.mark.parametrize("tile_order", [0, 1])
+def test_descriptor_protocols_and_tile_order(gps, oracle, protocol, tile_order):
+    """atom.exch/ld.relaxed (default), st.release/ld.acquire and st.relaxed/ld.relaxed; ticket
+    vs blockIdx tile order -- all bit-exact."""
+    ps = gps.PrefixSum(1 << 24)
+    ps.set_option("desc_protocol", protocol)
+    ps.set_option("tile_order", tile_order)
+    n = (1 << 23) + 777
+    x = oracle.random_u32(n, seed=9)
+    want, _ = oracle.scan_u32(x, exclusive=True)
+    for algo in ("csdl_reg", "csdl_tma"):
+        out = ps.scan(to_dev_u32(x), algo=algo, exclusive=True)
+        ps.check()
+        assert np.array_equal(to_np_u32(out), want), (algo, protocol, tile_order)
+    ps.close()
