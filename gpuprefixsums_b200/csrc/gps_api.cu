@@ -52,6 +52,7 @@ constexpr uint32_t kHostChunkKeysDefault = 1u << 24;  // 64 MiB per pipeline chu
 constexpr int kHostBufs = 3;
 static_assert(GPS_REG_NT * GPS_REG_V * 4 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
 static_assert(GPS_TMA_NT * 16 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
+static_assert(GPS_SMEM_NT * GPS_SMEM_V * 4 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
 static_assert(GPS_RTS_NT * GPS_RTS_V * 4 >= (int)kMinTileKeys, "partials array sized for 4096-key tiles");
 }  // namespace
 
@@ -64,6 +65,7 @@ struct gps_ctx {
     uint64_t host_chunk_keys = kHostChunkKeysDefault;
     // cached launch geometry
     int tma_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [dtype][kind]
+    bool smem_configured[2][2] = {{false, false}, {false, false}};
     // host pipeline (lazy)
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
     void* stage[kHostBufs] = {nullptr, nullptr, nullptr};
@@ -102,7 +104,9 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
     } else {
         if (algo == GPS_ALGO_CSDL) {
             const int v = c->csdl_variant ? c->csdl_variant : GPS_CSDL_DEFAULT_VARIANT;
-            algo = v == 2 ? GPS_ALGO_CSDL_TMA : GPS_ALGO_CSDL_REG;
+            algo = v == 2 ? GPS_ALGO_CSDL_TMA : v == 3 ? GPS_ALGO_CSDL_SMEM : GPS_ALGO_CSDL_REG;
+            // small inputs are launch/latency bound: the register path with 16 KB tiles
+            if (algo == GPS_ALGO_CSDL_SMEM && n <= GPS_REG_SMALL_MAX_N) algo = GPS_ALGO_CSDL_REG;
         }
         switch (algo) {
             case GPS_ALGO_CSDL_REG:
@@ -111,6 +115,10 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
                     e = launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 else
                     e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                break;
+            case GPS_ALGO_CSDL_SMEM:
+                e = launch_csdl_smem<T, GPS_SMEM_NT, GPS_SMEM_V, INCL, GPS_LOOKBACK_WIN>(
+                    c->s, in, out, n, cs, c->smem_configured[dt_index<T>()][INCL ? 0 : 1], st);
                 break;
             case GPS_ALGO_CSDL_TMA:
                 e = launch_csdl_tma<T, GPS_TMA_NT, GPS_TMA_STAGES, INCL, GPS_LOOKBACK_WIN>(
@@ -289,7 +297,7 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
 {
     if (!c || !key) return fail(GPS_ERR_INVALID, "null argument");
     if (!strcmp(key, "csdl_variant")) {
-        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..2");
+        if (value < 0 || value > 3) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..3");
         c->csdl_variant = (int)value;
     } else if (!strcmp(key, "debug_epoch")) {
         // test hook: jump the launch epoch (e.g. just below the 2^30 wrap)
@@ -304,7 +312,7 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
         c->s.counter_base = v;
     } else if (!strcmp(key, "tile_order")) {
         // 0 = atomic ticket (default: provably deadlock-free), 1 = blockIdx.x (what
-        // cub::DeviceScan relies on: CTAs are dispatched in index order); register path only
+        // cub::DeviceScan relies on: CTAs are dispatched in index order); register / smem paths
         if (value != 0 && value != 1) return fail(GPS_ERR_INVALID, "tile_order must be 0 or 1");
         c->s.flags = (c->s.flags & ~PF_STATIC_TILE) | (value ? PF_STATIC_TILE : 0u);
     } else if (!strcmp(key, "desc_protocol")) {

@@ -50,10 +50,21 @@
 #define GPS_RTS_V 12
 #endif
 
-// GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA path.  Chosen by measurement:
-// register path 785-803 Gkeys/s vs TMA ring 659 Gkeys/s at 2^28 keys
+// CSDL with the tile resident in shared memory: one TMA bulk load per CTA, NT threads,
+// V uint4 per thread.  <128,8> 837, <128,12> 806-832, <256,8> 821-825, <128,16> 795-810,
+// <64,16> 764, <256,4> 619-680 Gkeys/s; rows per pass-2 group 4 (2: same, 8: 640)
+#ifndef GPS_SMEM_NT
+#define GPS_SMEM_NT 128
+#endif
+#ifndef GPS_SMEM_V
+#define GPS_SMEM_V 8
+#endif
+
+// GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = smem-resident tile.
+// Chosen by measurement at 2^28 keys: smem-resident tile 837,
+// register path 785-805, TMA ring 659 Gkeys/s
 #ifndef GPS_CSDL_DEFAULT_VARIANT
-#define GPS_CSDL_DEFAULT_VARIANT 1
+#define GPS_CSDL_DEFAULT_VARIANT 3
 #endif
 
 // spin budget of GPS_ALGO_CSDL_FALLBACK (no emulated stalls): polls of a not-ready

@@ -8,6 +8,7 @@
 #include <algorithm>
 
 #include "gps_csdl_reg.cuh"
+#include "gps_csdl_smem.cuh"
 #include "gps_csdl_tma.cuh"
 #include "gps_rts.cuh"
 
@@ -99,6 +100,25 @@ cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, c
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
     csdl_reg_kernel<T, NT, V, INCL, WIN, PROF><<<p.num_tiles, NT, 0, st>>>(p);
+    if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
+    return cudaGetLastError();
+}
+
+// ---- CSDL shared-memory-resident tile (one TMA bulk load per CTA) ---------------------
+// configured: in/out flag, false = set the shared-memory carve-out preference first
+template <typename T, int NT, int V, bool INCL, int WIN = 1, int G = 4, int REGS = 40>
+cudaError_t launch_csdl_smem(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                             bool& configured, cudaStream_t st)
+{
+    auto kern = csdl_smem_kernel<T, NT, V, INCL, WIN, G, REGS>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
+    kern<<<p.num_tiles, NT, 0, st>>>(p);
     if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
     return cudaGetLastError();
 }

@@ -5,12 +5,11 @@
 //   kernel 1  rts_reduce     one CTA per tile, tile sum -> partials[tile].  Tiles are visited
 //                            BACK TO FRONT, so when the pass ends the front of the array is
 //                            what is left in the 126 MB L2 -- exactly what kernel 3 reads first
-//   kernel 2  rts_spine      ONE block turns the tile sums into exclusive prefixes (+ carry):
-//                            each thread sums a contiguous run of partials, one block scan of
-//                            the 1024 thread sums, prefixes written back -- a single pass, for
-//                            any number of tiles (the reference loops a 4096-wide window with
-//                            one block and gets the cross-warp offset wrong beyond 128 tiles,
-//                            ReduceThenScan.cuh:56-104)
+//   kernel 2  rts_spine      ONE block turns the tile sums into exclusive prefixes (+ carry),
+//                            8192 per step, coalesced, next chunk's loads in flight while the
+//                            current one is scanned (the reference's SpineScan walks a
+//                            4096-wide window the same way but gets the cross-warp offset
+//                            wrong beyond 128 tiles, ReduceThenScan.cuh:56-104)
 //   kernel 3  rts_propagate  one CTA per tile: load, block scan, add partials[tile], store --
 //                            the CSDL tile pipeline minus descriptors and look-back
 // Deterministic for float32 (fixed association order).  DRAM traffic 12 B/key.
@@ -83,11 +82,18 @@ __device__ __forceinline__ ScanParams carry_view(const RtsParams& p)
     return s;
 }
 
+// One block walks the tile sums in chunks of kSpineThreads * kSpineItems with fully
+// coalesced accesses (thread t owns kSpineItems consecutive values of the chunk), the loads of
+// the next chunk in flight while the current one is scanned; the running total is carried
+// in a register.  43,691 tile sums (2^28 keys) take 6 chunks.
+constexpr int kSpineItems = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_constant__ RtsParams p)
 {
     constexpr int NW = kSpineThreads / 32;
-    __shared__ T s_warp[NW];
+    constexpr uint32_t CHUNK = kSpineThreads * kSpineItems;
+    __shared__ T s_warp[2][NW];
     __shared__ T s_carry;
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
@@ -98,30 +104,42 @@ __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_c
         const T c = acquire_carry<T>(cv, lane);
         if (lane == 0) s_carry = c;
     }
-    // contiguous run of this thread (L2-resident: <= a few MB even at 2^32 keys)
-    const uint32_t per = (p.num_tiles + kSpineThreads - 1u) / kSpineThreads;
-    const uint32_t begin = min(threadIdx.x * per, p.num_tiles);
-    const uint32_t end = min(begin + per, p.num_tiles);
-    T tsum = T(0);
-    for (uint32_t i = begin; i < end; ++i) tsum += partials[i];
-
-    const T inc = warp_inclusive_scan(tsum, lane);
-    const T lane_excl = warp_exclusive_of(inc, tsum, lane);
-    if (lane == 31) s_warp[warp] = inc;
+    auto load_chunk = [&](uint32_t base, T (&v)[kSpineItems]) {
+        const uint32_t i0 = base + threadIdx.x * kSpineItems;
+#pragma unroll
+        for (int i = 0; i < kSpineItems; ++i) v[i] = (i0 + i < p.num_tiles) ? partials[i0 + i] : T(0);
+    };
+    T cur[kSpineItems], nxt[kSpineItems];
+    load_chunk(0, cur);
     __syncthreads();
-    T warp_prefix, total;
-    block_scan_warp_totals<T, NW>(s_warp, warp, lane, warp_prefix, total);
-
-    T run = (s_carry + warp_prefix) + lane_excl;
-    for (uint32_t i = begin; i < end; ++i) {
-        const T v = partials[i];
-        partials[i] = run;
-        run += v;
+    T running = s_carry;
+    uint32_t it = 0;
+    for (uint32_t base = 0; base < p.num_tiles; base += CHUNK, ++it) {
+        if (base + CHUNK < p.num_tiles) load_chunk(base + CHUNK, nxt);
+        T tsum = T(0);
+#pragma unroll
+        for (int i = 0; i < kSpineItems; ++i) tsum += cur[i];
+        const T inc = warp_inclusive_scan(tsum, lane);
+        const T lane_excl = warp_exclusive_of(inc, tsum, lane);
+        T* sw = s_warp[it & 1u];
+        if (lane == 31) sw[warp] = inc;
+        __syncthreads();
+        T warp_prefix, total;
+        block_scan_warp_totals<T, NW>(sw, warp, lane, warp_prefix, total);
+        T run = (running + warp_prefix) + lane_excl;
+        const uint32_t i0 = base + threadIdx.x * kSpineItems;
+#pragma unroll
+        for (int i = 0; i < kSpineItems; ++i) {
+            if (i0 + i < p.num_tiles) partials[i0 + i] = run;
+            run += cur[i];
+        }
+        running += total;
+#pragma unroll
+        for (int i = 0; i < kSpineItems; ++i) cur[i] = nxt[i];
     }
     if (threadIdx.x == 0) {
-        const T grand = s_carry + total;
-        if (p.total_out) *reinterpret_cast<T*>(p.total_out) = grand;
-        publish_total<T>(p.publish, grand);
+        if (p.total_out) *reinterpret_cast<T*>(p.total_out) = running;
+        publish_total<T>(p.publish, running);
     }
 }
 

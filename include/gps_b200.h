@@ -55,7 +55,8 @@ enum gps_algo {
     GPS_ALGO_CSDL_REG = 1,      /*   register path: 128-bit coalesced LDG/STG          */
     GPS_ALGO_CSDL_TMA = 2,      /*   TMA bulk copies into a shared-memory ring        */
     GPS_ALGO_CSDL_FALLBACK = 3, /* CSDL + Decoupled Fallback (no emulated stalls)     */
-    GPS_ALGO_RTS = 4            /* three-kernel Reduce-then-Scan                      */
+    GPS_ALGO_RTS = 4,           /* three-kernel Reduce-then-Scan                      */
+    GPS_ALGO_CSDL_SMEM = 5      /*   one TMA bulk load per CTA, tile resident in smem  */
 };
 enum gps_kind { GPS_INCLUSIVE = 0, GPS_EXCLUSIVE = 1 };
 enum gps_dtype { GPS_U32 = 0, GPS_F32 = 1 };
@@ -78,7 +79,10 @@ void gps_destroy(gps_ctx* ctx);
  * check tripped the look-back watchdog (then clears the flag). */
 int gps_check(gps_ctx* ctx, void* stream);
 /* Tuning knobs (key/value); unknown keys return GPS_ERR_INVALID.  Keys:
- *   "csdl_variant"  0 = auto, 1 = register path, 2 = TMA ring
+ *   "csdl_variant"  0 = auto, 1 = register path, 2 = TMA ring, 3 = smem-resident tile
+ *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)
+ *   "desc_protocol" 0 = atom.exch + ld.relaxed (default), 1 = st.release + ld.acquire,
+ *                   2 = st.relaxed + ld.relaxed
  *   "poll_sleep_ns" nanosleep between unsuccessful descriptor polls (default 0)
  *   "host_chunk_keys" chunk size of gps_scan_host (default 2^24; before first use) */
 int gps_set_option(gps_ctx* ctx, const char* key, int64_t value);

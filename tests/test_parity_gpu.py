@@ -9,10 +9,11 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-ALGOS = ["csdl_reg", "csdl_tma", "rts", "csdl_fallback"]
-# tile sizes in play: 4096 (register path / RTS / fallback), 8192 (TMA path)
+ALGOS = ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"]
+# tile sizes in play: 4096 (smem path, small-input register path), 6144 (register path / RTS /
+# fallback), 8192 (TMA path)
 EDGE_SIZES = [0, 1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 127, 128, 129, 1023, 1024, 1025, 4095, 4096, 4097, 8191,
-              8192, 8193, 12287, 12288, 12289, 16384, 16385, 65535, 65536, 65537, 100_003, 1 << 20]
+              6143, 6144, 6145, 8192, 8193, 12287, 12288, 12289, 16384, 16385, 65535, 65536, 65537, 100_003, 1 << 20]
 # float32 tolerance: |gpu_i - ref_i| <= RTOL * sum_{j<=i}|x_j| + ATOL vs the float64
 # serial scan.  Observed max is ~1e-6 (reported by test_float_2p28_tolerance).
 F32_RTOL = 2e-5
@@ -93,7 +94,7 @@ def test_config0_2p20_random_vs_host_serial(ps, oracle):
     """BASELINE config[0]: uint32 inclusive, 2^20 random keys, CSDL vs the host serial scan."""
     n = 1 << 20
     x = oracle.random_u32(n, seed=1)
-    for algo in ["csdl", "csdl_reg", "csdl_tma"]:
+    for algo in ["csdl", "csdl_smem", "csdl_reg", "csdl_tma"]:
         got = to_np_u32(ps.scan(to_dev_u32(x), algo=algo))
         ps.check()
         errs, first = oracle.check_u32(x, got)
@@ -103,7 +104,7 @@ def test_config0_2p20_random_vs_host_serial(ps, oracle):
 # ---------------------------------------------------------------------------------------
 # the reference's own protocol: all-ones, closed form, sizes 4096..8192 (+ around 8192-key tiles)
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ["csdl_reg", "csdl_tma", "rts"])
+@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "rts"])
 @pytest.mark.parametrize("exclusive", [False, True])
 def test_reference_all_ones_sweep(gps, algo, exclusive):
     from gpuprefixsums_b200.dispatchers import (ChainedScanDecoupledLookbackDispatcher,
@@ -167,7 +168,7 @@ def test_rts_float_is_deterministic(ps, oracle):
 # ---------------------------------------------------------------------------------------
 # full size (2^28): closed form, properties, CUB and the reference's CUDA kernels
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ["csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
+@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
 def test_2p28_all_ones_closed_form(gps, ps, algo):
     n = 1 << 28
     buf = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -188,7 +189,7 @@ def test_2p28_random_vs_cub_and_properties(gps, ps, oracle):
     gps.cub_scan(x, ref)  # CUB validated against the oracle on a prefix, then used as device oracle
     assert oracle.check_u32(head, to_np_u32(ref[: 1 << 16]))[0] == 0
     out = torch.empty_like(x)
-    for algo in ["csdl_reg", "csdl_tma", "rts", "csdl_fallback"]:
+    for algo in ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"]:
         total = torch.zeros(1, dtype=torch.int32, device="cuda")
         ps.scan(x, out, algo=algo, total_out=total)
         ps.check()
@@ -296,7 +297,7 @@ def test_reduce_matches_oracle(ps, oracle):
         assert int(to_np_u32(got)[0]) == want
 
 
-@pytest.mark.parametrize("algo", ["csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
+@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
 def test_carry_slots_fold_into_lookback(gps, ps, oracle, algo):
     """Two 'ranks' on one GPU: totals published as tagged slots, tile 0 sums the upstream ones."""
     from gpuprefixsums_b200.sharded import pack_slot
@@ -353,7 +354,7 @@ def test_error_behaviour(gps, ps):
 # ---------------------------------------------------------------------------------------
 # 64-bit sizes: more than 2^32 keys on one GPU (the 2-GPU shard of the 2^33-key case)
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ["csdl", "rts", "csdl_tma"])
+@pytest.mark.parametrize("algo", ["csdl", "csdl_reg", "rts", "csdl_tma"])
 def test_more_than_2p32_keys(gps, algo):
     n = (1 << 32) + 12_345
     free, _ = torch.cuda.mem_get_info()
@@ -375,7 +376,7 @@ def test_more_than_2p32_keys(gps, algo):
 # ---------------------------------------------------------------------------------------
 # scratch bookkeeping that replaces the reference's per-launch memsets
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ["csdl_reg", "csdl_tma", "csdl_fallback"])
+@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "csdl_fallback"])
 def test_epoch_and_ticket_counter_wraparound(gps, oracle, algo):
     """Descriptors are epoch-tagged and the ticket counter is never reset: both must
     survive their wrap (2^30 launches / 2^32 tickets)."""
@@ -404,7 +405,7 @@ def test_descriptor_protocols_and_tile_order(gps, oracle, protocol, tile_order):
     n = (1 << 23) + 777
     x = oracle.random_u32(n, seed=9)
     want, _ = oracle.scan_u32(x, exclusive=True)
-    for algo in ("csdl_reg", "csdl_tma"):
+    for algo in ("csdl_smem", "csdl_reg", "csdl_tma"):
         out = ps.scan(to_dev_u32(x), algo=algo, exclusive=True)
         ps.check()
         assert np.array_equal(to_np_u32(out), want), (algo, protocol, tile_order)

@@ -20,7 +20,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("algo", ["csdl", "rts", "csdl_tma"])
+@pytest.mark.parametrize("algo", ["csdl", "csdl_reg", "rts", "csdl_tma"])
 @pytest.mark.parametrize("carry_mode", [0, 1])
 def test_single_process_sharded_scan(oracle, algo, carry_mode):
     import gpuprefixsums_b200 as gps

@@ -228,6 +228,18 @@ static void add_reg(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, 
     });
 }
 
+template <typename T, int NT, int V, bool INCL, int G = 4, int REGS = 40>
+static void add_smem(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v)
+{
+    char name[96];
+    snprintf(name, sizeof(name), "csdl_smem<%d,%d>/g%d/r%d", NT, V, G, REGS);
+    auto cfg = std::make_shared<bool>(false);
+    v.emplace_back(name, [&env, cfg](const void* in, void* out) {
+        CarrySpec cs;
+        return launch_csdl_smem<T, NT, V, INCL, 1, G, REGS>(env.s, in, out, env.n, cs, *cfg, 0);
+    });
+}
+
 template <typename T, int NT, int STAGES, bool INCL, int WIN = 2>
 static void add_tma(Env& env, std::vector<std::pair<std::string, LaunchFn>>& v, int max_ctas)
 {
@@ -285,6 +297,22 @@ static void build_variants(Env& env, std::vector<std::pair<std::string, LaunchFn
     add_reg<T, 32, 24, INCL, 1>(env, v);
     add_reg<T, 32, 32, INCL, 1>(env, v);
     add_reg<T, 32, 40, INCL, 1>(env, v);
+    add_smem<T, 128, 8, INCL>(env, v);
+    add_smem<T, 128, 8, INCL, 2>(env, v);
+    add_smem<T, 128, 8, INCL, 8, 48>(env, v);
+    add_smem<T, 128, 8, INCL, 4, 32>(env, v);
+    add_smem<T, 128, 8, INCL, 2, 32>(env, v);
+    add_smem<T, 128, 12, INCL>(env, v);
+    add_smem<T, 128, 12, INCL, 4, 48>(env, v);
+    add_smem<T, 128, 12, INCL, 6, 48>(env, v);
+    add_smem<T, 128, 16, INCL>(env, v);
+    add_smem<T, 96, 8, INCL>(env, v);
+    add_smem<T, 96, 12, INCL>(env, v);
+    add_smem<T, 160, 8, INCL>(env, v);
+    add_smem<T, 192, 8, INCL>(env, v);
+    add_smem<T, 256, 8, INCL>(env, v);
+    add_smem<T, 256, 4, INCL, 4, 32>(env, v);
+    add_smem<T, 64, 16, INCL>(env, v);
     add_tma<T, 512, 2, INCL, 1>(env, v, 0);
     add_tma<T, 256, 2, INCL, 1>(env, v, 0);
     add_tma<T, 384, 2, INCL, 1>(env, v, 0);
@@ -485,6 +513,16 @@ static int run_all(Env& env, const char* filter)
             run_variant(env, name, fl != PF_SKIP_LOOKBACK, [&](const void* in, void* out) {
                 CarrySpec cs;
                 return launch_csdl_reg<T, 64, 24, INCL, 1>(env.s, in, out, env.n, cs, 0);
+            });
+        }
+        for (uint32_t fl : {(uint32_t)PF_STATIC_TILE, (uint32_t)PF_SKIP_LOOKBACK, (uint32_t)(PF_SKIP_LOOKBACK | PF_STATIC_TILE)}) {
+            env.s.flags = fl;
+            char name[96];
+            static bool cfgx = false;
+            snprintf(name, sizeof(name), "exp/smem<128,12>/flags%u", fl);
+            run_variant(env, name, !(fl & PF_SKIP_LOOKBACK), [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_smem<T, 128, 12, INCL, 1>(env.s, in, out, env.n, cs, cfgx, 0);
             });
         }
         env.s.flags = PF_LOOKBACK_WAIT_ALL;
