@@ -17,7 +17,7 @@ A "step" is one pass of the hot path over one batch of synthetic keys:
 through the host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed
 region).  `--impl reference` times the CPU oracle restatement of the reference's serial
 scan on all host threads (the reference's CUDA directory has no CPU implementation and
-its kernels are the GPU baselines reported by tests/test_compare_baselines.py).
+its kernels are the GPU baselines reported by tests/test_compare_baselines_gpu.py).
 """
 from __future__ import annotations
 
@@ -46,12 +46,14 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--algo", default="csdl", help="csdl | csdl_reg | csdl_tma | rts | csdl_fallback")
+    ap.add_argument("--algo", default="csdl", help="csdl | csdl_smem | csdl_reg | csdl_tma | rts | csdl_fallback")
     ap.add_argument("--log2-keys-per-gpu", type=int, default=LOG2_KEYS_PER_GPU)
     ap.add_argument("--log2-total", type=int, default=0, help="N>1: total keys = 2^this (strong-scaling point)")
     ap.add_argument("--carry", default="p2p", choices=["p2p", "nccl"], help="N>1 carry exchange")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="gps_set_option passthrough (tuning), e.g. poll_sleep_ns=100, tile_order=1")
     return ap.parse_args()
 
 
@@ -160,11 +162,19 @@ def run_reference(args) -> None:
 
     oracle = oracle_lib.load()
     threads = os.cpu_count() or 1
-    n = 1 << args.log2_keys_per_gpu  # bounded sample: one GPU's share of the workload per step
+    n = 1 << args.log2_keys_per_gpu  # one GPU's share of the workload per step
     x = oracle.random_u32(n, seed=1)
     out = np.empty_like(x)
-    steps = min(args.steps, 40)  # keep the whole run within a few minutes on any host
-    warm = min(args.warmup, 3)
+    steps, warm = args.steps, max(1, min(args.warmup, 3))
+    # bounded sample: keep the whole run under ~2 minutes on any host by shrinking the
+    # per-step sample (a power of two of the same keys) if one step is too slow
+    t0 = time.perf_counter()
+    oracle.scan_u32_mt(x, out, False, 0, threads)
+    one = time.perf_counter() - t0
+    while n > (1 << 20) and one * (steps + warm) > 120.0:
+        n >>= 1
+        one /= 2
+    x, out = x[:n], out[:n]
     for _ in range(warm):
         oracle.scan_u32_mt(x, out, False, 0, threads)
     t0 = time.perf_counter()
@@ -174,7 +184,7 @@ def run_reference(args) -> None:
     assert oracle.check_u32(x[: 1 << 20], out[: 1 << 20])[0] == 0
     value = n / dt / 1e9
     sample = (f"oracle port of the reference's serial scan, chunked over {threads} host threads; "
-              f"{steps} steps of 2^{args.log2_keys_per_gpu} random uint32 keys (one GPU's share per step)")
+              f"{steps} steps of {n} random uint32 keys each (one GPU's share is 2^{args.log2_keys_per_gpu})")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -235,6 +245,10 @@ def run_ours(args) -> None:
         launches_per_step = (2 + (3 if args.algo == "rts" else 1)) + (1 if args.carry == "nccl" else 0)
         checker = sh.ps
 
+    for kv in args.option:
+        key, _, val = kv.partition("=")
+        checker.set_option(key, int(val))
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -261,8 +275,28 @@ def run_ours(args) -> None:
     ms_per_step = ms_total / args.steps
     value = n_total / (ms_per_step * 1e-3) / 1e9
 
-    # quick correctness guard on what was just timed: out[i]-out[i-1] == x[i], first key
-    assert torch.equal(out[1:1 << 20] - out[:(1 << 20) - 1], x[1:1 << 20]), "scan output failed the difference check"
+    # correctness of what was just timed, on the WHOLE slice (outside the timed region):
+    # (1) out[i] - out[i-1] == x[i] (mod 2^32) everywhere, (2) out[0] == carry + x[0] where the
+    # carry is recomputed independently (torch sums of every rank's slice, all_gathered),
+    # (3) the last output equals carry + slice total.  Together they pin every output.
+    chunk = 1 << 26
+    total = 0
+    for lo_c in range(0, n_local, chunk):
+        hi_c = min(n_local, lo_c + chunk)
+        if hi_c - lo_c > 1:
+            assert torch.equal(out[lo_c + 1:hi_c] - out[lo_c:hi_c - 1], x[lo_c + 1:hi_c]), "difference check failed"
+        if lo_c:
+            assert int(out[lo_c].item() - out[lo_c - 1].item() - x[lo_c].item()) % (1 << 32) == 0
+        total += int(x[lo_c:hi_c].to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
+    total &= 0xFFFFFFFF
+    carry = 0
+    if world > 1:
+        totals = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(totals, torch.tensor([total], dtype=torch.int64, device=dev))
+        carry = sum(int(t.item()) for t in totals[:rank]) & 0xFFFFFFFF
+    if n_local:
+        assert (int(out[0].item()) - carry - int(x[0].item())) % (1 << 32) == 0, "carry / first key check failed"
+        assert (int(out[-1].item()) - carry - total) % (1 << 32) == 0, "slice total check failed"
 
     # ---- end to end through the host-buffer call ----------------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 20)

@@ -47,6 +47,7 @@ SIGNATURES = {
     "gps_destroy": (None, [_vp]),
     "gps_check": (_i32, [_vp, _vp]),
     "gps_set_option": (_i32, [_vp, C.c_char_p, C.c_int64]),
+    "gps_scratch_bytes": (_u64, [_u64]),
     "gps_scan": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gps_scan_carry_slots": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp]),
     "gps_reduce": (_i32, [_vp, _i32, _vp, _u64, _vp, _vp]),

@@ -258,6 +258,12 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
     return GPS_OK;
 }
 
+uint64_t gps_scratch_bytes(uint64_t max_n)
+{
+    const uint64_t tiles = std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
+    return tiles * sizeof(uint64_t) + tiles * 4 + 64;
+}
+
 void gps_destroy(gps_ctx* c)
 {
     if (!c) return;
@@ -315,6 +321,10 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
         // cub::DeviceScan relies on: CTAs are dispatched in index order); register / smem paths
         if (value != 0 && value != 1) return fail(GPS_ERR_INVALID, "tile_order must be 0 or 1");
         c->s.flags = (c->s.flags & ~PF_STATIC_TILE) | (value ? PF_STATIC_TILE : 0u);
+    } else if (!strcmp(key, "lookback")) {
+        // 0 = warp-parallel look-back (default), 1 = single-thread look-back
+        if (value != 0 && value != 1) return fail(GPS_ERR_INVALID, "lookback must be 0 or 1");
+        c->s.flags = (c->s.flags & ~PF_LOOKBACK_SINGLE) | (value ? PF_LOOKBACK_SINGLE : 0u);
     } else if (!strcmp(key, "desc_protocol")) {
         // 0 = atom.exch + ld.relaxed (default), 1 = st.release.gpu + ld.acquire.gpu,
         // 2 = st.relaxed + ld.relaxed  (see gps_common.cuh for the measured cost of each)

@@ -79,6 +79,7 @@ enum : uint32_t {
     PF_DELAY_FIRST = 128u,       // experiment: nanosleep(poll_sleep_ns) once before the first poll
     PF_POLL_ACQUIRE = 256u,      // poll with ld.acquire.gpu (else ld.relaxed.gpu)
     PF_LOOKBACK_WAIT_ALL = 512u, // experiment: consume a window only when all 32 are ready
+    PF_LOOKBACK_SINGLE = 1024u,  // one-thread look-back (reference LookbackSingle, CSDL.cuh:28-47)
 };
 
 enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
@@ -460,6 +461,31 @@ __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, u
     int64_t top = (int64_t)tile - 1;
     uint32_t polls = 0, windows = 0;
     if ((p.flags & PF_DELAY_FIRST) && p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
+    if (p.flags & PF_LOOKBACK_SINGLE) {
+        // the reference's other look-back (ChainedScanDecoupledLookback.cuh:28-47, defined
+        // there but not called): lane 0 walks one descriptor at a time; kept selectable to
+        // measure it (gps_set_option "lookback" = 1).  The reference notes "negligible
+        // performance difference" on its hardware; on B200 see DESIGN.md section 5.
+        if (lane == 0) {
+            while (top >= 0) {
+                const uint64_t d = desc_poll(p, p.desc + top);
+                if (!desc_valid(d, p.epoch)) {
+                    if (watchdog_tick(polls, p.status)) break;
+                    continue;
+                }
+                prefix += from_bits<T>(desc_value(d));
+                ++windows;
+                if (desc_status(d) == ST_INCLUSIVE) break;
+                --top;
+            }
+        }
+        prefix = __shfl_sync(kFullMask, prefix, 0);
+        if (stats) {
+            stats->windows = windows;
+            stats->polls = polls;
+        }
+        return prefix;
+    }
     const bool wait_all = p.flags & PF_LOOKBACK_WAIT_ALL;
     while (true) {
         uint64_t d[WIN];

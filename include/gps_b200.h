@@ -83,9 +83,15 @@ int gps_check(gps_ctx* ctx, void* stream);
  *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)
  *   "desc_protocol" 0 = atom.exch + ld.relaxed (default), 1 = st.release + ld.acquire,
  *                   2 = st.relaxed + ld.relaxed
+ *   "lookback"      0 = warp-parallel (default, LookbackWarp), 1 = single thread
+ *                   (LookbackSingle, ChainedScanDecoupledLookback.cuh:28-47)
  *   "poll_sleep_ns" nanosleep between unsuccessful descriptor polls (default 0)
  *   "host_chunk_keys" chunk size of gps_scan_host (default 2^24; before first use) */
 int gps_set_option(gps_ctx* ctx, const char* key, int64_t value);
+/* Scratch a context of capacity max_n allocates on the device, in bytes (descriptors +
+ * RTS partials + counters) -- the "temp storage size" of the Unity port's caller-owned-
+ * buffer API (GPUPrefixSumsUnity/Runtime/ReduceThenScan.cs:156-279). */
+uint64_t gps_scratch_bytes(uint64_t max_n);
 
 /* ---- scans -------------------------------------------------------------------
  * gps_scan replaces DispatchKernelsInclusive / DispatchKernelsExclusive of

@@ -1,0 +1,26 @@
+"""The drop-in acceptance test: the C++ driver that mirrors the reference's main()
+(GPUPrefixSumsCUDA.cu:14-38) over the C ABI -- same dispatcher classes, same TestAll* /
+BatchTiming* protocol, same stdout lines -- must report every reference test as passed."""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "gpuprefixsums_b200", "bin", "gps_main")
+
+
+def test_gps_main_full_reference_protocol():
+    out = subprocess.run([BIN], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    # CSDL exclusive + inclusive, RTS exclusive + inclusive, EmulatedDeadlock inclusive:
+    # 4097 sizes in [4096, 8192] + 2^26, 2^27, 2^28 each (fully validated here)
+    assert out.stdout.count("4100/4100 All tests passed.") == 5, out.stdout[-3000:]
+    assert "Test failed" not in out.stdout and "failed (" not in out.stdout
+    speeds = [float(m) for m in re.findall(r"Estimated speed at 268435456 32-bit elements: ([0-9.E+]+) keys/sec", out.stdout)]
+    assert len(speeds) == 4  # CSDL, RTS, EmulatedDeadlock, CUB
+    assert speeds[0] > speeds[3], "CSDL should beat cub::DeviceScan"
+    assert "Fallback stats" in out.stdout

@@ -394,6 +394,21 @@ def test_epoch_and_ticket_counter_wraparound(gps, oracle, algo):
     ps.close()
 
 
+def test_single_thread_lookback(gps, oracle):
+    """The reference's LookbackSingle (defined but unused there) as a selectable variant."""
+    ps = gps.PrefixSum(1 << 24)
+    ps.set_option("lookback", 1)
+    n = (1 << 23) + 5
+    x = oracle.random_u32(n, seed=77)
+    want, _ = oracle.scan_u32(x)
+    for algo in ("csdl_smem", "csdl_reg", "csdl_tma"):
+        out = ps.scan(to_dev_u32(x), algo=algo)
+        ps.check()
+        assert np.array_equal(to_np_u32(out), want), algo
+    assert gps._capi.lib.gps_scratch_bytes(1 << 28) == (1 << 16) * 12 + 64
+    ps.close()
+
+
 @pytest.mark.parametrize("protocol", [0, 1, 2])
 @pytest.mark.parametrize("tile_order", [0, 1])
 def test_descriptor_protocols_and_tile_order(gps, oracle, protocol, tile_order):

@@ -515,14 +515,14 @@ static int run_all(Env& env, const char* filter)
                 return launch_csdl_reg<T, 64, 24, INCL, 1>(env.s, in, out, env.n, cs, 0);
             });
         }
-        for (uint32_t fl : {(uint32_t)PF_STATIC_TILE, (uint32_t)PF_SKIP_LOOKBACK, (uint32_t)(PF_SKIP_LOOKBACK | PF_STATIC_TILE)}) {
+        for (uint32_t fl : {(uint32_t)PF_STATIC_TILE, (uint32_t)PF_SKIP_LOOKBACK, (uint32_t)(PF_SKIP_LOOKBACK | PF_STATIC_TILE), (uint32_t)PF_LOOKBACK_SINGLE, (uint32_t)PF_LOOKBACK_WAIT_ALL}) {
             env.s.flags = fl;
             char name[96];
             static bool cfgx = false;
-            snprintf(name, sizeof(name), "exp/smem<128,12>/flags%u", fl);
+            snprintf(name, sizeof(name), "exp/smem<128,8>/flags%u", fl);
             run_variant(env, name, !(fl & PF_SKIP_LOOKBACK), [&](const void* in, void* out) {
                 CarrySpec cs;
-                return launch_csdl_smem<T, 128, 12, INCL, 1>(env.s, in, out, env.n, cs, cfgx, 0);
+                return launch_csdl_smem<T, 128, 8, INCL, 1>(env.s, in, out, env.n, cs, cfgx, 0);
             });
         }
         env.s.flags = PF_LOOKBACK_WAIT_ALL;
