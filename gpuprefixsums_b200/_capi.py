@@ -12,7 +12,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgps_b200.so")
+LIB_PATH = os.environ.get("GPS_B200_LIB") or os.path.join(_HERE, "lib", "libgps_b200.so")  # env: tuning builds
 CUB_LIB_PATH = os.path.join(_HERE, "lib", "libgps_cub.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gps_b200.h")
 
@@ -22,7 +22,7 @@ GPS_ERR_INVALID, GPS_ERR_ALIGNMENT, GPS_ERR_CUDA = -1, -2, -3
 GPS_ERR_WATCHDOG, GPS_ERR_MISMATCH, GPS_ERR_UNSUPPORTED = -4, -5, -6
 ALGO_CSDL, ALGO_CSDL_REG, ALGO_CSDL_TMA, ALGO_CSDL_FALLBACK, ALGO_RTS, ALGO_CSDL_SMEM = 0, 1, 2, 3, 4, 5
 INCLUSIVE, EXCLUSIVE = 0, 1
-U32, F32 = 0, 1
+U32, F32, U64, F64, U32X4 = 0, 1, 2, 3, 4
 NO_STALL = 0xFFFFFFFF
 IPC_HANDLE_BYTES = 64
 
@@ -49,6 +49,7 @@ SIGNATURES = {
     "gps_set_option": (_i32, [_vp, C.c_char_p, C.c_int64]),
     "gps_scratch_bytes": (_u64, [_u64]),
     "gps_scan": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp, _vp]),
+    "gps_scan_wide": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _vp, _vp]),
     "gps_scan_carry_slots": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp]),
     "gps_reduce": (_i32, [_vp, _i32, _vp, _u64, _vp, _vp]),
     "gps_reduce_publish": (_i32, [_vp, _i32, _vp, _u64, C.POINTER(_vp), _u32, _u32, _vp, _vp]),

@@ -19,6 +19,7 @@
 #include "gps_config.h"
 #include "gps_launch.cuh"
 #include "gps_util_kernels.cuh"
+#include "gps_wide.cuh"
 
 using namespace gps;
 
@@ -172,6 +173,37 @@ int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, voi
                                  : dispatch_scan_tk<float, false>(c, algo, in, out, n, cs, st);
 }
 
+template <typename E>
+E wide_zero_host()
+{
+    E z;
+    memset(&z, 0, sizeof(E));
+    return z;
+}
+
+template <typename E, bool INCL>
+int launch_wide(gps_ctx* c, const void* in, void* out, uint64_t n, const void* h_carry, void* total_out,
+                cudaStream_t st)
+{
+    using Tile = WideTile<E, GPS_WIDE_NT, GPS_WIDE_V>;
+    WideParams<E> p{};
+    p.in = in;
+    p.out = out;
+    p.n = n;
+    p.partials = c->s.partials;
+    p.num_tiles = (uint32_t)div_up(n, Tile::TILE_ELEMS);
+    p.carry = wide_zero_host<E>();
+    if (h_carry) memcpy(&p.carry, h_carry, sizeof(E));
+    p.total_out = total_out;
+    if (p.num_tiles > c->s.partials_capacity) return fail(GPS_ERR_INVALID, "n exceeds ctx capacity");
+    if (p.num_tiles) wide_reduce_kernel<E, GPS_WIDE_NT, GPS_WIDE_V><<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+    wide_spine_kernel<E><<<1, 1024, 0, st>>>(p);
+    if (p.num_tiles)
+        wide_propagate_kernel<E, GPS_WIDE_NT, GPS_WIDE_V, INCL><<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+    GPS_CUDA(cudaGetLastError());
+    return GPS_OK;
+}
+
 int fill_publish(PublishList& pl, uint64_t* const* dst, uint32_t n_dst, uint32_t tag)
 {
     if (n_dst > (uint32_t)kMaxPublish)
@@ -246,7 +278,7 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
     cudaError_t e = cudaMalloc(&c->s.desc, (size_t)c->s.desc_tiles * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->s.counter, 64);
     c->s.partials_capacity = c->s.desc_tiles;
-    if (e == cudaSuccess) e = cudaMalloc(&c->s.partials, (size_t)c->s.partials_capacity * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&c->s.partials, (size_t)c->s.partials_capacity * 16);  // up to 16-byte elements
     if (e == cudaSuccess) e = cudaMemset(c->s.desc, 0, (size_t)c->s.desc_tiles * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemset(c->s.counter, 0, 64);
     if (e != cudaSuccess) {
@@ -261,7 +293,7 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
 uint64_t gps_scratch_bytes(uint64_t max_n)
 {
     const uint64_t tiles = std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
-    return tiles * sizeof(uint64_t) + tiles * 4 + 64;
+    return tiles * sizeof(uint64_t) + tiles * 16 + 64;
 }
 
 void gps_destroy(gps_ctx* c)
@@ -356,6 +388,33 @@ int gps_scan(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* 
     cs.carry_bits = carry_in_bits;
     cs.total_out = d_total_out;
     return dispatch_scan(c, algo, kind, dtype, d_in, d_out, n, cs, (cudaStream_t)stream);
+}
+
+int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
+                  const void* h_carry, void* d_total_out, void* stream)
+{
+    (void)algo;
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    if (kind != GPS_INCLUSIVE && kind != GPS_EXCLUSIVE) return fail(GPS_ERR_INVALID, "bad kind %d", kind);
+    const uint64_t es = dtype == GPS_U64 || dtype == GPS_F64 ? 8 : dtype == GPS_U32X4 ? 16 : 0;
+    if (!es) return fail(GPS_ERR_INVALID, "gps_scan_wide takes GPS_U64, GPS_F64 or GPS_U32X4");
+    if (n > c->max_n * 4 / es) return fail(GPS_ERR_INVALID, "n * element size exceeds ctx capacity");
+    if (n && (!d_in || !d_out)) return fail(GPS_ERR_INVALID, "null data pointer");
+    if (!aligned16(d_in) || !aligned16(d_out)) return fail(GPS_ERR_ALIGNMENT, "data pointers must be 16-byte aligned");
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool incl = kind == GPS_INCLUSIVE;
+    switch (dtype) {
+        case GPS_U64:
+            return incl ? launch_wide<uint64_t, true>(c, d_in, d_out, n, h_carry, d_total_out, st)
+                        : launch_wide<uint64_t, false>(c, d_in, d_out, n, h_carry, d_total_out, st);
+        case GPS_F64:
+            return incl ? launch_wide<double, true>(c, d_in, d_out, n, h_carry, d_total_out, st)
+                        : launch_wide<double, false>(c, d_in, d_out, n, h_carry, d_total_out, st);
+        default:
+            return incl ? launch_wide<u32x4, true>(c, d_in, d_out, n, h_carry, d_total_out, st)
+                        : launch_wide<u32x4, false>(c, d_in, d_out, n, h_carry, d_total_out, st);
+    }
 }
 
 int gps_scan_carry_slots(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out,

@@ -60,6 +60,14 @@
 #define GPS_SMEM_V 8
 #endif
 
+// wide elements (uint64 / float64 / vec4<u32>): threads x 128-bit vectors per thread
+#ifndef GPS_WIDE_NT
+#define GPS_WIDE_NT 128
+#endif
+#ifndef GPS_WIDE_V
+#define GPS_WIDE_V 8
+#endif
+
 // GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = smem-resident tile.
 // Chosen by measurement at 2^28 keys: smem-resident tile 837,
 // register path 785-805, TMA ring 659 Gkeys/s

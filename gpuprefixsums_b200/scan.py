@@ -102,6 +102,31 @@ class PrefixSum:
                            _stream_ptr(stream, self.device)))
         return out
 
+    def scan_wide(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, exclusive: bool = False,
+                  struct4: bool = False, carry=None, total_out: Optional[torch.Tensor] = None,
+                  stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """uint64 (torch.int64 bit pattern), float64, or -- with struct4=True on an int32 tensor
+        whose last dimension is 4 -- the four-lane struct scan."""
+        inp, out = self._prep(inp, out)
+        if struct4:
+            if inp.dtype not in (torch.int32, torch.uint32) or inp.numel() % 4:
+                raise TypeError("struct4 needs an int32 tensor with a multiple of 4 values")
+            dtype, n, host = capi.U32X4, inp.numel() // 4, (C.c_uint32 * 4)
+            cval = host(*[int(v) & 0xFFFFFFFF for v in carry]) if carry is not None else None
+        elif inp.dtype == torch.int64:
+            dtype, n = capi.U64, inp.numel()
+            cval = C.c_uint64(int(carry) & 0xFFFFFFFFFFFFFFFF) if carry is not None else None
+        elif inp.dtype == torch.float64:
+            dtype, n = capi.F64, inp.numel()
+            cval = C.c_double(float(carry)) if carry is not None else None
+        else:
+            raise TypeError(f"scan_wide: unsupported dtype {inp.dtype}")
+        check(lib.gps_scan_wide(self._ctx, capi.ALGO_RTS, _kind(exclusive), dtype, inp.data_ptr(), out.data_ptr(), n,
+                                C.cast(C.byref(cval), C.c_void_p) if cval is not None else None,
+                                total_out.data_ptr() if total_out is not None else None,
+                                _stream_ptr(stream, self.device)))
+        return out
+
     def scan_carry_slots(self, inp: torch.Tensor, out: Optional[torch.Tensor], slots_ptr: int, n_slots: int,
                          n_carry: int, tag: int, *, algo="csdl", exclusive: bool = False,
                          total_out: Optional[torch.Tensor] = None,

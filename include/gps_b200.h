@@ -59,7 +59,14 @@ enum gps_algo {
     GPS_ALGO_CSDL_SMEM = 5      /*   one TMA bulk load per CTA, tile resident in smem  */
 };
 enum gps_kind { GPS_INCLUSIVE = 0, GPS_EXCLUSIVE = 1 };
-enum gps_dtype { GPS_U32 = 0, GPS_F32 = 1 };
+enum gps_dtype {
+    GPS_U32 = 0,
+    GPS_F32 = 1,
+    /* wide element types: gps_scan_wide only */
+    GPS_U64 = 2,
+    GPS_F64 = 3,
+    GPS_U32X4 = 4 /* struct scan: four interleaved uint32 lanes per 16-byte element */
+};
 
 /* ---- library / device ------------------------------------------------------- */
 int gps_abi_version(void);
@@ -103,6 +110,15 @@ uint64_t gps_scratch_bytes(uint64_t max_n);
  * still writes d_total_out. */
 int gps_scan(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void* d_out,
              uint64_t n, uint32_t carry_in_bits, void* d_total_out, void* stream);
+
+/* Scans over wide elements: GPS_U64, GPS_F64 (8-byte keys) and GPS_U32X4,
+ * the four-lane struct scan of GPUPrefixSumsWebGPUapis/SharedShaders/csdldf_struct.wgsl:61-316
+ * (validate.wgsl:50-60).  n counts ELEMENTS (8 or 16 bytes each); n * element size must not
+ * exceed 4 * max_n bytes of the ctx.  h_carry (nullable) points to one element on the HOST
+ * that seeds the scan; d_total_out (nullable) receives carry + sum on the device.  Runs the
+ * Reduce-then-Scan structure whatever `algo` says (deterministic for float64); asynchronous. */
+int gps_scan_wide(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void* d_out,
+                  uint64_t n, const void* h_carry, void* d_total_out, void* stream);
 
 /* Same, with the carry read ON THE DEVICE by tile 0 from 64-bit carry slots
  * {value bits : 32 | tag : 32} (low word = value).  Tile 0 polls all `n_slots` slots

@@ -123,6 +123,62 @@ uint64_t oracle_check_u32(const uint32_t *in, const uint32_t *cand, uint64_t n, 
     return errs;
 }
 
+/* ---- wide elements ------------------------------------------------ */
+/* uint64: same serial loops, arithmetic mod 2^64 */
+uint64_t oracle_scan_u64(const uint64_t *in, uint64_t *out, uint64_t n, int exclusive, uint64_t carry)
+{
+    uint64_t sum = carry;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (exclusive) out[i] = sum;
+        sum += in[i];
+        if (!exclusive) out[i] = sum;
+    }
+    return sum;
+}
+
+/* four-lane struct scan: GPUPrefixSumsWebGPUapis/SharedShaders/csdldf_struct.wgsl scans an
+ * array of vec4<u32> lane by lane; validate.wgsl:50-60 checks all-ones input against
+ * out[i] == (i >> 2) + 1 over the flat u32 view.  n counts vec4 elements. */
+void oracle_scan_u32x4(const uint32_t *in, uint32_t *out, uint64_t n, int exclusive, const uint32_t carry[4],
+                       uint32_t total[4])
+{
+    uint32_t sum[4] = {carry[0], carry[1], carry[2], carry[3]};
+    for (uint64_t i = 0; i < n; ++i)
+        for (int l = 0; l < 4; ++l) {
+            if (exclusive) out[4 * i + l] = sum[l];
+            sum[l] += in[4 * i + l];
+            if (!exclusive) out[4 * i + l] = sum[l];
+        }
+    for (int l = 0; l < 4; ++l) total[l] = sum[l];
+}
+
+/* float64: serial scan accumulated in long double (x87 80-bit on this platform), returns
+ * the count of candidate values with |cand - ref| > rtol * sum|x| + atol */
+uint64_t oracle_check_f64(const double *in, const double *cand, uint64_t n, int exclusive, double carry,
+                          double rtol, double atol, double *max_rel_out)
+{
+    long double sum = carry, asum = carry < 0 ? -carry : carry, max_rel = 0.0L;
+    uint64_t errs = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const long double t = in[i];
+        if (!exclusive) {
+            sum += t;
+            asum += t < 0 ? -t : t;
+        }
+        long double d = (long double)cand[i] - sum;
+        if (d < 0) d = -d;
+        if (!(d <= (long double)rtol * asum + atol)) ++errs;
+        const long double rel = d / (asum > 1e-300L ? asum : 1e-300L);
+        if (rel > max_rel) max_rel = rel;
+        if (exclusive) {
+            sum += t;
+            asum += t < 0 ? -t : t;
+        }
+    }
+    if (max_rel_out) *max_rel_out = (double)max_rel;
+    return errs;
+}
+
 /* ---- all-ones closed form (UtilityKernels.cuh:22-38) ------------------------- */
 uint64_t oracle_validate_ones(const uint32_t *scan, uint64_t n, int exclusive)
 {

@@ -41,6 +41,14 @@ class Oracle:
                                          C.POINTER(C.c_double)]
         lib.oracle_check_u32.restype = C.c_uint64
         lib.oracle_check_u32.argtypes = [_u32p, _u32p, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(C.c_uint64)]
+        _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+        lib.oracle_scan_u64.restype = C.c_uint64
+        lib.oracle_scan_u64.argtypes = [_u64p, _u64p, C.c_uint64, C.c_int, C.c_uint64]
+        lib.oracle_scan_u32x4.restype = None
+        lib.oracle_scan_u32x4.argtypes = [_u32p, _u32p, C.c_uint64, C.c_int, _u32p, _u32p]
+        lib.oracle_check_f64.restype = C.c_uint64
+        lib.oracle_check_f64.argtypes = [_f64p, _f64p, C.c_uint64, C.c_int, C.c_double, C.c_double, C.c_double,
+                                         C.POINTER(C.c_double)]
         lib.oracle_validate_ones.restype = C.c_uint64
         lib.oracle_validate_ones.argtypes = [_u32p, C.c_uint64, C.c_int]
         lib.oracle_init_random_d3d12.restype = None
@@ -81,6 +89,28 @@ class Oracle:
                                          np.ascontiguousarray(cand, dtype=np.uint32), x.size, int(exclusive),
                                          carry & 0xFFFFFFFF, C.byref(first))
         return errs, first.value
+
+    def scan_u64(self, x: np.ndarray, exclusive: bool = False, carry: int = 0):
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        out = np.empty_like(x)
+        total = self.lib.oracle_scan_u64(x, out, x.size, int(exclusive), carry & 0xFFFFFFFFFFFFFFFF)
+        return out, total
+
+    def scan_u32x4(self, x: np.ndarray, exclusive: bool = False, carry=(0, 0, 0, 0)):
+        """x: flat uint32 view of n vec4 elements (4n values)."""
+        x = np.ascontiguousarray(x, dtype=np.uint32)
+        out = np.empty_like(x)
+        total = np.zeros(4, dtype=np.uint32)
+        self.lib.oracle_scan_u32x4(x, out, x.size // 4, int(exclusive), np.asarray(carry, dtype=np.uint32), total)
+        return out, total
+
+    def check_f64(self, x: np.ndarray, cand: np.ndarray, exclusive: bool = False, carry: float = 0.0,
+                  rtol: float = 1e-13, atol: float = 1e-300):
+        mx = C.c_double(0.0)
+        errs = self.lib.oracle_check_f64(np.ascontiguousarray(x, dtype=np.float64),
+                                         np.ascontiguousarray(cand, dtype=np.float64), x.size, int(exclusive),
+                                         float(carry), rtol, atol, C.byref(mx))
+        return errs, mx.value
 
     def validate_ones(self, scan: np.ndarray, exclusive: bool) -> int:
         return self.lib.oracle_validate_ones(np.ascontiguousarray(scan, dtype=np.uint32), scan.size, int(exclusive))
