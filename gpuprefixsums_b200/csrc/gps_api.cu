@@ -67,6 +67,7 @@ struct gps_ctx {
     // cached launch geometry
     int tma_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [dtype][kind]
     bool smem_configured[2][2] = {{false, false}, {false, false}};
+    bool wide_configured[5][2][2] = {};             // [dtype][kind][rts]
     // host pipeline (lazy)
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
     void* stage[kHostBufs] = {nullptr, nullptr, nullptr};
@@ -181,25 +182,62 @@ E wide_zero_host()
     return z;
 }
 
+// bytes of wide-element data one ctx can scan = 4 * max_n; descriptor words for the smallest
+// wide tile (GPS_WIDE_NT x GPS_WIDE_V vectors of 16 bytes) at W = 4 words per element
+constexpr uint64_t kWideTileBytes = (uint64_t)GPS_WIDE_NT * GPS_WIDE_V * 16;
+inline uint64_t wide_desc_words(uint64_t max_n) { return std::max<uint64_t>(1, div_up(max_n * 4, kWideTileBytes)) * 8; }
+
 template <typename E, bool INCL>
-int launch_wide(gps_ctx* c, const void* in, void* out, uint64_t n, const void* h_carry, void* total_out,
-                cudaStream_t st)
+int launch_wide(gps_ctx* c, int algo, const void* in, void* out, uint64_t n, const void* h_carry, void* total_out,
+                bool& configured, cudaStream_t st)
 {
-    using Tile = WideTile<E, GPS_WIDE_NT, GPS_WIDE_V>;
+    using S = WideShape<E, GPS_WIDE_NT, GPS_WIDE_V>;
+    Scratch& s = c->s;
     WideParams<E> p{};
     p.in = in;
     p.out = out;
     p.n = n;
-    p.partials = c->s.partials;
-    p.num_tiles = (uint32_t)div_up(n, Tile::TILE_ELEMS);
+    p.desc = s.wdesc;
+    p.counter = s.counter;
+    p.counter_base = s.counter_base;
+    p.partials = s.partials;
+    p.status = s.status;
+    p.num_tiles = (uint32_t)div_up(n, S::TILE_ELEMS);
     p.carry = wide_zero_host<E>();
     if (h_carry) memcpy(&p.carry, h_carry, sizeof(E));
     p.total_out = total_out;
-    if (p.num_tiles > c->s.partials_capacity) return fail(GPS_ERR_INVALID, "n exceeds ctx capacity");
-    if (p.num_tiles) wide_reduce_kernel<E, GPS_WIDE_NT, GPS_WIDE_V><<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
-    wide_spine_kernel<E><<<1, 1024, 0, st>>>(p);
-    if (p.num_tiles)
-        wide_propagate_kernel<E, GPS_WIDE_NT, GPS_WIDE_V, INCL><<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+    if ((uint64_t)p.num_tiles * 2 * S::W > s.wdesc_words || p.num_tiles > s.partials_capacity)
+        return fail(GPS_ERR_INVALID, "n exceeds ctx capacity");
+    if (p.num_tiles == 0) {  // only the carry travels
+        wide_spine_kernel<E><<<1, 1024, 0, st>>>(p);
+        GPS_CUDA(cudaGetLastError());
+        return GPS_OK;
+    }
+    if (algo == GPS_ALGO_RTS) {
+        auto kern = wide_scan_kernel<E, GPS_WIDE_NT, GPS_WIDE_V, INCL, false, GPS_WIDE_REGS>;
+        if (!configured) {
+            GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+            configured = true;
+        }
+        wide_reduce_kernel<E, GPS_WIDE_NT, GPS_WIDE_V><<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+        wide_spine_kernel<E><<<1, 1024, 0, st>>>(p);
+        kern<<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+    } else {
+        auto kern = wide_scan_kernel<E, GPS_WIDE_NT, GPS_WIDE_V, INCL, true, GPS_WIDE_REGS>;
+        if (!configured) {
+            GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+            configured = true;
+        }
+        if (++s.wepoch == 0) {  // wrap: epoch values would alias -> clear once
+            GPS_CUDA(cudaMemsetAsync(s.wdesc, 0, (size_t)s.wdesc_words * sizeof(uint64_t), st));
+            s.wepoch = 1;
+        }
+        p.epoch = s.wepoch;
+        kern<<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+        s.counter_base += p.num_tiles;  // one claim per CTA
+    }
     GPS_CUDA(cudaGetLastError());
     return GPS_OK;
 }
@@ -277,10 +315,13 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
     c->s.desc_tiles = (uint32_t)std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
     cudaError_t e = cudaMalloc(&c->s.desc, (size_t)c->s.desc_tiles * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc(&c->s.counter, 64);
-    c->s.partials_capacity = c->s.desc_tiles;
+    c->s.wdesc_words = wide_desc_words(max_n);
+    c->s.partials_capacity = (uint32_t)std::max<uint64_t>(c->s.desc_tiles, c->s.wdesc_words / 8);  // wide tiles may be smaller
     if (e == cudaSuccess) e = cudaMalloc(&c->s.partials, (size_t)c->s.partials_capacity * 16);  // up to 16-byte elements
     if (e == cudaSuccess) e = cudaMemset(c->s.desc, 0, (size_t)c->s.desc_tiles * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMemset(c->s.counter, 0, 64);
+    if (e == cudaSuccess) e = cudaMalloc(&c->s.wdesc, (size_t)c->s.wdesc_words * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMemset(c->s.wdesc, 0, (size_t)c->s.wdesc_words * sizeof(uint64_t));
     if (e != cudaSuccess) {
         gps_destroy(c);
         return fail(GPS_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(e));
@@ -293,7 +334,8 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
 uint64_t gps_scratch_bytes(uint64_t max_n)
 {
     const uint64_t tiles = std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
-    return tiles * sizeof(uint64_t) + tiles * 16 + 64;
+    const uint64_t wwords = wide_desc_words(max_n);
+    return tiles * sizeof(uint64_t) + std::max(tiles, wwords / 8) * 16 + 64 + wwords * sizeof(uint64_t);
 }
 
 void gps_destroy(gps_ctx* c)
@@ -303,6 +345,7 @@ void gps_destroy(gps_ctx* c)
     cudaFree(c->s.desc);
     cudaFree(c->s.counter);
     cudaFree(c->s.partials);
+    cudaFree(c->s.wdesc);
     for (int i = 0; i < kHostBufs; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]);
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
@@ -393,27 +436,36 @@ int gps_scan(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* 
 int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
                   const void* h_carry, void* d_total_out, void* stream)
 {
-    (void)algo;
     if (!c) return fail(GPS_ERR_INVALID, "null ctx");
     if (kind != GPS_INCLUSIVE && kind != GPS_EXCLUSIVE) return fail(GPS_ERR_INVALID, "bad kind %d", kind);
-    const uint64_t es = dtype == GPS_U64 || dtype == GPS_F64 ? 8 : dtype == GPS_U32X4 ? 16 : 0;
-    if (!es) return fail(GPS_ERR_INVALID, "gps_scan_wide takes GPS_U64, GPS_F64 or GPS_U32X4");
+    if (algo != GPS_ALGO_CSDL && algo != GPS_ALGO_RTS)
+        return fail(GPS_ERR_INVALID, "gps_scan_wide takes GPS_ALGO_CSDL or GPS_ALGO_RTS");
+    const uint64_t es = dtype == GPS_U64 || dtype == GPS_F64 ? 8 : dtype == GPS_U32X4 ? 16
+                        : dtype == GPS_U32 || dtype == GPS_F32 ? 4 : 0;
+    if (!es) return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
     if (n > c->max_n * 4 / es) return fail(GPS_ERR_INVALID, "n * element size exceeds ctx capacity");
     if (n && (!d_in || !d_out)) return fail(GPS_ERR_INVALID, "null data pointer");
     if (!aligned16(d_in) || !aligned16(d_out)) return fail(GPS_ERR_ALIGNMENT, "data pointers must be 16-byte aligned");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const bool incl = kind == GPS_INCLUSIVE;
+    bool& cfg = c->wide_configured[dtype][incl ? 0 : 1][algo == GPS_ALGO_RTS ? 1 : 0];
     switch (dtype) {
+        case GPS_U32:  // the blocked-tile kernel at W = 1, kept to compare it with gps_scan's kernels
+            return incl ? launch_wide<uint32_t, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
+                        : launch_wide<uint32_t, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
+        case GPS_F32:
+            return incl ? launch_wide<float, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
+                        : launch_wide<float, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
         case GPS_U64:
-            return incl ? launch_wide<uint64_t, true>(c, d_in, d_out, n, h_carry, d_total_out, st)
-                        : launch_wide<uint64_t, false>(c, d_in, d_out, n, h_carry, d_total_out, st);
+            return incl ? launch_wide<uint64_t, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
+                        : launch_wide<uint64_t, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
         case GPS_F64:
-            return incl ? launch_wide<double, true>(c, d_in, d_out, n, h_carry, d_total_out, st)
-                        : launch_wide<double, false>(c, d_in, d_out, n, h_carry, d_total_out, st);
+            return incl ? launch_wide<double, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
+                        : launch_wide<double, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
         default:
-            return incl ? launch_wide<u32x4, true>(c, d_in, d_out, n, h_carry, d_total_out, st)
-                        : launch_wide<u32x4, false>(c, d_in, d_out, n, h_carry, d_total_out, st);
+            return incl ? launch_wide<u32x4, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
+                        : launch_wide<u32x4, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
     }
 }
 

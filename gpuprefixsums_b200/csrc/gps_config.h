@@ -60,12 +60,19 @@
 #define GPS_SMEM_V 8
 #endif
 
-// wide elements (uint64 / float64 / vec4<u32>): threads x 128-bit vectors per thread
+// wide elements (uint64 / float64 / vec4<u32>), gps_wide.cuh: NT threads x V (odd) 16-byte
+// vectors per thread, tile resident in shared memory; REGS = register budget per thread.
+// Measured at 1 GiB in + 1 GiB out on B200 (profiles/r01_wide_sweep.txt), useful GB/s for
+// uint64 / vec4<u32>: <256,9> 6508 / 6178 (default), <256,11> 6372 / 6208, <128,15> 6458 / 6039,
+// <128,13> 6454 / 5864, <128,9> 6423 / 5357, <128,7> 6045 / 4596, <64,21> 6427 / 5141.
 #ifndef GPS_WIDE_NT
-#define GPS_WIDE_NT 128
+#define GPS_WIDE_NT 256
 #endif
 #ifndef GPS_WIDE_V
-#define GPS_WIDE_V 8
+#define GPS_WIDE_V 9
+#endif
+#ifndef GPS_WIDE_REGS
+#define GPS_WIDE_REGS 40
 #endif
 
 // GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = smem-resident tile.

@@ -30,6 +30,10 @@ struct Scratch {
     uint32_t poll_sleep_ns = 0;
     uint32_t flags = 0;
     unsigned long long* prof = nullptr;  // optional profiling counters (tuning harness)
+    // wide-element chained scan (gps_wide.cuh): 2*W words per tile, own epoch counter
+    uint64_t* wdesc = nullptr;
+    uint64_t wdesc_words = 0;
+    uint32_t wepoch = 0;
 };
 
 // everything a scan launch needs besides the buffers

@@ -4,10 +4,31 @@
 // the reference's CUDA port is uint32 only; its WebGPU port
 // ships a struct scan (GPUPrefixSumsWebGPUapis/SharedShaders/csdldf_struct.wgsl:61-316,
 // validated by validate.wgsl:50-60: all-ones input -> out[i] == (i >> 2) + 1 over the flat
-// u32 view).  Here the wide element types run through the Reduce-then-Scan structure of
-// gps_rts.cuh (no tile descriptors, so no 128/256-bit descriptor protocol is needed and the
-// result is deterministic for float64): one CTA per 24 KB tile, 128-bit coalesced
-// accesses, the same lane-strided layout and branch-free PTX scan steps.
+// u32 view).
+//
+// Why this is not the uint32 kernel with a wider type: a lane-strided tile needs one warp
+// scan per 512-byte row, i.e. 5 shuffles per 32-bit word of the element per row.  At the
+// HBM rate an SM has ~22 clocks per row and issues one shuffle per clock: uint32 spends 7,
+// uint64 ~14, vec4<u32> ~26 -- the struct scan would be SHUFFLE bound (the first version of
+// this file, lane-strided Reduce-then-Scan in registers, ran at 2.3-3.4 TB/s of useful
+// bytes).  So the wide kernels use a BLOCKED tile instead:
+//   * one TMA bulk load (cp.async.bulk) brings the whole tile into shared memory, as in
+//     gps_csdl_smem.cuh;
+//   * thread t owns the V consecutive 16-byte vectors [t*V, (t+1)*V) of the tile; V is ODD,
+//     so the LDS.128/STS.128 of a quarter-warp fall into 8 distinct 16-byte bank groups
+//     (stride V*16 B, V coprime to 8): bank-conflict free without padding or swizzle;
+//   * the thread scans its run serially; ONE warp scan of the thread totals per tile (5 steps
+//     x W shuffles, W = 32-bit words per element) replaces the V per-row warp scans;
+//   * results are written back into the same shared memory and leave with one TMA bulk
+//     store per warp (cp.async.bulk.global.shared::cta), so the global writes are full
+//     lines although each thread produced a contiguous run.
+// Chained scan (default): tile descriptors are 2*W 64-bit words {value32 | epoch32} per
+// tile -- W words for the AGGREGATE and W separate words for the INCLUSIVE prefix.  Nothing
+// is ever overwritten within a launch, every word validates itself by its epoch, and a set
+// counts as published when all its W words carry the launch's epoch: no 128/256-bit atomic
+// is needed and a torn update cannot be mistaken for a value.  Reduce-then-Scan
+// (GPS_ALGO_RTS) runs the same tile kernel with the prefix taken from the spine; it is
+// deterministic for float64.
 #pragma once
 #include "gps_common.cuh"
 
@@ -32,6 +53,35 @@ __device__ __forceinline__ E wide_zero()
         return u32x4{0u, 0u, 0u, 0u};
     else
         return E(0);
+}
+
+// ---- 32-bit words of an element (descriptor payload) --------------------------------------
+template <typename E>
+__device__ __forceinline__ uint32_t wide_word(const E& v, uint32_t w)
+{
+    if constexpr (std::is_same<E, u32x4>::value) {
+        return w == 0 ? v.a : w == 1 ? v.b : w == 2 ? v.c : v.d;
+    } else if constexpr (std::is_same<E, uint64_t>::value) {
+        return w ? (uint32_t)(v >> 32) : (uint32_t)v;
+    } else if constexpr (std::is_same<E, double>::value) {
+        const uint64_t b = (uint64_t)__double_as_longlong(v);
+        return w ? (uint32_t)(b >> 32) : (uint32_t)b;
+    } else {
+        return to_bits(v);
+    }
+}
+template <typename E>
+__device__ __forceinline__ E wide_from_words(const uint32_t* w)
+{
+    if constexpr (std::is_same<E, u32x4>::value) {
+        return u32x4{w[0], w[1], w[2], w[3]};
+    } else if constexpr (std::is_same<E, uint64_t>::value) {
+        return ((uint64_t)w[1] << 32) | w[0];
+    } else if constexpr (std::is_same<E, double>::value) {
+        return __longlong_as_double((long long)(((uint64_t)w[1] << 32) | w[0]));
+    } else {
+        return from_bits<E>(w[0]);
+    }
 }
 
 // ---- branch-free Kogge-Stone steps for the wide types (see scan_step_up in gps_common.cuh)
@@ -71,15 +121,6 @@ __device__ __forceinline__ u32x4 scan_step_up(u32x4 v, int d)
 }
 
 template <typename E>
-__device__ __forceinline__ E wide_shfl(E v, int src)
-{
-    if constexpr (std::is_same<E, u32x4>::value)
-        return u32x4{__shfl_sync(kFullMask, v.a, src), __shfl_sync(kFullMask, v.b, src),
-                     __shfl_sync(kFullMask, v.c, src), __shfl_sync(kFullMask, v.d, src)};
-    else
-        return __shfl_sync(kFullMask, v, src);
-}
-template <typename E>
 __device__ __forceinline__ E wide_shfl_up1(E v)
 {
     if constexpr (std::is_same<E, u32x4>::value)
@@ -94,6 +135,8 @@ __device__ __forceinline__ E wide_warp_reduce(E v)
     if constexpr (std::is_same<E, u32x4>::value) {
         return u32x4{__reduce_add_sync(kFullMask, v.a), __reduce_add_sync(kFullMask, v.b),
                      __reduce_add_sync(kFullMask, v.c), __reduce_add_sync(kFullMask, v.d)};
+    } else if constexpr (std::is_same<E, uint32_t>::value) {
+        return __reduce_add_sync(kFullMask, v);
     } else {
 #pragma unroll
         for (int m = 16; m; m >>= 1) v = v + __shfl_xor_sync(kFullMask, v, m);
@@ -110,7 +153,7 @@ __device__ __forceinline__ E wide_warp_inclusive_scan(E v)
 template <typename E>
 __device__ __forceinline__ E wide_exclusive_of(E inc, E raw, uint32_t lane)
 {
-    if constexpr (std::is_same<E, double>::value) {
+    if constexpr (std::is_floating_point<E>::value) {
         const E t = wide_shfl_up1(inc);
         return lane ? t : E(0);
     } else {
@@ -118,156 +161,292 @@ __device__ __forceinline__ E wide_exclusive_of(E inc, E raw, uint32_t lane)
     }
 }
 
-// ---- tile: V 128-bit vectors per thread, lane-strided; KPV elements per vector -------------
-template <typename E, int NT, int V>
-struct WideTile {
-    static constexpr int KPV = 16 / (int)sizeof(E);
-    static constexpr int NW = NT / 32;
-    static constexpr uint32_t TILE_VEC = NT * V;
-    static constexpr uint32_t TILE_ELEMS = TILE_VEC * KPV;
-    union Vec {
-        uint4 u;
-        E e[KPV];
-    };
-    E x[V][KPV];
-    E lane_excl[V];
-    E warp_total;
-
-    __device__ __forceinline__ static uint64_t vec_base(uint64_t tile, uint32_t warp, uint32_t lane)
-    {
-        return tile * TILE_VEC + (uint64_t)warp * (32u * V) + lane;
-    }
-    // elements at index >= n read as zero (n counts ELEMENTS)
-    __device__ __forceinline__ void load(const void* in, uint64_t vbase, uint64_t n, bool full)
-    {
-        const uint4* in4 = reinterpret_cast<const uint4*>(in);
-        const E* in1 = reinterpret_cast<const E*>(in);
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            const uint64_t v = vbase + 32u * k;
-            if (full || (v + 1u) * KPV <= n) {
-                Vec t;
-                t.u = ldg_stream(in4 + v);
-#pragma unroll
-                for (int c = 0; c < KPV; ++c) x[k][c] = t.e[c];
-            } else {
-#pragma unroll
-                for (int c = 0; c < KPV; ++c) x[k][c] = (v * KPV + c < n) ? in1[v * KPV + c] : wide_zero<E>();
-            }
-        }
-    }
-    __device__ __forceinline__ E row_sum(int k) const
-    {
-        E s = x[k][0];
-#pragma unroll
-        for (int c = 1; c < KPV; ++c) s = s + x[k][c];
-        return s;
-    }
-    __device__ __forceinline__ E thread_sum() const
-    {
-        E s = row_sum(0);
-#pragma unroll
-        for (int k = 1; k < V; ++k) s = s + row_sum(k);
-        return s;
-    }
-    __device__ __forceinline__ void scan_warp(uint32_t lane)
-    {
-        E rs[V], inc[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) inc[k] = rs[k] = row_sum(k);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) inc[k] = scan_step_up(inc[k], d);
-        }
-        E run = wide_zero<E>();
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            lane_excl[k] = run + wide_exclusive_of(inc[k], rs[k], lane);
-            run = run + wide_shfl(inc[k], 31);
-        }
-        warp_total = run;
-    }
-    template <bool INCLUSIVE>
-    __device__ __forceinline__ void store(void* out, uint64_t vbase, uint64_t n, bool full, E prefix) const
-    {
-        uint4* out4 = reinterpret_cast<uint4*>(out);
-        E* out1 = reinterpret_cast<E*>(out);
-#pragma unroll
-        for (int k = 0; k < V; ++k) {
-            Vec t;
-            E run = prefix + lane_excl[k];
-#pragma unroll
-            for (int c = 0; c < KPV; ++c) {
-                if (INCLUSIVE) {
-                    run = run + x[k][c];
-                    t.e[c] = run;
-                } else {
-                    t.e[c] = run;
-                    run = run + x[k][c];
-                }
-            }
-            const uint64_t v = vbase + 32u * k;
-            if (full || (v + 1u) * KPV <= n) {
-                stg_stream(out4 + v, t.u);
-            } else {
-#pragma unroll
-                for (int c = 0; c < KPV; ++c)
-                    if (v * KPV + c < n) out1[v * KPV + c] = t.e[c];
-            }
-        }
-    }
-};
-
+// ---- parameters ----------------------------------------------------------------------------
 template <typename E>
 struct WideParams {
     const void* in;
     void* out;
-    uint64_t n;          // elements
-    void* partials;      // one element per tile
+    uint64_t n;             // ELEMENTS
+    uint64_t* desc;         // chained: 2*W words per tile {value32 | epoch32}: W aggregate, W inclusive
+    uint32_t* counter;      // tile-claim counter shared with the 32-bit kernels, never reset
+    uint32_t counter_base;
+    uint32_t epoch;         // != 0, unique per launch until the host clears desc
     uint32_t num_tiles;
+    void* partials;         // RTS: one element per tile
+    uint32_t* status;       // watchdog word
     E carry;
-    void* total_out;     // nullable, one element
+    void* total_out;        // nullable, one element: carry + sum of all elements
 };
 
-template <typename E, int NW>
-__device__ __forceinline__ void wide_block_scan(const E* s_warp, uint32_t warp, uint32_t lane, E& warp_prefix,
-                                                E& aggregate)
+template <typename E, int NT, int V>
+struct WideShape {
+    static_assert(V % 2 == 1, "V must be odd: conflict-free LDS.128 at stride V*16 bytes");
+    static constexpr int W = (int)sizeof(E) / 4;     // 32-bit words per element
+    static constexpr int KPV = 16 / (int)sizeof(E);  // elements per 16-byte vector
+    static constexpr int NW = NT / 32;
+    static constexpr uint32_t TILE_VEC = NT * V;
+    static constexpr uint32_t TILE_ELEMS = TILE_VEC * KPV;
+    static constexpr uint32_t TILE_BYTES = TILE_VEC * 16;
+    static constexpr uint32_t WARP_VEC = 32 * V;
+    union Vec {
+        uint4 u;
+        E e[KPV];
+    };
+};
+
+__device__ __forceinline__ void wide_desc_publish(uint64_t* ptr, uint32_t value, uint32_t epoch)
 {
-    const E raw = lane < (uint32_t)NW ? s_warp[lane] : wide_zero<E>();
-    const E inc = wide_warp_inclusive_scan(raw);
-    const E exc = wide_exclusive_of(inc, raw, lane);
-    warp_prefix = wide_shfl(exc, (int)warp);
-    aggregate = wide_shfl(inc, NW - 1);
+    uint64_t v = ((uint64_t)epoch << 32) | value;
+    asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(v) : "memory");
 }
 
-// kernel 1: tile sums, back to front (L2 reuse by kernel 3, see gps_rts.cuh)
-template <typename E, int NT, int V>
-__global__ void __launch_bounds__(NT) wide_reduce_kernel(const __grid_constant__ WideParams<E> p)
+// Warp-parallel decoupled look-back over the two-set descriptors: lane l examines tile
+// (top - l); a tile is INCLUSIVE when its W inclusive words carry this launch's epoch,
+// AGGREGATE when its W aggregate words do, NOT_READY otherwise.  Same window policy as
+// lookback_warp (gps_common.cuh): consume the ready run nearest to the tile, stop at the
+// nearest INCLUSIVE in it.
+template <typename E>
+__device__ __forceinline__ E wide_lookback(const WideParams<E>& p, uint32_t tile, uint32_t lane)
 {
-    using Tile = WideTile<E, NT, V>;
-    __shared__ E s_red[NT / 32];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t tile = p.num_tiles - 1u - blockIdx.x;
-    const bool full = ((uint64_t)tile + 1u) * Tile::TILE_ELEMS <= p.n;
-    Tile t;
-    t.load(p.in, Tile::vec_base(tile, warp, lane), p.n, full);
-    const E ws = wide_warp_reduce(t.thread_sum());
-    if (lane == 0) s_red[warp] = ws;
+    constexpr int W = (int)sizeof(E) / 4;
+    E prefix = wide_zero<E>();
+    int64_t top = (int64_t)tile - 1;
+    uint32_t polls = 0;
+    while (true) {
+        const int64_t idx = top - (int64_t)lane;
+        uint32_t state = ST_INCLUSIVE;  // virtual entry below tile 0: INCLUSIVE / 0
+        E v = wide_zero<E>();
+        if (idx >= 0) {
+            const uint64_t* d = p.desc + (uint64_t)idx * (2 * W);
+            uint64_t w[2 * W];
+            if constexpr (W == 1) {
+                w[0] = ld_relaxed_gpu(d);
+                w[1] = ld_relaxed_gpu(d + 1);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2 * W; i += 2)
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];"
+                                 : "=l"(w[i]), "=l"(w[i + 1])
+                                 : "l"(d + i)
+                                 : "memory");
+            }
+            bool agg_ok = true, inc_ok = true;
+#pragma unroll
+            for (int i = 0; i < W; ++i) {
+                agg_ok = agg_ok && (uint32_t)(w[i] >> 32) == p.epoch;
+                inc_ok = inc_ok && (uint32_t)(w[W + i] >> 32) == p.epoch;
+            }
+            state = inc_ok ? ST_INCLUSIVE : agg_ok ? ST_AGGREGATE : ST_NOT_READY;
+            uint32_t words[W];
+#pragma unroll
+            for (int i = 0; i < W; ++i) words[i] = (uint32_t)(inc_ok ? w[W + i] : w[i]);
+            v = wide_from_words<E>(words);
+        }
+        const uint32_t not_ready = __ballot_sync(kFullMask, state == ST_NOT_READY);
+        const uint32_t run = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
+        const uint32_t in_run = run >= 32u ? kFullMask : ((1u << run) - 1u);
+        const uint32_t incl = __ballot_sync(kFullMask, state == ST_INCLUSIVE) & in_run;
+        if (incl) {
+            const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
+            prefix = prefix + wide_warp_reduce(lane <= nearest ? v : wide_zero<E>());
+            break;
+        }
+        if (run == 0u) {
+            const bool bail = watchdog_tick(polls, p.status);
+            if (__any_sync(kFullMask, bail)) break;  // warp-uniform exit
+            continue;
+        }
+        prefix = prefix + wide_warp_reduce(lane < run ? v : wide_zero<E>());
+        top -= (int64_t)run;
+    }
+    return prefix;
+}
+
+// ---- the tile kernel: chained scan (CHAINED) or RTS propagate ------------------------------
+template <typename E, int NT, int V, bool INCLUSIVE, bool CHAINED, int REGS = 40>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
+    wide_scan_kernel(const __grid_constant__ WideParams<E> p)
+{
+    using S = WideShape<E, NT, V>;
+    using Vec = typename S::Vec;
+    constexpr int W = S::W, KPV = S::KPV, NW = S::NW;
+    __shared__ __align__(128) uint4 s_data[S::TILE_VEC];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) E s_warp[NW];
+    __shared__ __align__(16) E s_prefix;
+    __shared__ uint32_t s_tile;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        const uint32_t t = CHAINED ? atomicAdd(p.counter, 1u) - p.counter_base : blockIdx.x;
+        s_tile = t;
+        if (((uint64_t)t + 1u) * S::TILE_ELEMS <= p.n) {
+            mbar_arrive_expect_tx(&s_bar, S::TILE_BYTES);
+            bulk_load(s_data, reinterpret_cast<const unsigned char*>(p.in) + (uint64_t)t * S::TILE_BYTES,
+                      S::TILE_BYTES, &s_bar);
+        }
+    }
     __syncthreads();
-    if (warp == 0) {
-        const E tot = wide_warp_reduce(lane < (uint32_t)(NT / 32) ? s_red[lane] : wide_zero<E>());
-        if (lane == 0) reinterpret_cast<E*>(p.partials)[tile] = tot;
+    const uint32_t tile = s_tile;
+    const bool full = ((uint64_t)tile + 1u) * S::TILE_ELEMS <= p.n;
+    const uint32_t v0 = tid * V;  // this thread's first vector within the tile
+
+    if (full) {
+        if (!mbar_wait_bounded(&s_bar, 0u)) {  // never expected; do not hang the GPU
+            atomicOr(p.status, STATUS_WATCHDOG);
+            return;
+        }
+    } else {
+        // partial (last) tile: guarded loads through the LSU, elements at index >= n read as 0;
+        // each thread only re-reads what it wrote itself until the warp-level copy-out
+        const E* in1 = reinterpret_cast<const E*>(p.in);
+#pragma unroll 1
+        for (int k = 0; k < V; ++k) {
+            const uint64_t e0 = ((uint64_t)tile * S::TILE_VEC + v0 + k) * KPV;
+            Vec t;
+#pragma unroll
+            for (int c = 0; c < KPV; ++c) t.e[c] = e0 + c < p.n ? in1[e0 + c] : wide_zero<E>();
+            s_data[v0 + k] = t.u;
+        }
+    }
+
+    // ---- pass 1: thread total -> one warp scan per tile -> aggregate first
+    E acc = wide_zero<E>();
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        Vec t;
+        t.u = s_data[v0 + k];
+#pragma unroll
+        for (int c = 0; c < KPV; ++c) acc = acc + t.e[c];
+    }
+    const E inc = wide_warp_inclusive_scan(acc);
+    const E thread_excl = wide_exclusive_of(inc, acc, lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    E warp_prefix = wide_zero<E>(), aggregate = wide_zero<E>();
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        const E w = s_warp[j];
+        if ((uint32_t)j < warp) warp_prefix = warp_prefix + w;
+        aggregate = aggregate + w;
+    }
+
+    E tile_prefix;
+    if constexpr (CHAINED) {
+        if (warp == 0) {
+            uint64_t* d = p.desc + (uint64_t)tile * (2 * W);
+            if (tile != 0 && lane < (uint32_t)W) wide_desc_publish(d + lane, wide_word(aggregate, lane), p.epoch);
+            const E prefix = tile == 0 ? p.carry : wide_lookback<E>(p, tile, lane);
+            const E inclusive = prefix + aggregate;
+            if (lane < (uint32_t)W) wide_desc_publish(d + W + lane, wide_word(inclusive, lane), p.epoch);
+            if (lane == 0) {
+                s_prefix = prefix;
+                if (tile == p.num_tiles - 1 && p.total_out) *reinterpret_cast<E*>(p.total_out) = inclusive;
+            }
+        }
+        __syncthreads();
+        tile_prefix = s_prefix;
+    } else {
+        tile_prefix = reinterpret_cast<const E*>(p.partials)[tile];
+    }
+
+    // ---- pass 2: serial scan of the thread's run, in place in shared memory
+    E run = (tile_prefix + warp_prefix) + thread_excl;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        Vec t;
+        t.u = s_data[v0 + k];
+#pragma unroll
+        for (int c = 0; c < KPV; ++c) {
+            const E x = t.e[c];
+            if (INCLUSIVE) {
+                run = run + x;
+                t.e[c] = run;
+            } else {
+                t.e[c] = run;
+                run = run + x;
+            }
+        }
+        s_data[v0 + k] = t.u;
+    }
+
+    // ---- the warp's 32*V vectors are contiguous in the tile and in memory
+    const uint64_t warp_vec0 = (uint64_t)tile * S::TILE_VEC + (uint64_t)warp * S::WARP_VEC;
+    if (full) {
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(reinterpret_cast<unsigned char*>(p.out) + warp_vec0 * 16u, s_data + warp * S::WARP_VEC,
+                       S::WARP_VEC * 16u);
+            bulk_commit();
+            bulk_wait_read<0>();  // shared memory must outlive the engine's read
+        }
+    } else {
+        __syncwarp();
+        const E* s_e = reinterpret_cast<const E*>(s_data + warp * S::WARP_VEC);
+        E* out1 = reinterpret_cast<E*>(p.out);
+        const uint64_t e0 = warp_vec0 * KPV;
+#pragma unroll 1
+        for (uint32_t i = lane; i < S::WARP_VEC * KPV; i += 32u)
+            if (e0 + i < p.n) out1[e0 + i] = s_e[i];
     }
 }
 
-// kernel 2: one-block spine over the tile sums, 4 per thread per coalesced step
+// ---- RTS kernel 1: tile sums (tiles of the same extent as wide_scan_kernel's), visited
+// back to front so that the front of the array is what L2 still holds for kernel 3
+template <typename E, int NT, int V>
+__global__ void __launch_bounds__(NT) wide_reduce_kernel(const __grid_constant__ WideParams<E> p)
+{
+    using S = WideShape<E, NT, V>;
+    using Vec = typename S::Vec;
+    constexpr int KPV = S::KPV;
+    __shared__ __align__(16) E s_red[S::NW];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t tile = p.num_tiles - 1u - blockIdx.x;
+    const bool full = ((uint64_t)tile + 1u) * S::TILE_ELEMS <= p.n;
+    const uint4* in4 = reinterpret_cast<const uint4*>(p.in);
+    const E* in1 = reinterpret_cast<const E*>(p.in);
+    const uint64_t vbase = (uint64_t)tile * S::TILE_VEC + (uint64_t)warp * S::WARP_VEC + lane;  // lane-strided
+    Vec t[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const uint64_t v = vbase + 32u * k;
+        if (full || (v + 1u) * KPV <= p.n) {
+            t[k].u = ldg_stream(in4 + v);
+        } else {
+#pragma unroll
+            for (int c = 0; c < KPV; ++c) t[k].e[c] = (v * KPV + c < p.n) ? in1[v * KPV + c] : wide_zero<E>();
+        }
+    }
+    E acc = wide_zero<E>();
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+#pragma unroll
+        for (int c = 0; c < KPV; ++c) acc = acc + t[k].e[c];
+    const E ws = wide_warp_reduce(acc);
+    if (lane == 0) s_red[warp] = ws;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        E tot = s_red[0];
+#pragma unroll
+        for (int j = 1; j < S::NW; ++j) tot = tot + s_red[j];
+        reinterpret_cast<E*>(p.partials)[tile] = tot;
+    }
+}
+
+// ---- RTS kernel 2: one-block spine over the tile sums, 4 per thread per coalesced step;
+// also the n == 0 path of the chained scan (writes total = carry)
 template <typename E>
 __global__ void __launch_bounds__(1024) wide_spine_kernel(const __grid_constant__ WideParams<E> p)
 {
     constexpr int NW = 32, ITEMS = 4;
     constexpr uint32_t CHUNK = 1024 * ITEMS;
-    __shared__ E s_warp[2][NW];
+    __shared__ __align__(16) E s_warp[2][NW];
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     E* partials = reinterpret_cast<E*>(p.partials);
     E running = p.carry;
@@ -286,8 +465,19 @@ __global__ void __launch_bounds__(1024) wide_spine_kernel(const __grid_constant_
         E* sw = s_warp[it & 1u];
         if (lane == 31) sw[warp] = inc;
         __syncthreads();
+        const E raw = sw[lane];
+        const E winc = wide_warp_inclusive_scan(raw);
+        const E wexc = wide_exclusive_of(winc, raw, lane);
         E warp_prefix, total;
-        wide_block_scan<E, NW>(sw, warp, lane, warp_prefix, total);
+        if constexpr (std::is_same<E, u32x4>::value) {
+            warp_prefix = u32x4{__shfl_sync(kFullMask, wexc.a, (int)warp), __shfl_sync(kFullMask, wexc.b, (int)warp),
+                                __shfl_sync(kFullMask, wexc.c, (int)warp), __shfl_sync(kFullMask, wexc.d, (int)warp)};
+            total = u32x4{__shfl_sync(kFullMask, winc.a, 31), __shfl_sync(kFullMask, winc.b, 31),
+                          __shfl_sync(kFullMask, winc.c, 31), __shfl_sync(kFullMask, winc.d, 31)};
+        } else {
+            warp_prefix = __shfl_sync(kFullMask, wexc, (int)warp);
+            total = __shfl_sync(kFullMask, winc, 31);
+        }
         E run = (running + warp_prefix) + lane_excl;
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
@@ -297,30 +487,6 @@ __global__ void __launch_bounds__(1024) wide_spine_kernel(const __grid_constant_
         running = running + total;
     }
     if (threadIdx.x == 0 && p.total_out) *reinterpret_cast<E*>(p.total_out) = running;
-}
-
-// kernel 3: propagate
-#ifndef GPS_WIDE_REGS
-#define GPS_WIDE_REGS 64
-#endif
-template <typename E, int NT, int V, bool INCLUSIVE>
-__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, GPS_WIDE_REGS)) wide_propagate_kernel(const __grid_constant__ WideParams<E> p)
-{
-    using Tile = WideTile<E, NT, V>;
-    __shared__ E s_warp[Tile::NW];
-    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x;
-    const bool full = ((uint64_t)tile + 1u) * Tile::TILE_ELEMS <= p.n;
-    const uint64_t vbase = Tile::vec_base(tile, warp, lane);
-    const E tile_prefix = reinterpret_cast<const E*>(p.partials)[tile];
-    Tile t;
-    t.load(p.in, vbase, p.n, full);
-    t.scan_warp(lane);
-    if (lane == 0) s_warp[warp] = t.warp_total;
-    __syncthreads();
-    E warp_prefix, aggregate;
-    wide_block_scan<E, Tile::NW>(s_warp, warp, lane, warp_prefix, aggregate);
-    t.template store<INCLUSIVE>(p.out, vbase, p.n, full, tile_prefix + warp_prefix);
 }
 
 }  // namespace gps

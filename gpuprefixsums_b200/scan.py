@@ -102,11 +102,14 @@ class PrefixSum:
                            _stream_ptr(stream, self.device)))
         return out
 
-    def scan_wide(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, exclusive: bool = False,
-                  struct4: bool = False, carry=None, total_out: Optional[torch.Tensor] = None,
+    def scan_wide(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, algo="csdl",
+                  exclusive: bool = False, struct4: bool = False, carry=None, total_out: Optional[torch.Tensor] = None,
                   stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """uint64 (torch.int64 bit pattern), float64, or -- with struct4=True on an int32 tensor
-        whose last dimension is 4 -- the four-lane struct scan."""
+        whose last dimension is 4 -- the four-lane struct scan.  algo: "csdl" (chained scan,
+        default) or "rts" (Reduce-then-Scan, deterministic for float64)."""
+        if algo not in ("csdl", "rts"):
+            raise ValueError("scan_wide: algo must be 'csdl' or 'rts'")
         inp, out = self._prep(inp, out)
         if struct4:
             if inp.dtype not in (torch.int32, torch.uint32) or inp.numel() % 4:
@@ -119,9 +122,15 @@ class PrefixSum:
         elif inp.dtype == torch.float64:
             dtype, n = capi.F64, inp.numel()
             cval = C.c_double(float(carry)) if carry is not None else None
+        elif inp.dtype in (torch.int32, torch.uint32):  # blocked-tile kernel at 32 bits (comparison)
+            dtype, n = capi.U32, inp.numel()
+            cval = C.c_uint32(int(carry) & 0xFFFFFFFF) if carry is not None else None
+        elif inp.dtype == torch.float32:
+            dtype, n = capi.F32, inp.numel()
+            cval = C.c_float(float(carry)) if carry is not None else None
         else:
             raise TypeError(f"scan_wide: unsupported dtype {inp.dtype}")
-        check(lib.gps_scan_wide(self._ctx, capi.ALGO_RTS, _kind(exclusive), dtype, inp.data_ptr(), out.data_ptr(), n,
+        check(lib.gps_scan_wide(self._ctx, capi.ALGO_RTS if algo == "rts" else capi.ALGO_CSDL, _kind(exclusive), dtype, inp.data_ptr(), out.data_ptr(), n,
                                 C.cast(C.byref(cval), C.c_void_p) if cval is not None else None,
                                 total_out.data_ptr() if total_out is not None else None,
                                 _stream_ptr(stream, self.device)))

@@ -115,8 +115,12 @@ int gps_scan(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void
  * the four-lane struct scan of GPUPrefixSumsWebGPUapis/SharedShaders/csdldf_struct.wgsl:61-316
  * (validate.wgsl:50-60).  n counts ELEMENTS (8 or 16 bytes each); n * element size must not
  * exceed 4 * max_n bytes of the ctx.  h_carry (nullable) points to one element on the HOST
- * that seeds the scan; d_total_out (nullable) receives carry + sum on the device.  Runs the
- * Reduce-then-Scan structure whatever `algo` says (deterministic for float64); asynchronous. */
+ * that seeds the scan; d_total_out (nullable) receives carry + sum on the device.
+ * algo: GPS_ALGO_CSDL = chained scan with decoupled look-back over two-set epoch-tagged
+ * descriptors (single pass, 2 x element size of HBM traffic per element), GPS_ALGO_RTS =
+ * Reduce-then-Scan (3 x, deterministic for float64).  Both use the blocked shared-memory
+ * tile of csrc/gps_wide.cuh (TMA bulk load and store).  GPS_U32 / GPS_F32 are accepted too:
+ * the same kernel at 32 bits, kept to compare it with gps_scan's kernels.  Asynchronous. */
 int gps_scan_wide(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void* d_out,
                   uint64_t n, const void* h_carry, void* d_total_out, void* stream);
 

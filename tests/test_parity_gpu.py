@@ -405,7 +405,8 @@ def test_single_thread_lookback(gps, oracle):
         out = ps.scan(to_dev_u32(x), algo=algo)
         ps.check()
         assert np.array_equal(to_np_u32(out), want), algo
-    assert gps._capi.lib.gps_scratch_bytes(1 << 28) == (1 << 16) * (8 + 16) + 64
+    wide_words = -(-(4 << 28) // (256 * 9 * 16)) * 8  # gps_wide.cuh descriptors: 8 words per 36 KB tile
+    assert gps._capi.lib.gps_scratch_bytes(1 << 28) == (1 << 16) * (8 + 16) + 64 + wide_words * 8
     ps.close()
 
 
