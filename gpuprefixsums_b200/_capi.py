@@ -44,6 +44,7 @@ SIGNATURES = {
     "gps_device_count": (_i32, [C.POINTER(_i32)]),
     "gps_device_info": (_i32, [_i32, C.c_char_p, C.POINTER(_i32), C.POINTER(_u64), C.POINTER(_u64)]),
     "gps_create": (_i32, [C.POINTER(_vp), _i32, _u64]),
+    "gps_create_with_scratch": (_i32, [C.POINTER(_vp), _i32, _u64, _vp, _u64]),
     "gps_destroy": (None, [_vp]),
     "gps_check": (_i32, [_vp, _vp]),
     "gps_set_option": (_i32, [_vp, C.c_char_p, C.c_int64]),

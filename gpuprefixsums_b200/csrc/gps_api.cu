@@ -61,6 +61,8 @@ struct gps_ctx {
     int device = 0;
     uint64_t max_n = 0;
     Scratch s;                      // descriptors, claim counter, status word, partials
+    void* scratch_base = nullptr;   // one allocation behind all of s.* (the ctx's or the caller's)
+    bool owns_scratch = true;
     // options
     int csdl_variant = 0;           // 0 auto, 1 reg, 2 tma
     uint64_t host_chunk_keys = kHostChunkKeysDefault;
@@ -293,7 +295,29 @@ int gps_set_device(int device)
 // ---------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------
-int gps_create(gps_ctx** out, int device, uint64_t max_n)
+namespace {
+// one device allocation (the ctx's own, or the caller's), carved into 256-byte aligned segments
+struct ScratchLayout {
+    uint64_t desc_tiles, partials_capacity, wdesc_words;
+    uint64_t off_desc, off_partials, off_wdesc, off_counter, total;
+};
+inline uint64_t align256(uint64_t v) { return (v + 255u) & ~(uint64_t)255u; }
+ScratchLayout scratch_layout(uint64_t max_n)
+{
+    ScratchLayout L{};
+    L.desc_tiles = std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
+    L.wdesc_words = wide_desc_words(max_n);
+    L.partials_capacity = std::max<uint64_t>(L.desc_tiles, L.wdesc_words / 8);  // wide tiles may be smaller
+    L.off_desc = 0;
+    L.off_partials = align256(L.off_desc + L.desc_tiles * sizeof(uint64_t));
+    L.off_wdesc = align256(L.off_partials + L.partials_capacity * 16);  // up to 16-byte elements
+    L.off_counter = align256(L.off_wdesc + L.wdesc_words * sizeof(uint64_t));
+    L.total = L.off_counter + 256;
+    return L;
+}
+}  // namespace
+
+int gps_create_with_scratch(gps_ctx** out, int device, uint64_t max_n, void* d_scratch, uint64_t scratch_bytes)
 {
     if (!out) return fail(GPS_ERR_INVALID, "null ctx out");
     *out = nullptr;
@@ -302,6 +326,14 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
     if (device < 0 || device >= count) return fail(GPS_ERR_INVALID, "device %d of %d", device, count);
     if (div_up(max_n, kMinTileKeys) >= (1ull << 31))
         return fail(GPS_ERR_INVALID, "max_n too large");
+    const ScratchLayout L = scratch_layout(max_n);
+    if (d_scratch) {
+        if (reinterpret_cast<uintptr_t>(d_scratch) & 255u)
+            return fail(GPS_ERR_ALIGNMENT, "caller scratch must be 256-byte aligned");
+        if (scratch_bytes < L.total)
+            return fail(GPS_ERR_INVALID, "caller scratch of %llu bytes is smaller than gps_scratch_bytes() = %llu",
+                        (unsigned long long)scratch_bytes, (unsigned long long)L.total);
+    }
     DeviceGuard g(device);
     cudaDeviceProp prop;
     GPS_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -312,40 +344,38 @@ int gps_create(gps_ctx** out, int device, uint64_t max_n)
     c->device = device;
     c->max_n = max_n;
     c->s.sm_count = prop.multiProcessorCount;
-    c->s.desc_tiles = (uint32_t)std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
-    cudaError_t e = cudaMalloc(&c->s.desc, (size_t)c->s.desc_tiles * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&c->s.counter, 64);
-    c->s.wdesc_words = wide_desc_words(max_n);
-    c->s.partials_capacity = (uint32_t)std::max<uint64_t>(c->s.desc_tiles, c->s.wdesc_words / 8);  // wide tiles may be smaller
-    if (e == cudaSuccess) e = cudaMalloc(&c->s.partials, (size_t)c->s.partials_capacity * 16);  // up to 16-byte elements
-    if (e == cudaSuccess) e = cudaMemset(c->s.desc, 0, (size_t)c->s.desc_tiles * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMemset(c->s.counter, 0, 64);
-    if (e == cudaSuccess) e = cudaMalloc(&c->s.wdesc, (size_t)c->s.wdesc_words * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMemset(c->s.wdesc, 0, (size_t)c->s.wdesc_words * sizeof(uint64_t));
+    c->owns_scratch = d_scratch == nullptr;
+    cudaError_t e = cudaSuccess;
+    if (c->owns_scratch) e = cudaMalloc(&c->scratch_base, (size_t)L.total);
+    else c->scratch_base = d_scratch;
+    // descriptors and counters start at zero ONCE; epoch tags replace per-launch clears
+    if (e == cudaSuccess) e = cudaMemset(c->scratch_base, 0, (size_t)L.total);
     if (e != cudaSuccess) {
         gps_destroy(c);
         return fail(GPS_ERR_CUDA, "scratch allocation failed: %s", cudaGetErrorString(e));
     }
+    unsigned char* base = static_cast<unsigned char*>(c->scratch_base);
+    c->s.desc = reinterpret_cast<uint64_t*>(base + L.off_desc);
+    c->s.desc_tiles = (uint32_t)L.desc_tiles;
+    c->s.partials = base + L.off_partials;
+    c->s.partials_capacity = (uint32_t)L.partials_capacity;
+    c->s.wdesc = reinterpret_cast<uint64_t*>(base + L.off_wdesc);
+    c->s.wdesc_words = L.wdesc_words;
+    c->s.counter = reinterpret_cast<uint32_t*>(base + L.off_counter);
     c->s.status = c->s.counter + 1;
     *out = c;
     return GPS_OK;
 }
 
-uint64_t gps_scratch_bytes(uint64_t max_n)
-{
-    const uint64_t tiles = std::max<uint64_t>(1, div_up(max_n, kMinTileKeys));
-    const uint64_t wwords = wide_desc_words(max_n);
-    return tiles * sizeof(uint64_t) + std::max(tiles, wwords / 8) * 16 + 64 + wwords * sizeof(uint64_t);
-}
+int gps_create(gps_ctx** out, int device, uint64_t max_n) { return gps_create_with_scratch(out, device, max_n, nullptr, 0); }
+
+uint64_t gps_scratch_bytes(uint64_t max_n) { return scratch_layout(max_n).total; }
 
 void gps_destroy(gps_ctx* c)
 {
     if (!c) return;
     DeviceGuard g(c->device);
-    cudaFree(c->s.desc);
-    cudaFree(c->s.counter);
-    cudaFree(c->s.partials);
-    cudaFree(c->s.wdesc);
+    if (c->owns_scratch && c->scratch_base) cudaFree(c->scratch_base);
     for (int i = 0; i < kHostBufs; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]);
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);

@@ -50,7 +50,8 @@ class PrefixSum:
     Use one instance per stream; calls are asynchronous on the current torch stream.
     """
 
-    def __init__(self, max_n: int, device: int | torch.device | None = None):
+    def __init__(self, max_n: int, device: int | torch.device | None = None,
+                 scratch: Optional[torch.Tensor] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("gpuprefixsums_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -59,7 +60,18 @@ class PrefixSum:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.max_n = int(max_n)
         self._ctx = C.c_void_p()
-        check(lib.gps_create(C.byref(self._ctx), self.device.index, self.max_n))
+        # scratch: None = the library allocates; a uint8 CUDA tensor of at least
+        # scratch_bytes(max_n) bytes = caller-owned temp storage (Unity-style API)
+        self._scratch = scratch
+        if scratch is None:
+            check(lib.gps_create(C.byref(self._ctx), self.device.index, self.max_n))
+        else:
+            check(lib.gps_create_with_scratch(C.byref(self._ctx), self.device.index, self.max_n,
+                                              scratch.data_ptr(), scratch.numel() * scratch.element_size()))
+
+    @staticmethod
+    def scratch_bytes(max_n: int) -> int:
+        return int(lib.gps_scratch_bytes(int(max_n)))
 
     def close(self) -> None:
         if getattr(self, "_ctx", None) is not None and self._ctx.value:

@@ -95,10 +95,17 @@ int gps_check(gps_ctx* ctx, void* stream);
  *   "poll_sleep_ns" nanosleep between unsuccessful descriptor polls (default 0)
  *   "host_chunk_keys" chunk size of gps_scan_host (default 2^24; before first use) */
 int gps_set_option(gps_ctx* ctx, const char* key, int64_t value);
-/* Scratch a context of capacity max_n allocates on the device, in bytes (descriptors +
- * RTS partials + counters) -- the "temp storage size" of the Unity port's caller-owned-
- * buffer API (GPUPrefixSumsUnity/Runtime/ReduceThenScan.cs:156-279). */
+/* Scratch a context of capacity max_n needs on the device, in bytes (descriptors + RTS
+ * partials + counters) -- the "temp storage size" of the Unity port's caller-owned-buffer
+ * API (GPUPrefixSumsUnity/Runtime/ReduceThenScan.cs:156-279,
+ * ChainedScanDecoupledLookbackDecoupledFallback.cs:120-186). */
 uint64_t gps_scratch_bytes(uint64_t max_n);
+/* gps_create on CALLER-OWNED temp storage: d_scratch is a device buffer of at least
+ * gps_scratch_bytes(max_n) bytes, 256-byte aligned, on `device`.  It is zeroed here once and
+ * never freed by the library; it must outlive the ctx and must not be touched while a scan
+ * of this ctx is in flight.  d_scratch == NULL behaves like gps_create. */
+int gps_create_with_scratch(gps_ctx** ctx, int device, uint64_t max_n, void* d_scratch,
+                            uint64_t scratch_bytes);
 
 /* ---- scans -------------------------------------------------------------------
  * gps_scan replaces DispatchKernelsInclusive / DispatchKernelsExclusive of

@@ -405,8 +405,10 @@ def test_single_thread_lookback(gps, oracle):
         out = ps.scan(to_dev_u32(x), algo=algo)
         ps.check()
         assert np.array_equal(to_np_u32(out), want), algo
-    wide_words = -(-(4 << 28) // (256 * 9 * 16)) * 8  # gps_wide.cuh descriptors: 8 words per 36 KB tile
-    assert gps._capi.lib.gps_scratch_bytes(1 << 28) == (1 << 16) * (8 + 16) + 64 + wide_words * 8
+    # descriptors 8 B + partials 16 B per 4096-key tile, wide descriptors 64 B per 36 KB tile, counters
+    wide_words = -(-(4 << 28) // (256 * 9 * 16)) * 8
+    a256 = lambda v: (v + 255) & ~255
+    assert gps._capi.lib.gps_scratch_bytes(1 << 28) == a256(a256(a256((1 << 16) * 8) + (1 << 16) * 16) + wide_words * 8) + 256
     ps.close()
 
 
@@ -426,3 +428,28 @@ def test_descriptor_protocols_and_tile_order(gps, oracle, protocol, tile_order):
         ps.check()
         assert np.array_equal(to_np_u32(out), want), (algo, protocol, tile_order)
     ps.close()
+
+
+def test_caller_owned_scratch(gps, oracle):
+    """Unity-style caller-owned temp storage (ReduceThenScan.cs:156-279): size
+    query, ctx built on the caller's buffer, every algorithm bit-exact, undersized and
+    misaligned buffers rejected."""
+    n = (1 << 22) + 4099
+    need = gps.PrefixSum.scratch_bytes(n)
+    scratch = torch.full((need,), 0xA5, dtype=torch.uint8, device="cuda")  # dirty on purpose
+    ps = gps.PrefixSum(n, scratch=scratch)
+    x = oracle.random_u32(n, seed=12)
+    want, _ = oracle.scan_u32(x)
+    for algo in ["csdl", "csdl_reg", "csdl_tma", "csdl_smem", "csdl_fallback", "rts"]:
+        for _ in range(2):
+            out = ps.scan(to_dev_u32(x), algo=algo)
+            ps.check()
+            assert np.array_equal(to_np_u32(out), want), algo
+    x64 = np.random.default_rng(1).integers(0, 2**63, size=n // 2, dtype=np.uint64)
+    w64, _ = oracle.scan_u64(x64)
+    assert np.array_equal(ps.scan_wide(torch.from_numpy(x64.view(np.int64)).cuda()).cpu().numpy().view(np.uint64), w64)
+    ps.close()
+    with pytest.raises(gps.GpsError):
+        gps.PrefixSum(n, scratch=scratch[: need - 1])
+    with pytest.raises(gps.GpsError):
+        gps.PrefixSum(n, scratch=torch.empty(need + 256, dtype=torch.uint8, device="cuda")[16:])
