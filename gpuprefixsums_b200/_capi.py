@@ -51,6 +51,8 @@ SIGNATURES = {
     "gps_scratch_bytes": (_u64, [_u64]),
     "gps_scan": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gps_scan_wide": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "gps_sort_scratch_bytes": (_u64, [_u64]),
+    "gps_sort_u32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _vp]),
     "gps_scan_carry_slots": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp]),
     "gps_reduce": (_i32, [_vp, _i32, _vp, _u64, _vp, _vp]),
     "gps_reduce_publish": (_i32, [_vp, _i32, _vp, _u64, C.POINTER(_vp), _u32, _u32, _vp, _vp]),
@@ -117,6 +119,8 @@ def cub_lib() -> C.CDLL:
         _cub = _load(CUB_LIB_PATH)
         _cub.gps_cub_scan.restype = _i32
         _cub.gps_cub_scan.argtypes = [_i32, _i32, _vp, _vp, _u64, _vp]
+        _cub.gps_cub_sort_u32.restype = _i32
+        _cub.gps_cub_sort_u32.argtypes = [_vp, _vp, _vp, _vp, _u64, _i32, _vp]
     return _cub
 
 

@@ -19,6 +19,7 @@
 #include "gps_config.h"
 #include "gps_launch.cuh"
 #include "gps_util_kernels.cuh"
+#include "gps_sort.cuh"
 #include "gps_wide.cuh"
 
 using namespace gps;
@@ -77,6 +78,12 @@ struct gps_ctx {
     uint64_t* chain_slots = nullptr;  // 2 tagged slots chaining chunk totals
     uint32_t chain_tag = 0;
     void* chain_total = nullptr;
+    // radix sort (lazy, grows on demand): 256 descriptors per tile shared by all passes,
+    // 4 x 256 histogram + 4 x 256 digit bases
+    uint64_t* sort_desc = nullptr;
+    uint64_t sort_desc_tiles = 0;
+    uint32_t* sort_hist = nullptr;
+    uint32_t sort_epoch = 0;
 };
 
 namespace {
@@ -259,6 +266,17 @@ int fill_publish(PublishList& pl, uint64_t* const* dst, uint32_t n_dst, uint32_t
 // ---------------------------------------------------------------------------------
 // library / device
 // ---------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t kSortTile = (uint32_t)GPS_SORT_NT * GPS_SORT_KPT;
+
+template <bool PAIRS>
+void launch_sort_pass(const SortParams& p, cudaStream_t st)
+{
+    sort_pass_kernel<GPS_SORT_NT, GPS_SORT_KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS>
+        <<<p.num_tiles, GPS_SORT_NT, 0, st>>>(p);
+}
+}  // namespace
+
 extern "C" {
 
 int gps_abi_version(void) { return GPS_ABI_VERSION; }
@@ -383,6 +401,8 @@ void gps_destroy(gps_ctx* c)
         if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
     }
     if (c->chain_slots) cudaFree(c->chain_slots);
+    if (c->sort_desc) cudaFree(c->sort_desc);
+    if (c->sort_hist) cudaFree(c->sort_hist);
     if (c->chain_total) cudaFree(c->chain_total);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
@@ -497,6 +517,88 @@ int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, v
             return incl ? launch_wide<u32x4, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
                         : launch_wide<u32x4, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
     }
+}
+
+// ---------------------------------------------------------------------------------
+// radix sort: the scan's consumer (gps_sort.cuh)
+// ---------------------------------------------------------------------------------
+uint64_t gps_sort_scratch_bytes(uint64_t n)
+{
+    return std::max<uint64_t>(1, div_up(n, kSortTile)) * kRadix * sizeof(uint64_t) + 2 * 4 * kRadix * sizeof(uint32_t);
+}
+
+int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp, const void* d_vals_in,
+                 void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
+{
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    if (end_bit < 1 || end_bit > 32) return fail(GPS_ERR_INVALID, "end_bit %d outside 1..32", end_bit);
+    if (n >= (1ull << 32)) return fail(GPS_ERR_INVALID, "gps_sort_u32 takes fewer than 2^32 keys");
+    const bool pairs = d_vals_in || d_vals_out || d_vals_tmp;
+    if (n == 0) return GPS_OK;
+    if (!d_keys_in || !d_keys_out || !d_keys_tmp) return fail(GPS_ERR_INVALID, "null key pointer");
+    if (pairs && (!d_vals_in || !d_vals_out || !d_vals_tmp)) return fail(GPS_ERR_INVALID, "null value pointer");
+    if (!aligned16(d_keys_in) || !aligned16(d_keys_out) || !aligned16(d_keys_tmp))
+        return fail(GPS_ERR_ALIGNMENT, "key pointers must be 16-byte aligned");
+    if (d_keys_tmp == d_keys_in || d_keys_tmp == d_keys_out || (pairs && (d_vals_tmp == d_vals_in || d_vals_tmp == d_vals_out)))
+        return fail(GPS_ERR_INVALID, "the tmp buffer must be distinct from in and out");
+    const int passes = (end_bit + 7) / 8;
+    if ((passes & 1) && (d_keys_in == d_keys_out || (pairs && d_vals_in == d_vals_out)))
+        return fail(GPS_ERR_INVALID, "in == out needs an even number of digit passes (end_bit 9..16 or 25..32)");
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t tiles = (uint32_t)div_up(n, kSortTile);
+    if (tiles > c->sort_desc_tiles) {  // grow (synchronous, rare)
+        GPS_CUDA(cudaDeviceSynchronize());
+        if (c->sort_desc) cudaFree(c->sort_desc);
+        c->sort_desc = nullptr;
+        c->sort_desc_tiles = 0;
+        GPS_CUDA(cudaMalloc(&c->sort_desc, (size_t)tiles * kRadix * sizeof(uint64_t)));
+        GPS_CUDA(cudaMemset(c->sort_desc, 0, (size_t)tiles * kRadix * sizeof(uint64_t)));
+        c->sort_desc_tiles = tiles;
+        c->sort_epoch = 0;
+    }
+    if (!c->sort_hist) GPS_CUDA(cudaMalloc(&c->sort_hist, 2 * 4 * kRadix * sizeof(uint32_t)));
+    uint32_t* hist = c->sort_hist;
+    uint32_t* digit_base = c->sort_hist + 4 * kRadix;
+    GPS_CUDA(cudaMemsetAsync(hist, 0, 4 * kRadix * sizeof(uint32_t), st));
+    {
+        constexpr int HNT = 512;
+        const uint32_t per_cta = HNT * 4 * 16;  // 32 Ki keys per CTA
+        const uint32_t grid = (uint32_t)div_up(n, per_cta);
+        sort_hist_kernel<HNT><<<grid, HNT, 0, st>>>((const uint32_t*)d_keys_in, (uint32_t)n, hist, passes, per_cta);
+        sort_digit_base_kernel<<<passes, kRadix, 0, st>>>(hist, digit_base);
+    }
+    // ping-pong so that the last pass lands in `out`
+    const uint32_t* src_k = (const uint32_t*)d_keys_in;
+    const uint32_t* src_v = (const uint32_t*)d_vals_in;
+    for (int pass = 0; pass < passes; ++pass) {
+        const bool to_out = ((passes - 1 - pass) & 1) == 0;
+        SortParams p{};
+        p.keys_in = src_k;
+        p.keys_out = (uint32_t*)(to_out ? d_keys_out : d_keys_tmp);
+        p.vals_in = src_v;
+        p.vals_out = (uint32_t*)(to_out ? d_vals_out : d_vals_tmp);
+        p.n = (uint32_t)n;
+        p.shift = 8u * pass;
+        p.desc = c->sort_desc;
+        p.digit_base = digit_base + pass * kRadix;
+        p.counter = c->s.counter;
+        p.counter_base = c->s.counter_base;
+        if (++c->sort_epoch >= (1u << 30)) {  // wrap: epoch values would alias -> clear once
+            GPS_CUDA(cudaMemsetAsync(c->sort_desc, 0, (size_t)c->sort_desc_tiles * kRadix * sizeof(uint64_t), st));
+            c->sort_epoch = 1;
+        }
+        p.epoch = c->sort_epoch;
+        p.num_tiles = tiles;
+        p.status = c->s.status;
+        if (pairs) launch_sort_pass<true>(p, st);
+        else launch_sort_pass<false>(p, st);
+        c->s.counter_base += tiles;  // one claim per CTA
+        src_k = p.keys_out;
+        src_v = p.vals_out;
+    }
+    GPS_CUDA(cudaGetLastError());
+    return GPS_OK;
 }
 
 int gps_scan_carry_slots(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out,

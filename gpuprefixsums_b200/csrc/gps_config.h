@@ -75,6 +75,20 @@
 #define GPS_WIDE_REGS 40
 #endif
 
+// radix sort digit pass (gps_sort.cuh): NT threads x KPT keys per thread per tile
+#ifndef GPS_SORT_NT
+#define GPS_SORT_NT 256
+#endif
+#ifndef GPS_SORT_KPT
+#define GPS_SORT_KPT 16
+#endif
+#ifndef GPS_SORT_REGS
+#define GPS_SORT_REGS 64
+#endif
+#ifndef GPS_SORT_PAIRS_REGS
+#define GPS_SORT_PAIRS_REGS 96
+#endif
+
 // GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = smem-resident tile.
 // Chosen by measurement at 2^28 keys: smem-resident tile 837,
 // register path 785-805, TMA ring 659 Gkeys/s

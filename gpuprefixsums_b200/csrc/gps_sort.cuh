@@ -1,0 +1,316 @@
+// gps_sort.cuh -- LSD radix sort of uint32 keys (optionally with a 32-bit payload): the
+// downstream consumer of the chained scan (the reference's README.md:7
+// names sorting as what its scans are for -- the sort itself lives in the author's sibling
+// repository GPUSorting, which is NOT part of /root/reference, so nothing here follows
+// reference source; the algorithm is the published "Onesweep" scheme, Adinets & Merrill 2022).
+//
+// One pass over the keys builds all digit histograms up front; then ONE kernel per 8-bit
+// digit reads each key once and writes it once.  Inside that kernel the 256 per-digit
+// offsets of a tile come from a chained scan with decoupled look-back across tiles -- the
+// scan of this library, 256 lanes wide: thread d walks the descriptors of digit d.  Re-used
+// from the scan kernels: the 64-bit descriptor {value:32 | epoch:30 | status:2} (no clearing
+// between passes or sorts: every pass takes a fresh epoch), the atomic tile ticket (forward
+// progress without relying on dispatch order), and the tile fetched by one TMA bulk load into
+// shared memory.
+//   tile pipeline:  TMA -> smem -> registers (warp-striped, KPT keys per thread)
+//                   -> warp-level multi-split ranking (match.any, per-warp digit counters)
+//                   -> tile digit counts -> publish AGGREGATE -> keys to smem in digit order
+//                   -> look-back per digit -> publish INCLUSIVE -> coalesced-by-run scatter
+// Stable, so pairs come out in the unique stable order and 4 passes sort 32 bits.
+#pragma once
+#include "gps_common.cuh"
+
+namespace gps {
+
+constexpr int kRadix = 256;
+
+struct SortParams {
+    const uint32_t* keys_in;
+    uint32_t* keys_out;
+    const uint32_t* vals_in;   // pairs only
+    uint32_t* vals_out;
+    uint32_t n;
+    uint32_t shift;            // 0, 8, 16, 24
+    uint64_t* desc;            // num_tiles * 256 descriptors, shared by all passes
+    const uint32_t* digit_base;  // 256 exclusive digit offsets of THIS pass
+    uint32_t* counter;         // tile-claim counter (never reset)
+    uint32_t counter_base;
+    uint32_t epoch;
+    uint32_t num_tiles;
+    uint32_t* status;          // watchdog word
+};
+
+// digit = byte (shift / 8) of the key: one PRMT (selector 0x4440 + byte index: byte 0 <- that
+// byte of the key, bytes 1..3 <- byte 0 of the zero operand)
+__device__ __forceinline__ uint32_t sort_digit(uint32_t key, uint32_t shift)
+{
+    return __byte_perm(key, 0u, 0x4440u + (shift >> 3));
+}
+
+// 256 descriptors per tile are published by 8 full warps: plain coalesced stores by default
+// (one 256-byte line pair per warp), the scan kernels' atom.exch as an option
+#ifndef GPS_SORT_PUBLISH_ATOMIC
+#define GPS_SORT_PUBLISH_ATOMIC 0
+#endif
+__device__ __forceinline__ void desc_publish_plain(uint64_t* ptr, uint64_t v)
+{
+#if GPS_SORT_PUBLISH_ATOMIC
+    asm volatile("atom.relaxed.gpu.global.exch.b64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(v) : "memory");
+#else
+    st_relaxed_gpu(ptr, v);
+#endif
+}
+
+// ---- all digit histograms in one sweep: hist[pass][digit] -----------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist,
+                                                      int passes, uint32_t keys_per_cta)
+{
+    __shared__ uint32_t s_hist[4 * kRadix];
+    for (uint32_t i = threadIdx.x; i < 4 * kRadix; i += NT) s_hist[i] = 0;
+    __syncthreads();
+    const uint64_t begin = (uint64_t)blockIdx.x * keys_per_cta;  // multiple of 4
+    const uint64_t end = begin + keys_per_cta < n ? begin + keys_per_cta : n;
+    auto add = [&](uint32_t k) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (p < passes) atomicAdd(&s_hist[p * kRadix + ((k >> (8 * p)) & 0xFFu)], 1u);
+    };
+    if (begin < end) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(keys + begin);
+        const uint32_t nvec = (uint32_t)((end - begin) / 4);
+        for (uint32_t v = threadIdx.x; v < nvec; v += NT) {
+            const uint4 k = ldg_stream(k4 + v);
+            add(k.x);
+            add(k.y);
+            add(k.z);
+            add(k.w);
+        }
+        for (uint64_t i = begin + (uint64_t)nvec * 4 + threadIdx.x; i < end; i += NT) add(keys[i]);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < (uint32_t)passes * kRadix; i += NT) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+
+// ---- exclusive scan of each pass's 256-bin histogram: grid = passes, block = 256 -------------
+__global__ void __launch_bounds__(kRadix) sort_digit_base_kernel(const uint32_t* hist, uint32_t* digit_base)
+{
+    __shared__ uint32_t s_warp[kRadix / 32];
+    const uint32_t d = threadIdx.x, lane = d & 31u, warp = d >> 5;
+    const uint32_t c = hist[blockIdx.x * kRadix + d];
+    const uint32_t inc = warp_inclusive_scan(c, lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wp = 0;
+#pragma unroll
+    for (int j = 0; j < kRadix / 32; ++j)
+        if ((uint32_t)j < warp) wp += s_warp[j];
+    digit_base[blockIdx.x * kRadix + d] = wp + inc - c;
+}
+
+// ---- one digit pass ------------------------------------------------------------------------
+// Lanes of the warp holding the same 8-bit digit.  Measured per digit pass at 2^28 keys on
+// B200 (tools/gpu_sort.sh): match.any.sync 2.39 ms; eight ballots written in C++ 1.5 ms (nvcc
+// spends ~8 SASS instructions per bit); eight ballots in PTX, 4 instructions per bit: bit test
+// into a predicate, ballot, select the lane's own bit as a mask, one LOP3 -- see DESIGN.md.
+#ifndef GPS_SORT_MATCH
+#define GPS_SORT_MATCH 2  // 0 = ballots in C++, 1 = match.any.sync, 2 = ballots in PTX
+#endif
+
+template <int B>
+__device__ __forceinline__ void sort_peers_bit(uint32_t& peers, uint32_t d)
+{
+    // peers &= ~(ballot(bit B of d) ^ (own bit B ? ~0 : 0))   [LOP3 0x90 = a & ~(b ^ c)]
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b32 t, bal, sx;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+        "selp.b32 sx, -1, 0, p;\n\t"
+        "lop3.b32 %0, %0, bal, sx, 0x90;\n\t}"
+        : "+r"(peers)
+        : "r"(d), "n"(1 << B));
+}
+
+__device__ __forceinline__ uint32_t sort_peers(uint32_t d)
+{
+#if GPS_SORT_MATCH == 1
+    return __match_any_sync(kFullMask, d);
+#elif GPS_SORT_MATCH == 2
+    uint32_t peers = kFullMask;
+    sort_peers_bit<0>(peers, d);
+    sort_peers_bit<1>(peers, d);
+    sort_peers_bit<2>(peers, d);
+    sort_peers_bit<3>(peers, d);
+    sort_peers_bit<4>(peers, d);
+    sort_peers_bit<5>(peers, d);
+    sort_peers_bit<6>(peers, d);
+    sort_peers_bit<7>(peers, d);
+    return peers;
+#else
+    uint32_t peers = kFullMask;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t bal = __ballot_sync(kFullMask, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? bal : ~bal;
+    }
+    return peers;
+#endif
+}
+
+template <int NT, int KPT, bool PAIRS, int REGS = 64>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kernel(const __grid_constant__ SortParams p)
+{
+    static_assert(NT >= kRadix && NT % 32 == 0, "one thread per digit for the look-back");
+    constexpr int NW = NT / 32;
+    constexpr uint32_t TILE = NT * KPT;
+    constexpr uint32_t WARP_KEYS = 32 * KPT;
+    __shared__ __align__(128) uint32_t s_keys[TILE];
+    __shared__ uint32_t s_whist[NW][kRadix];  // per-warp digit counters -> placement offsets
+    __shared__ uint32_t s_goff[kRadix];       // global position of sorted-tile index 0 of each digit run
+    __shared__ uint32_t s_wtot[kRadix / 32];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tile;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        const uint32_t t = atomicAdd(p.counter, 1u) - p.counter_base;
+        s_tile = t;
+        if (((uint64_t)t + 1u) * TILE <= p.n) {
+            mbar_arrive_expect_tx(&s_bar, TILE * 4u);
+            bulk_load(s_keys, p.keys_in + (uint64_t)t * TILE, TILE * 4u, &s_bar);
+        }
+    }
+#pragma unroll
+    for (uint32_t i = tid; i < (uint32_t)NW * kRadix; i += NT) (&s_whist[0][0])[i] = 0u;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_base = (uint64_t)tile * TILE;
+    const bool full = tile_base + TILE <= p.n;
+    const uint32_t valid = full ? TILE : (uint32_t)(p.n - tile_base);
+
+    if (full) {
+        if (!mbar_wait_bounded(&s_bar, 0u)) {
+            atomicOr(p.status, STATUS_WATCHDOG);
+            return;
+        }
+    } else {
+        // last tile: pad with 0xFFFFFFFF -- digit 255 in every pass, ranked after every real key
+        // of the tile, so the padding occupies exactly the sorted-tile indices >= valid
+#pragma unroll 1
+        for (uint32_t i = tid; i < TILE; i += NT) s_keys[i] = i < valid ? p.keys_in[tile_base + i] : 0xFFFFFFFFu;
+        __syncthreads();
+    }
+
+    // ---- keys to registers, warp-striped: key j of lane l is element warp*32*KPT + j*32 + l
+    uint32_t key[KPT];
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) key[j] = s_keys[warp * WARP_KEYS + j * 32 + lane];
+    uint32_t val[PAIRS ? KPT : 1];
+    if constexpr (PAIRS) {
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+            const uint32_t i = warp * WARP_KEYS + j * 32 + lane;
+            val[j] = (full || i < valid) ? p.vals_in[tile_base + i] : 0u;
+        }
+    }
+
+    // ---- warp-level multi-split: rank of each key among the warp's keys of the same digit,
+    // in (j, lane) order == original order (stability)
+    uint32_t pos[KPT];
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        const uint32_t d = sort_digit(key[j], p.shift);
+        const uint32_t peers = sort_peers(d);
+        const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t pre = s_whist[warp][d];
+        __syncwarp();
+        if (below == 0u) s_whist[warp][d] = pre + __popc(peers);
+        __syncwarp();
+        pos[j] = pre + below;
+    }
+    __syncthreads();  // every warp counted; s_keys no longer needed in its loaded order
+
+    // ---- thread d: digit d's count in the tile, warp-exclusive offsets, block scan over digits
+    uint32_t count = 0, cta_excl = 0;
+    if (tid < (uint32_t)kRadix) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t c = s_whist[w][tid];
+            s_whist[w][tid] = count;
+            count += c;
+        }
+        if (tile != 0) desc_publish_plain(p.desc + (uint64_t)tile * kRadix + tid, pack_desc(count, p.epoch, ST_AGGREGATE));
+        const uint32_t inc = warp_inclusive_scan(count, lane);
+        if (lane == 31) s_wtot[warp] = inc;
+        cta_excl = inc - count;
+    }
+    __syncthreads();
+    if (tid < (uint32_t)kRadix) {
+#pragma unroll
+        for (int j = 0; j < kRadix / 32; ++j)
+            if ((uint32_t)j < warp) cta_excl += s_wtot[j];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s_whist[w][tid] += cta_excl;
+    }
+    __syncthreads();
+
+    // ---- keys into shared memory in digit order
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+        pos[j] += s_whist[warp][sort_digit(key[j], p.shift)];
+        s_keys[pos[j]] = key[j];
+    }
+
+    // ---- chained scan across tiles, one look-back per digit (thread d walks digit d)
+    if (tid < (uint32_t)kRadix) {
+        uint32_t prefix = 0;
+        if (tile != 0) {
+            uint32_t polls = 0;
+            int64_t t = (int64_t)tile - 1;
+            while (t >= 0) {
+                const uint64_t dsc = ld_relaxed_gpu(p.desc + (uint64_t)t * kRadix + tid);
+                if (!desc_valid(dsc, p.epoch)) {
+                    if (watchdog_tick(polls, p.status)) break;
+                    continue;
+                }
+                prefix += desc_value(dsc);
+                if (desc_status(dsc) == ST_INCLUSIVE) break;
+                --t;
+            }
+        }
+        desc_publish_plain(p.desc + (uint64_t)tile * kRadix + tid, pack_desc(prefix + count, p.epoch, ST_INCLUSIVE));
+        s_goff[tid] = p.digit_base[tid] + prefix - cta_excl;
+    }
+    __syncthreads();
+
+    // ---- scatter: consecutive sorted-tile indices of one digit are consecutive in memory
+    uint32_t gidx[PAIRS ? KPT : 1];
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+        const uint32_t i = k * NT + tid;
+        const uint32_t kk = s_keys[i];
+        const uint32_t g = s_goff[sort_digit(kk, p.shift)] + i;
+        if (full || i < valid) p.keys_out[g] = kk;
+        if constexpr (PAIRS) gidx[k] = g;
+    }
+    if constexpr (PAIRS) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) s_keys[pos[j]] = val[j];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KPT; ++k) {
+            const uint32_t i = k * NT + tid;
+            if (full || i < valid) p.vals_out[gidx[k]] = s_keys[i];
+        }
+    }
+}
+
+}  // namespace gps

@@ -148,6 +148,27 @@ class PrefixSum:
                                 _stream_ptr(stream, self.device)))
         return out
 
+    def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None, *, end_bit: int = 32,
+             keys_out: Optional[torch.Tensor] = None, values_out: Optional[torch.Tensor] = None,
+             stream: Optional[torch.cuda.Stream] = None):
+        """Stable ascending LSD radix sort of uint32 keys (int32 bit pattern) on their low
+        `end_bit` bits, optionally moving a 32-bit payload; returns keys or (keys, values)."""
+        if keys.dtype not in (torch.int32, torch.uint32) or not keys.is_cuda or not keys.is_contiguous():
+            raise TypeError("sort: keys must be a contiguous int32/uint32 CUDA tensor")
+        ko = torch.empty_like(keys) if keys_out is None else keys_out
+        kt = torch.empty_like(keys)
+        if values is not None:
+            if values.numel() != keys.numel() or values.element_size() != 4 or not values.is_contiguous():
+                raise TypeError("sort: values must be 32-bit, contiguous, one per key")
+            vo = torch.empty_like(values) if values_out is None else values_out
+            vt = torch.empty_like(values)
+            vptrs = (values.data_ptr(), vo.data_ptr(), vt.data_ptr())
+        else:
+            vo, vptrs = None, (None, None, None)
+        check(lib.gps_sort_u32(self._ctx, keys.data_ptr(), ko.data_ptr(), kt.data_ptr(), *vptrs, keys.numel(),
+                               int(end_bit), _stream_ptr(stream, self.device)))
+        return ko if values is None else (ko, vo)
+
     def scan_carry_slots(self, inp: torch.Tensor, out: Optional[torch.Tensor], slots_ptr: int, n_slots: int,
                          n_carry: int, tag: int, *, algo="csdl", exclusive: bool = False,
                          total_out: Optional[torch.Tensor] = None,
@@ -231,3 +252,14 @@ def cub_scan(inp: torch.Tensor, out: torch.Tensor, exclusive: bool = False) -> t
     if rc != 0:
         raise RuntimeError("cub::DeviceScan failed")
     return out
+
+
+def cub_sort(keys: torch.Tensor, keys_out: torch.Tensor, values: Optional[torch.Tensor] = None,
+             values_out: Optional[torch.Tensor] = None, end_bit: int = 32) -> None:
+    """cub::DeviceRadixSort baseline (libgps_cub.so) on the current stream."""
+    rc = capi.cub_lib().gps_cub_sort_u32(keys.data_ptr(), keys_out.data_ptr(),
+                                         values.data_ptr() if values is not None else None,
+                                         values_out.data_ptr() if values_out is not None else None,
+                                         keys.numel(), end_bit, _stream_ptr(None, keys.device))
+    if rc != 0:
+        raise RuntimeError("cub::DeviceRadixSort failed")

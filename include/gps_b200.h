@@ -131,6 +131,22 @@ int gps_scan(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void
 int gps_scan_wide(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void* d_out,
                   uint64_t n, const void* h_carry, void* d_total_out, void* stream);
 
+/* ---- radix sort: the scan's consumer (reference README.md:7 names sorting
+ * as the downstream use of its scans -- the sort itself is in the sibling repository
+ * GPUSorting, outside /root/reference).  Stable LSD radix sort of uint32 keys, ascending, on
+ * the low `end_bit` bits (32 = full sort), 8 bits per pass.  One sweep builds the digit
+ * histograms; each digit pass reads and writes every key once and obtains its 256 per-tile
+ * digit offsets from a chained scan with decoupled look-back (csrc/gps_sort.cuh).
+ * d_vals_* (all three or none): a 32-bit payload moved with its key.  The result lands in
+ * d_*_out; d_*_tmp is a work buffer of n elements distinct from in and out; in may equal out
+ * when the number of passes ceil(end_bit/8) is even; the input is otherwise preserved.
+ * n < 2^32.  The ctx keeps the sort's own scratch (gps_sort_scratch_bytes(n) bytes, grown on
+ * demand).  Asynchronous on `stream`; gps_check reports a tripped watchdog. */
+uint64_t gps_sort_scratch_bytes(uint64_t n);
+int gps_sort_u32(gps_ctx* ctx, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                 const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,
+                 int end_bit, void* stream);
+
 /* Same, with the carry read ON THE DEVICE by tile 0 from 64-bit carry slots
  * {value bits : 32 | tag : 32} (low word = value).  Tile 0 polls all `n_slots` slots
  * with ld.acquire.sys until their tag equals `tag`, sums the values of the first

@@ -179,6 +179,40 @@ uint64_t oracle_check_f64(const double *in, const double *cand, uint64_t n, int 
     return errs;
 }
 
+/* ---- radix sort consumer -------------------------------------------- */
+/* Stable LSD radix sort of uint32 keys on their low `end_bit` bits, 8 bits per pass, with an
+ * optional 32-bit payload: the textbook counting-sort-per-digit loop (count, exclusive scan
+ * of the 256 counts -- the prefix sum the reference's README.md:7 says its scans exist for --
+ * then a stable scatter).  The sort itself is not part of /root/reference (sibling repository
+ * GPUSorting), so this is pinned in tests/test_oracle.py against numpy's stable sort instead
+ * of reference vectors.  tmp_* are caller-provided work arrays of n elements; the result
+ * lands in keys_out / vals_out.  vals_* may all be NULL. */
+void oracle_sort_u32(const uint32_t *keys_in, uint32_t *keys_out, uint32_t *keys_tmp, const uint32_t *vals_in,
+                     uint32_t *vals_out, uint32_t *vals_tmp, uint64_t n, int end_bit)
+{
+    const int passes = (end_bit + 7) / 8;
+    const uint32_t *sk = keys_in, *sv = vals_in;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int to_out = ((passes - 1 - pass) & 1) == 0;
+        uint32_t *dk = to_out ? keys_out : keys_tmp, *dv = to_out ? vals_out : vals_tmp;
+        const int shift = 8 * pass;
+        uint64_t count[256] = {0}, sum = 0;
+        for (uint64_t i = 0; i < n; ++i) ++count[(sk[i] >> shift) & 0xFF];
+        for (int d = 0; d < 256; ++d) {
+            const uint64_t c = count[d];
+            count[d] = sum;
+            sum += c;
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t pos = count[(sk[i] >> shift) & 0xFF]++;
+            dk[pos] = sk[i];
+            if (sv) dv[pos] = sv[i];
+        }
+        sk = dk;
+        sv = sv ? dv : sv;
+    }
+}
+
 /* ---- all-ones closed form (UtilityKernels.cuh:22-38) ------------------------- */
 uint64_t oracle_validate_ones(const uint32_t *scan, uint64_t n, int exclusive)
 {

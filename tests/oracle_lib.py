@@ -49,6 +49,8 @@ class Oracle:
         lib.oracle_check_f64.restype = C.c_uint64
         lib.oracle_check_f64.argtypes = [_f64p, _f64p, C.c_uint64, C.c_int, C.c_double, C.c_double, C.c_double,
                                          C.POINTER(C.c_double)]
+        lib.oracle_sort_u32.restype = None
+        lib.oracle_sort_u32.argtypes = [C.c_void_p] * 6 + [C.c_uint64, C.c_int]
         lib.oracle_validate_ones.restype = C.c_uint64
         lib.oracle_validate_ones.argtypes = [_u32p, C.c_uint64, C.c_int]
         lib.oracle_init_random_d3d12.restype = None
@@ -111,6 +113,19 @@ class Oracle:
                                          np.ascontiguousarray(cand, dtype=np.float64), x.size, int(exclusive),
                                          float(carry), rtol, atol, C.byref(mx))
         return errs, mx.value
+
+    def sort_u32(self, keys: np.ndarray, vals: np.ndarray | None = None, end_bit: int = 32):
+        """Stable LSD radix sort on the low end_bit bits; returns keys or (keys, vals)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        ko, kt = np.empty_like(keys), np.empty_like(keys)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        if vals is None:
+            self.lib.oracle_sort_u32(ptr(keys), ptr(ko), ptr(kt), None, None, None, keys.size, end_bit)
+            return ko
+        vals = np.ascontiguousarray(vals, dtype=np.uint32)
+        vo, vt = np.empty_like(vals), np.empty_like(vals)
+        self.lib.oracle_sort_u32(ptr(keys), ptr(ko), ptr(kt), ptr(vals), ptr(vo), ptr(vt), keys.size, end_bit)
+        return ko, vo
 
     def validate_ones(self, scan: np.ndarray, exclusive: bool) -> int:
         return self.lib.oracle_validate_ones(np.ascontiguousarray(scan, dtype=np.uint32), scan.size, int(exclusive))

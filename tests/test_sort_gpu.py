@@ -1,0 +1,136 @@
+"""GPU parity for the radix-sort consumer: keys bit-exact against the oracle's
+stable LSD sort (itself pinned on numpy), pairs in the unique stable order; ragged sizes around
+the 4096-key tile, few distinct keys, already-sorted / reversed / constant inputs, partial bit
+ranges, in == out, back-to-back sorts on one ctx (epoch-tagged descriptors, no clearing)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [1, 2, 31, 255, 256, 257, 4095, 4096, 4097, 8191, 8192, 12_289, 100_003, (1 << 20) + 7, (1 << 22) + 4099]
+
+
+@pytest.fixture(scope="module")
+def ps():
+    import gpuprefixsums_b200 as gps
+
+    p = gps.PrefixSum(1 << 24)
+    yield p
+    p.close()
+
+
+def dev(x):
+    return torch.from_numpy(x.view(np.int32)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def test_sort_keys_bit_exact(ps, oracle):
+    for n in SIZES:
+        x = oracle.random_u32(n, seed=300 + n)
+        out = ps.sort(dev(x))
+        ps.check()
+        assert np.array_equal(host(out), oracle.sort_u32(x)), n
+
+
+def test_sort_pairs_stable(ps, oracle):
+    rng = np.random.default_rng(8)
+    for n in SIZES:
+        # few distinct values in every byte: many ties, stability decides the payload order
+        x = (rng.integers(0, 7, size=n, dtype=np.uint64) * 0x01000193 % (1 << 32)).astype(np.uint32)
+        v = np.arange(n, dtype=np.uint32)
+        ko, vo = ps.sort(dev(x), dev(v))
+        ps.check()
+        wk, wv = oracle.sort_u32(x, v)
+        assert np.array_equal(host(ko), wk) and np.array_equal(host(vo), wv), n
+        y = oracle.random_u32(n, seed=500 + n)
+        ko, vo = ps.sort(dev(y), dev(v))
+        wk, wv = oracle.sort_u32(y, v)
+        assert np.array_equal(host(ko), wk) and np.array_equal(host(vo), wv), n
+
+
+@pytest.mark.parametrize("end_bit", [1, 8, 13, 16, 24, 32])
+def test_sort_bit_ranges(ps, oracle, end_bit):
+    n = 300_007
+    x = oracle.random_u32(n, seed=7)
+    v = np.arange(n, dtype=np.uint32)
+    ko, vo = ps.sort(dev(x), dev(v), end_bit=end_bit)
+    ps.check()
+    wk, wv = oracle.sort_u32(x, v, end_bit=end_bit)
+    assert np.array_equal(host(ko), wk) and np.array_equal(host(vo), wv)
+
+
+def test_sort_special_inputs(ps, oracle):
+    n = 200_001
+    cases = {
+        "sorted": np.arange(n, dtype=np.uint32) * np.uint32(17),
+        "reversed": (np.arange(n, dtype=np.uint32) * np.uint32(17))[::-1].copy(),
+        "constant": np.full(n, 0xDEADBEEF, dtype=np.uint32),
+        "all_ff": np.full(n, 0xFFFFFFFF, dtype=np.uint32),  # equals the padding key of the last tile
+        "zeros": np.zeros(n, dtype=np.uint32),
+        "one_digit": (np.arange(n, dtype=np.uint32) % 256) << np.uint32(16),
+    }
+    v = np.arange(n, dtype=np.uint32)
+    for name, x in cases.items():
+        ko, vo = ps.sort(dev(x), dev(v))
+        ps.check()
+        wk, wv = oracle.sort_u32(x, v)
+        assert np.array_equal(host(ko), wk) and np.array_equal(host(vo), wv), name
+
+
+def test_sort_in_place_and_input_preserved(ps, oracle):
+    import gpuprefixsums_b200 as gps
+
+    n = 150_000
+    x = oracle.random_u32(n, seed=2)
+    d = dev(x)
+    out = ps.sort(d)
+    assert np.array_equal(host(d), x)  # input untouched
+    buf = d.clone()
+    ps.sort(buf, keys_out=buf)  # 4 passes: in == out allowed
+    ps.check()
+    assert np.array_equal(host(buf), host(out))
+    with pytest.raises(gps.GpsError):
+        ps.sort(buf, keys_out=buf, end_bit=8)  # odd number of passes
+
+
+def test_sort_repeated_on_one_ctx(ps, oracle):
+    rng = np.random.default_rng(4)
+    for it in range(30):
+        n = int(rng.integers(1, 400_000))
+        x = oracle.random_u32(n, seed=it)
+        assert np.array_equal(host(ps.sort(dev(x))), np.sort(x)), (it, n)
+    # interleaved with scans on the same ctx (shared ticket counter)
+    x = oracle.random_u32(1 << 20, seed=99)
+    want, _ = oracle.scan_u32(x)
+    assert np.array_equal(host(ps.scan(dev(x))), want)
+    assert np.array_equal(host(ps.sort(dev(x))), np.sort(x))
+    ps.check()
+
+
+def test_sort_2p28_sortedness_and_multiset():
+    """BASELINE-size property test: 2^28 random keys come out non-decreasing, with the same
+    multiset (sum of keys, sum of squares mod 2^64) -- checked on the device."""
+    import gpuprefixsums_b200 as gps
+
+    n = 1 << 28
+    big = gps.PrefixSum(1 << 20)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device="cuda", generator=g)
+    out = big.sort(x)
+    big.check()
+    u = lambda t: t.to(torch.int64) & 0xFFFFFFFF
+    ok = True
+    for lo in range(0, n, 1 << 26):  # chunked to bound temporary memory
+        hi = min(n, lo + (1 << 26) + 1)
+        c = u(out[lo:hi])
+        ok = ok and bool((c[1:] >= c[:-1]).all())
+    assert ok, "not sorted"
+    sx, so = u(x), u(out)
+    assert int(sx.sum()) == int(so.sum())
+    assert int((sx * sx).sum()) == int((so * so).sum())  # wraps mod 2^64 identically
+    del sx, so
+    big.close()
