@@ -84,6 +84,8 @@ struct gps_ctx {
     uint64_t sort_desc_tiles = 0;
     uint32_t* sort_hist = nullptr;
     uint32_t sort_epoch = 0;
+    bool sort_configured[2] = {false, false};
+    bool sort_hist_configured = false;
 };
 
 namespace {
@@ -268,12 +270,24 @@ int fill_publish(PublishList& pl, uint64_t* const* dst, uint32_t n_dst, uint32_t
 // ---------------------------------------------------------------------------------
 namespace {
 constexpr uint32_t kSortTile = (uint32_t)GPS_SORT_NT * GPS_SORT_KPT;
+constexpr uint32_t kSortPairsTile = (uint32_t)GPS_SORT_PAIRS_NT * GPS_SORT_PAIRS_KPT;
+constexpr uint32_t kSortMinTile = kSortTile < kSortPairsTile ? kSortTile : kSortPairsTile;
 
 template <bool PAIRS>
-void launch_sort_pass(const SortParams& p, cudaStream_t st)
+cudaError_t launch_sort_pass(const SortParams& p, bool& configured, cudaStream_t st)
 {
-    sort_pass_kernel<GPS_SORT_NT, GPS_SORT_KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS>
-        <<<p.num_tiles, GPS_SORT_NT, 0, st>>>(p);
+    constexpr int NT = PAIRS ? GPS_SORT_PAIRS_NT : GPS_SORT_NT, KPT = PAIRS ? GPS_SORT_PAIRS_KPT : GPS_SORT_KPT;
+    constexpr size_t smem = ((size_t)(PAIRS ? 2 : 1) * NT * KPT + (size_t)(NT / 32) * kRadix) * sizeof(uint32_t);
+    auto kern = sort_pass_kernel<NT, KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS, GPS_SORT_LB>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<p.num_tiles, NT, smem, st>>>(p);
+    return cudaSuccess;
 }
 }  // namespace
 
@@ -524,7 +538,7 @@ int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, v
 // ---------------------------------------------------------------------------------
 uint64_t gps_sort_scratch_bytes(uint64_t n)
 {
-    return std::max<uint64_t>(1, div_up(n, kSortTile)) * kRadix * sizeof(uint64_t) + 2 * 4 * kRadix * sizeof(uint32_t);
+    return std::max<uint64_t>(1, div_up(n, kSortMinTile)) * kRadix * sizeof(uint64_t) + 2 * 4 * kRadix * sizeof(uint32_t);
 }
 
 int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp, const void* d_vals_in,
@@ -546,7 +560,7 @@ int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_ke
         return fail(GPS_ERR_INVALID, "in == out needs an even number of digit passes (end_bit 9..16 or 25..32)");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t tiles = (uint32_t)div_up(n, kSortTile);
+    const uint32_t tiles = (uint32_t)div_up(n, pairs ? kSortPairsTile : kSortTile);
     if (tiles > c->sort_desc_tiles) {  // grow (synchronous, rare)
         GPS_CUDA(cudaDeviceSynchronize());
         if (c->sort_desc) cudaFree(c->sort_desc);
@@ -562,10 +576,13 @@ int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_ke
     uint32_t* digit_base = c->sort_hist + 4 * kRadix;
     GPS_CUDA(cudaMemsetAsync(hist, 0, 4 * kRadix * sizeof(uint32_t), st));
     {
-        constexpr int HNT = 512;
-        const uint32_t per_cta = HNT * 4 * 16;  // 32 Ki keys per CTA
-        const uint32_t grid = (uint32_t)div_up(n, per_cta);
-        sort_hist_kernel<HNT><<<grid, HNT, 0, st>>>((const uint32_t*)d_keys_in, (uint32_t)n, hist, passes, per_cta);
+        if (!c->sort_hist_configured) {
+            GPS_CUDA(cudaFuncSetAttribute(sort_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)kHistSmemBytes));
+            c->sort_hist_configured = true;
+        }
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->s.sm_count, div_up(n, 4 * kHistThreads));
+        sort_hist_kernel<<<grid, kHistThreads, kHistSmemBytes, st>>>((const uint32_t*)d_keys_in, (uint32_t)n, hist, passes);
         sort_digit_base_kernel<<<passes, kRadix, 0, st>>>(hist, digit_base);
     }
     // ping-pong so that the last pass lands in `out`
@@ -591,8 +608,8 @@ int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_ke
         p.epoch = c->sort_epoch;
         p.num_tiles = tiles;
         p.status = c->s.status;
-        if (pairs) launch_sort_pass<true>(p, st);
-        else launch_sort_pass<false>(p, st);
+        GPS_CUDA(pairs ? launch_sort_pass<true>(p, c->sort_configured[1], st)
+                       : launch_sort_pass<false>(p, c->sort_configured[0], st));
         c->s.counter_base += tiles;  // one claim per CTA
         src_k = p.keys_out;
         src_v = p.vals_out;

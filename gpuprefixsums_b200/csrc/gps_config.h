@@ -75,18 +75,33 @@
 #define GPS_WIDE_REGS 40
 #endif
 
-// radix sort digit pass (gps_sort.cuh): NT threads x KPT keys per thread per tile
+// radix sort digit pass (gps_sort.cuh): NT threads x KPT keys per thread per tile.
+// Measured at 2^28 random keys on B200 (profiles/r01_sort_sweep.txt), Gkeys/s keys / pairs:
+// <256,16> LB 4: 50.0 / 44.9 (default); LB 1: 48.7 / 42.4; LB 8: 45.7 / 42.3; LB 16: 37.8 / 38.3;
+// <256,12>: 38.8 / 36.8; <512,8>: 34.4 (keys); <384,12>: 37.0 (keys);
+// cub::DeviceRadixSort (CCCL 2.8.2, onesweep) on the same box: 44.5 / 35.2
 #ifndef GPS_SORT_NT
 #define GPS_SORT_NT 256
 #endif
 #ifndef GPS_SORT_KPT
-#define GPS_SORT_KPT 16
+#define GPS_SORT_KPT 40
 #endif
 #ifndef GPS_SORT_REGS
-#define GPS_SORT_REGS 64
+#define GPS_SORT_REGS 128
+#endif
+// descriptors fetched per look-back round trip (per digit)
+#ifndef GPS_SORT_LB
+#define GPS_SORT_LB 4
+#endif
+// pairs: own tile shape (keys and payload both live in shared memory)
+#ifndef GPS_SORT_PAIRS_NT
+#define GPS_SORT_PAIRS_NT GPS_SORT_NT
+#endif
+#ifndef GPS_SORT_PAIRS_KPT
+#define GPS_SORT_PAIRS_KPT GPS_SORT_KPT
 #endif
 #ifndef GPS_SORT_PAIRS_REGS
-#define GPS_SORT_PAIRS_REGS 96
+#define GPS_SORT_PAIRS_REGS 128
 #endif
 
 // GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = smem-resident tile.

@@ -62,36 +62,49 @@ __device__ __forceinline__ void desc_publish_plain(uint64_t* ptr, uint64_t v)
 }
 
 // ---- all digit histograms in one sweep: hist[pass][digit] -----------------------------------
-template <int NT>
-__global__ void __launch_bounds__(NT) sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist,
-                                                      int passes, uint32_t keys_per_cta)
+// Shared-memory atomics on 4 x 256 counters are bank-conflict bound for random keys (32 random
+// addresses per warp instruction: ~3.5 wavefronts each; first version of this kernel: 0.41 ms
+// at 2^28 keys = 9.3 lanes/clk/SM).  Here every lane owns a private column of the table
+// (counter index = (pass * 256 + digit) * 32 + lane, so bank == lane): conflict free by
+// construction.  128 KB of shared memory, one persistent CTA per SM.
+constexpr int kHistThreads = 1024;
+constexpr size_t kHistSmemBytes = (size_t)4 * kRadix * 32 * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(kHistThreads, 1)
+    sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist, int passes)
 {
-    __shared__ uint32_t s_hist[4 * kRadix];
-    for (uint32_t i = threadIdx.x; i < 4 * kRadix; i += NT) s_hist[i] = 0;
+    extern __shared__ __align__(16) uint32_t s_hist[];  // [4 * 256][32]
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    for (uint32_t i = tid; i < 4u * kRadix * 32u; i += kHistThreads) s_hist[i] = 0u;
     __syncthreads();
-    const uint64_t begin = (uint64_t)blockIdx.x * keys_per_cta;  // multiple of 4
-    const uint64_t end = begin + keys_per_cta < n ? begin + keys_per_cta : n;
     auto add = [&](uint32_t k) {
 #pragma unroll
         for (int p = 0; p < 4; ++p)
-            if (p < passes) atomicAdd(&s_hist[p * kRadix + ((k >> (8 * p)) & 0xFFu)], 1u);
+            if (p < passes) atomicAdd(&s_hist[((p * kRadix + ((k >> (8 * p)) & 0xFFu)) << 5) + lane], 1u);
     };
-    if (begin < end) {
-        const uint4* k4 = reinterpret_cast<const uint4*>(keys + begin);
-        const uint32_t nvec = (uint32_t)((end - begin) / 4);
-        for (uint32_t v = threadIdx.x; v < nvec; v += NT) {
-            const uint4 k = ldg_stream(k4 + v);
-            add(k.x);
-            add(k.y);
-            add(k.z);
-            add(k.w);
-        }
-        for (uint64_t i = begin + (uint64_t)nvec * 4 + threadIdx.x; i < end; i += NT) add(keys[i]);
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    const uint32_t nvec = n / 4u;
+    const uint32_t stride = gridDim.x * kHistThreads;
+    uint32_t v = blockIdx.x * kHistThreads + tid;
+    // two independent loads in flight per thread
+    for (; v + stride < nvec; v += 2u * stride) {
+        const uint4 a = ldg_stream(k4 + v);
+        const uint4 b = ldg_stream(k4 + v + stride);
+        add(a.x); add(a.y); add(a.z); add(a.w);
+        add(b.x); add(b.y); add(b.z); add(b.w);
     }
+    if (v < nvec) {
+        const uint4 a = ldg_stream(k4 + v);
+        add(a.x); add(a.y); add(a.z); add(a.w);
+    }
+    if (blockIdx.x == 0 && tid < (n & 3u)) add(keys[(uint64_t)nvec * 4u + tid]);
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < (uint32_t)passes * kRadix; i += NT) {
-        const uint32_t c = s_hist[i];
-        if (c) atomicAdd(hist + i, c);
+    // thread t folds the 32 columns of counter t (rotated start: conflict free)
+    if (tid < (uint32_t)passes * kRadix) {
+        uint32_t c = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < 32u; ++i) c += s_hist[(tid << 5) + ((i + tid) & 31u)];
+        if (c) atomicAdd(hist + tid, c);
     }
 }
 
@@ -161,15 +174,18 @@ __device__ __forceinline__ uint32_t sort_peers(uint32_t d)
 #endif
 }
 
-template <int NT, int KPT, bool PAIRS, int REGS = 64>
+template <int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kernel(const __grid_constant__ SortParams p)
 {
     static_assert(NT >= kRadix && NT % 32 == 0, "one thread per digit for the look-back");
     constexpr int NW = NT / 32;
     constexpr uint32_t TILE = NT * KPT;
     constexpr uint32_t WARP_KEYS = 32 * KPT;
-    __shared__ __align__(128) uint32_t s_keys[TILE];
-    __shared__ uint32_t s_whist[NW][kRadix];  // per-warp digit counters -> placement offsets
+    // dynamic shared memory: keys | payload (pairs) | per-warp digit counters -> placement offsets
+    extern __shared__ __align__(128) uint32_t s_dyn[];
+    uint32_t* const s_keys = s_dyn;
+    uint32_t* const s_vals = s_dyn + TILE;  // payload: fetched by TMA, permuted in place
+    uint32_t(*const s_whist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(s_dyn + (PAIRS ? 2 : 1) * TILE);
     __shared__ uint32_t s_goff[kRadix];       // global position of sorted-tile index 0 of each digit run
     __shared__ uint32_t s_wtot[kRadix / 32];
     __shared__ __align__(8) uint64_t s_bar;
@@ -183,8 +199,9 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
         const uint32_t t = atomicAdd(p.counter, 1u) - p.counter_base;
         s_tile = t;
         if (((uint64_t)t + 1u) * TILE <= p.n) {
-            mbar_arrive_expect_tx(&s_bar, TILE * 4u);
+            mbar_arrive_expect_tx(&s_bar, TILE * 4u * (PAIRS ? 2u : 1u));
             bulk_load(s_keys, p.keys_in + (uint64_t)t * TILE, TILE * 4u, &s_bar);
+            if constexpr (PAIRS) bulk_load(s_vals, p.vals_in + (uint64_t)t * TILE, TILE * 4u, &s_bar);
         }
     }
 #pragma unroll
@@ -204,7 +221,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
         // last tile: pad with 0xFFFFFFFF -- digit 255 in every pass, ranked after every real key
         // of the tile, so the padding occupies exactly the sorted-tile indices >= valid
 #pragma unroll 1
-        for (uint32_t i = tid; i < TILE; i += NT) s_keys[i] = i < valid ? p.keys_in[tile_base + i] : 0xFFFFFFFFu;
+        for (uint32_t i = tid; i < TILE; i += NT) {
+            s_keys[i] = i < valid ? p.keys_in[tile_base + i] : 0xFFFFFFFFu;
+            if constexpr (PAIRS) s_vals[i] = i < valid ? p.vals_in[tile_base + i] : 0u;
+        }
         __syncthreads();
     }
 
@@ -212,15 +232,6 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     uint32_t key[KPT];
 #pragma unroll
     for (int j = 0; j < KPT; ++j) key[j] = s_keys[warp * WARP_KEYS + j * 32 + lane];
-    uint32_t val[PAIRS ? KPT : 1];
-    if constexpr (PAIRS) {
-#pragma unroll
-        for (int j = 0; j < KPT; ++j) {
-            const uint32_t i = warp * WARP_KEYS + j * 32 + lane;
-            val[j] = (full || i < valid) ? p.vals_in[tile_base + i] : 0u;
-        }
-    }
-
     // ---- warp-level multi-split: rank of each key among the warp's keys of the same digit,
     // in (j, lane) order == original order (stability)
     uint32_t pos[KPT];
@@ -267,22 +278,61 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
         pos[j] += s_whist[warp][sort_digit(key[j], p.shift)];
         s_keys[pos[j]] = key[j];
     }
+    if constexpr (PAIRS) {
+        // the payload takes the same permutation, in place in its own buffer (no registers are
+        // held across the look-back; the permutation does not depend on it)
+        uint32_t val[KPT];
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) val[j] = s_vals[warp * WARP_KEYS + j * 32 + lane];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) s_vals[pos[j]] = val[j];
+    }
 
     // ---- chained scan across tiles, one look-back per digit (thread d walks digit d)
     if (tid < (uint32_t)kRadix) {
+        // Thread d walks digit d's descriptors backwards, LB descriptors per L2 round trip: the
+        // loads of one round are independent, the walk consumes them nearest first and stops
+        // at the first INCLUSIVE (or re-polls from the first one that is not ready).  With
+        // hundreds of tiles in flight and a tile finishing every ~20 ns, the nearest INCLUSIVE
+        // is usually several tiles back.  Measured: LB = 4 is the best (50.0 Gkeys/s; LB = 1
+        // 48.7, LB = 8 45.7, LB = 16 37.8 -- deeper rounds mostly fetch descriptors that are
+        // never consumed).
         uint32_t prefix = 0;
         if (tile != 0) {
             uint32_t polls = 0;
             int64_t t = (int64_t)tile - 1;
-            while (t >= 0) {
-                const uint64_t dsc = ld_relaxed_gpu(p.desc + (uint64_t)t * kRadix + tid);
-                if (!desc_valid(dsc, p.epoch)) {
-                    if (watchdog_tick(polls, p.status)) break;
-                    continue;
+            bool done = false;
+            const uint32_t tag = p.epoch << 2;  // hi word of a valid descriptor = tag | status
+            const uint64_t* dp = p.desc + (uint64_t)t * kRadix + tid;
+            while (!done) {
+                uint32_t lo[LB], hi[LB];
+#pragma unroll
+                for (int i = 0; i < LB; ++i) {
+                    lo[i] = 0u;
+                    hi[i] = tag | ST_INCLUSIVE;  // virtual entry below tile 0
+                    if (t - i >= 0) {
+                        const uint64_t d = ld_relaxed_gpu(dp - (int64_t)i * kRadix);
+                        lo[i] = (uint32_t)d;
+                        hi[i] = (uint32_t)(d >> 32);
+                    }
                 }
-                prefix += desc_value(dsc);
-                if (desc_status(dsc) == ST_INCLUSIVE) break;
-                --t;
+                uint32_t consumed = 0;
+                bool open = true;  // still consuming this round
+#pragma unroll
+                for (int i = 0; i < LB; ++i) {
+                    const uint32_t st = hi[i] ^ tag;  // 1 / 2 when valid, >= 4 otherwise
+                    const bool ok = open && st < 4u && st != 0u;
+                    if (ok) {
+                        prefix += lo[i];
+                        ++consumed;
+                        done = st == ST_INCLUSIVE;
+                    }
+                    open = ok && !done;
+                }
+                t -= consumed;
+                dp -= (int64_t)consumed * kRadix;
+                if (consumed == 0u && watchdog_tick(polls, p.status)) break;
             }
         }
         desc_publish_plain(p.desc + (uint64_t)tile * kRadix + tid, pack_desc(prefix + count, p.epoch, ST_INCLUSIVE));
@@ -291,24 +341,14 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     __syncthreads();
 
     // ---- scatter: consecutive sorted-tile indices of one digit are consecutive in memory
-    uint32_t gidx[PAIRS ? KPT : 1];
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
         const uint32_t i = k * NT + tid;
         const uint32_t kk = s_keys[i];
         const uint32_t g = s_goff[sort_digit(kk, p.shift)] + i;
-        if (full || i < valid) p.keys_out[g] = kk;
-        if constexpr (PAIRS) gidx[k] = g;
-    }
-    if constexpr (PAIRS) {
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < KPT; ++j) s_keys[pos[j]] = val[j];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < KPT; ++k) {
-            const uint32_t i = k * NT + tid;
-            if (full || i < valid) p.vals_out[gidx[k]] = s_keys[i];
+        if (full || i < valid) {
+            p.keys_out[g] = kk;
+            if constexpr (PAIRS) p.vals_out[g] = s_vals[i];
         }
     }
 }
