@@ -193,7 +193,40 @@ def run_reference(args) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    line["reference_cuda"] = reference_cuda_kernels(args.log2_keys_per_gpu)
     print(json.dumps(line), flush=True)
+
+
+def reference_cuda_kernels(log2n: int):
+    """Informational, not the arm's `value`: the reference's OWN CUDA kernels (oracle/_ref/
+    libref_shim.so = the reference headers rebuilt for sm_100a, launched with its <8,4> shapes
+    and its timing protocol incl. the per-launch descriptor memsets) on this box's GPU, so the
+    driver's JSON also carries the GPU-to-GPU comparison.  None when the shim or a GPU is absent."""
+    try:
+        import ctypes as C
+
+        from gpuprefixsums_b200 import _capi as capi
+        from tests import oracle_lib
+
+        shim = oracle_lib.load_ref_shim()
+        if shim is None:
+            return None
+        n = 1 << log2n
+        src, buf = C.c_void_p(), C.c_void_p()
+        capi.check(capi.lib.gps_malloc(C.byref(src), n * 4))
+        capi.check(capi.lib.gps_malloc(C.byref(buf), n * 4))
+        capi.check(capi.lib.gps_init_random(src, n, capi.U32, 1, 3, 0, None))  # keys in [0,4): total < 2^30,
+        capi.check(capi.lib.gps_device_sync())                                  # the reference CSDL's limit
+        res = {"unit": UNIT, "keys": n, "input": "random keys in [0,4) (reference CSDL truncates totals >= 2^30)",
+               "iters": 50}
+        for name, algo in [("csdl", 0), ("rts", 1), ("cub_device_scan", 3)]:
+            ms = shim.time_u32(algo, False, buf.value, src.value, n, 50)
+            res[name] = n / (ms * 1e-3) / 1e9 if ms > 0 else None
+        capi.lib.gps_free(src)
+        capi.lib.gps_free(buf)
+        return res
+    except Exception as e:  # no GPU / no shim: the CPU line stands on its own
+        return {"unavailable": str(e)[:200]}
 
 
 def workload_name(args, n_gpus: int) -> str:

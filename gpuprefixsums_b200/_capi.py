@@ -61,6 +61,8 @@ SIGNATURES = {
     "gps_init_ones": (_i32, [_vp, _u64, _i32, _vp]),
     "gps_init_random": (_i32, [_vp, _u64, _i32, _u64, _u32, _u64, _vp]),
     "gps_validate_ones": (_i32, [_vp, _u64, _i32, _u32, C.POINTER(_u64)]),
+    "gps_validate_ones_wide": (_i32, [_vp, _u64, _i32, _i32, C.POINTER(_u64)]),
+    "gps_sort_fingerprint": (_i32, [_vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "gps_compare_u32": (_i32, [_vp, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "gps_compare_f32": (_i32, [_vp, _vp, _vp, _u64, C.c_float, C.c_float, C.POINTER(_u64), C.POINTER(C.c_float)]),
     "gps_set_device": (_i32, [_i32]),

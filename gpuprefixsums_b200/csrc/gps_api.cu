@@ -821,6 +821,43 @@ int gps_validate_ones(const void* d, uint64_t n, int kind, uint32_t first_value,
     return GPS_OK;
 }
 
+int gps_validate_ones_wide(const void* d, uint64_t n, int kind, int dtype, uint64_t* h_errs)
+{
+    if (!h_errs || (n && !d)) return fail(GPS_ERR_INVALID, "null pointer");
+    if (dtype != GPS_U64 && dtype != GPS_U32X4) return fail(GPS_ERR_INVALID, "GPS_U64 or GPS_U32X4");
+    unsigned long long* d_err = nullptr;
+    GPS_CUDA(cudaMalloc(&d_err, sizeof(unsigned long long)));
+    GPS_CUDA(cudaMemset(d_err, 0, sizeof(unsigned long long)));
+    const uint32_t inc = kind == GPS_INCLUSIVE ? 1u : 0u;
+    if (n && dtype == GPS_U64)
+        validate_ones_u64_kernel<<<util_grid(n), 256>>>(static_cast<const uint64_t*>(d), n, inc, d_err);
+    else if (n)
+        validate_struct_ones_kernel<<<util_grid(4 * n), 256>>>(static_cast<const uint32_t*>(d), 4 * n, inc, d_err);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d_err, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_err);
+    GPS_CUDA(e);
+    *h_errs = h;
+    return GPS_OK;
+}
+
+int gps_sort_fingerprint(const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2])
+{
+    if (!h_inversions || !h_sums || (n && !d_keys)) return fail(GPS_ERR_INVALID, "null pointer");
+    unsigned long long* d_err = nullptr;
+    GPS_CUDA(cudaMalloc(&d_err, 3 * sizeof(unsigned long long)));
+    GPS_CUDA(cudaMemset(d_err, 0, 3 * sizeof(unsigned long long)));
+    if (n) sort_fingerprint_kernel<<<util_grid(n), 256>>>(static_cast<const uint32_t*>(d_keys), n, d_err);
+    unsigned long long h[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpy(h, d_err, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d_err);
+    GPS_CUDA(e);
+    *h_inversions = h[0];
+    h_sums[0] = h[1];
+    h_sums[1] = h[2];
+    return GPS_OK;
+}
+
 int gps_compare_u32(const void* d_a, const void* d_b, uint64_t n, uint64_t* h_errs, uint64_t* h_first_bad)
 {
     if (!h_errs || (n && (!d_a || !d_b))) return fail(GPS_ERR_INVALID, "null pointer");

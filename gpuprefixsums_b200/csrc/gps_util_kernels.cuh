@@ -91,4 +91,43 @@ __global__ void compare_f32_kernel(const float* a, const float* b, const float* 
 
 __global__ void write_value_kernel(uint32_t* dst, uint32_t bits) { *dst = bits; }
 
+// struct scan of all-ones input (GPUPrefixSumsWebGPUapis/SharedShaders/validate.wgsl:50-60):
+// flat u32 view, out[i] == (i >> 2) + 1 (inclusive) or (i >> 2) (exclusive); n4 = 4 * elements
+__global__ void validate_struct_ones_kernel(const uint32_t* d, uint64_t n4, uint32_t inclusive,
+                                            unsigned long long* errs)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+        local += d[i] != (uint32_t)(i >> 2) + inclusive;
+    if (local) atomicAdd(errs, local);
+}
+
+// uint64 scan of all-ones input: d[i] == i + 1 / i
+__global__ void validate_ones_u64_kernel(const uint64_t* d, uint64_t n, uint64_t inclusive, unsigned long long* errs)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        local += d[i] != i + inclusive;
+    if (local) atomicAdd(errs, local);
+}
+
+// sortedness + multiset fingerprint of a sort: errs[0] = inversions between neighbours,
+// errs[1] = sum of keys, errs[2] = sum of key * (key >> 7 | 1) (both mod 2^64)
+__global__ void sort_fingerprint_kernel(const uint32_t* d, uint64_t n, unsigned long long* errs)
+{
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long inv = 0, s1 = 0, s2 = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = d[i];
+        if (i && d[i - 1] > k) ++inv;
+        s1 += k;
+        s2 += (unsigned long long)k * ((k >> 7) | 1u);
+    }
+    if (inv) atomicAdd(errs, inv);
+    atomicAdd(errs + 1, s1);
+    atomicAdd(errs + 2, s2);
+}
+
 }  // namespace gps

@@ -201,6 +201,13 @@ int gps_init_random(void* d, uint64_t n, int dtype, uint64_t seed, uint32_t mask
 int gps_validate_ones(const void* d, uint64_t n, int kind, uint32_t first_value,
                       uint64_t* h_errs);
 /* word-for-word compare of two device arrays (uint32), synchronous */
+/* All-ones closed forms of the wide scans: GPS_U64 out[i] == i + 1 / i; GPS_U32X4 the flat
+ * u32 view out[i] == (i >> 2) + 1 / (i >> 2) (GPUPrefixSumsWebGPUapis/SharedShaders/
+ * validate.wgsl:50-60).  n counts elements.  Synchronous. */
+int gps_validate_ones_wide(const void* d, uint64_t n, int kind, int dtype, uint64_t* h_errs);
+/* Sort checker: *h_inversions = number of i with keys[i-1] > keys[i]; h_sums = two order-
+ * independent fingerprints of the key multiset (compare input against output).  Synchronous. */
+int gps_sort_fingerprint(const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2]);
 int gps_compare_u32(const void* d_a, const void* d_b, uint64_t n, uint64_t* h_errs,
                     uint64_t* h_first_bad);
 /* float32: counts |a-b| > rtol*|d_bound[i]| + atol (d_bound nullable -> |b|) */

@@ -419,6 +419,19 @@ static int run_all(Env& env, const char* filter)
             CarrySpec cs;
             return launch_csdl_reg<T, 128, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
         });
+        static bool cfg_a = false, cfg_b = false, cfg_c = false;
+        sv.emplace_back("sweep/csdl_smem<128,8>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_smem<T, 128, 8, INCL, 1>(env.s, in, out, env.n, cs, cfg_a, 0);
+        });
+        sv.emplace_back("sweep/csdl_smem<128,4>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_smem<T, 128, 4, INCL, 1>(env.s, in, out, env.n, cs, cfg_b, 0);
+        });
+        sv.emplace_back("sweep/csdl_smem<256,4>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_smem<T, 256, 4, INCL, 1>(env.s, in, out, env.n, cs, cfg_c, 0);
+        });
         sv.emplace_back("sweep/csdl_tma<512,S2>", [&](const void* in, void* out) {
             CarrySpec cs;
             return launch_csdl_tma<T, 512, 2, INCL, 1>(env.s, in, out, env.n, cs, occ_t, 0, 0);
