@@ -124,7 +124,11 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
         switch (algo) {
             case GPS_ALGO_CSDL_REG:
                 // small inputs: 16 KB tiles spread over more SMs (size sweep)
-                if (n <= GPS_REG_SMALL_MAX_N)
+                // (the descriptor array is sized for 4096-key tiles: the 2048-key variant only
+                // when its tiles fit, i.e. for every ctx of max_n >= 2^18)
+                if (n <= GPS_REG_TINY_MAX_N && div_up(n, GPS_REG_TINY_NT * GPS_REG_TINY_V * 4) <= c->s.desc_tiles)
+                    e = launch_csdl_reg<T, GPS_REG_TINY_NT, GPS_REG_TINY_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                else if (n <= GPS_REG_SMALL_MAX_N)
                     e = launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 else
                     e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);

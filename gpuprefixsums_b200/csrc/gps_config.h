@@ -24,6 +24,17 @@
 #ifndef GPS_REG_SMALL_V
 #define GPS_REG_SMALL_V 4
 #endif
+// launch-latency regime (profiles/r01_size_sweep.txt): up to 2^17 keys 8 KB tiles <128,4> finish
+// in 4.6 us where <256,4> takes 5.1 (14.2 vs 12.8 Gkeys/s at 2^16); from 2^18 <256,4> is ahead
+#ifndef GPS_REG_TINY_MAX_N
+#define GPS_REG_TINY_MAX_N (1u << 17)
+#endif
+#ifndef GPS_REG_TINY_NT
+#define GPS_REG_TINY_NT 128
+#endif
+#ifndef GPS_REG_TINY_V
+#define GPS_REG_TINY_V 4
+#endif
 // look-back windows (32 descriptors each) fetched per L2 round trip: 1 beat 2 and 4
 // (803 / 757 / 530 Gkeys/s on <128,12> resp. <256,4>): the nearest tiles decide
 #ifndef GPS_LOOKBACK_WIN
