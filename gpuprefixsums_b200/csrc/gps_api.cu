@@ -70,6 +70,8 @@ struct gps_ctx {
     // cached launch geometry
     int tma_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [dtype][kind]
     bool smem_configured[2][2] = {{false, false}, {false, false}};
+    bool smem_fb_configured[2][2] = {{false, false}, {false, false}};
+    int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile
     bool wide_configured[5][2][2] = {};             // [dtype][kind][rts]
     // host pipeline (lazy)
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
@@ -106,6 +108,22 @@ struct DeviceGuard {
 
 template <typename T>
 constexpr int dt_index() { return std::is_same<T, float>::value ? 1 : 0; }
+
+// Decoupled Fallback: by default the shared-memory-resident tile for large inputs without
+// emulated stalls (815 vs 747 Gkeys/s at 2^28; plain CSDL 829), the register tile below
+// GPS_REG_SMALL_MAX_N keys and whenever stalls are emulated (its slower polls spend the spin
+// budget later: 519 vs 455 Gkeys/s at mask 7 / spin 4); "fallback_variant" pins one
+template <typename T, bool INCL>
+cudaError_t launch_fallback(gps_ctx* c, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                            const FallbackParams& f, cudaStream_t st)
+{
+    const bool smem = c->fallback_variant == 2 ||
+                      (c->fallback_variant == 0 && n > GPS_REG_SMALL_MAX_N && f.stall_mask == kNoStall);
+    if (smem)
+        return launch_csdl_smem_fallback<T, GPS_SMEM_NT, GPS_SMEM_V, INCL>(
+            c->s, in, out, n, cs, f, c->smem_fb_configured[dt_index<T>()][INCL ? 0 : 1], st);
+    return launch_csdl_fallback<T, GPS_REG_NT, GPS_REG_V, INCL>(c->s, in, out, n, cs, f, st);
+}
 
 template <typename T, bool INCL>
 int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n,
@@ -144,7 +162,7 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
                 break;
             case GPS_ALGO_CSDL_FALLBACK: {
                 FallbackParams f{kNoStall, GPS_FALLBACK_DEFAULT_SPIN, nullptr};
-                e = launch_csdl_fallback<T, GPS_REG_NT, GPS_REG_V, INCL>(c->s, in, out, n, cs, f, st);
+                e = launch_fallback<T, INCL>(c, in, out, n, cs, f, st);
                 break;
             }
             case GPS_ALGO_RTS:
@@ -448,6 +466,9 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     if (!strcmp(key, "csdl_variant")) {
         if (value < 0 || value > 3) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..3");
         c->csdl_variant = (int)value;
+    } else if (!strcmp(key, "fallback_variant")) {
+        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "fallback_variant must be 0..2");
+        c->fallback_variant = (int)value;
     } else if (!strcmp(key, "debug_epoch")) {
         // test hook: jump the launch epoch (e.g. just below the 2^30 wrap)
         if (value < 0 || value >= (1ll << 30)) return fail(GPS_ERR_INVALID, "epoch out of range");
@@ -683,12 +704,12 @@ int gps_scan_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void* d_in
     cudaError_t e;
     if (dtype == GPS_U32)
         e = kind == GPS_INCLUSIVE
-                ? launch_csdl_fallback<uint32_t, GPS_REG_NT, GPS_REG_V, true>(c->s, d_in, d_out, n, cs, f, st)
-                : launch_csdl_fallback<uint32_t, GPS_REG_NT, GPS_REG_V, false>(c->s, d_in, d_out, n, cs, f, st);
+                ? launch_fallback<uint32_t, true>(c, d_in, d_out, n, cs, f, st)
+                : launch_fallback<uint32_t, false>(c, d_in, d_out, n, cs, f, st);
     else
         e = kind == GPS_INCLUSIVE
-                ? launch_csdl_fallback<float, GPS_REG_NT, GPS_REG_V, true>(c->s, d_in, d_out, n, cs, f, st)
-                : launch_csdl_fallback<float, GPS_REG_NT, GPS_REG_V, false>(c->s, d_in, d_out, n, cs, f, st);
+                ? launch_fallback<float, true>(c, d_in, d_out, n, cs, f, st)
+                : launch_fallback<float, false>(c, d_in, d_out, n, cs, f, st);
     if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "fallback scan launch failed: %s", cudaGetErrorString(e));
     return GPS_OK;
 }

@@ -168,6 +168,24 @@ cudaError_t launch_csdl_fallback(Scratch& s, const void* in, void* out, uint64_t
     return cudaGetLastError();
 }
 
+// the same on the shared-memory-resident tile (gps_csdl_smem.cuh)
+template <typename T, int NT, int V, bool INCL>
+cudaError_t launch_csdl_smem_fallback(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                                      const FallbackParams& f, bool& configured, cudaStream_t st)
+{
+    auto kern = csdl_smem_fallback_kernel<T, NT, V, INCL>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
+    kern<<<p.num_tiles, NT, 0, st>>>(p, f);
+    s.counter_base += p.num_tiles;
+    return cudaGetLastError();
+}
+
 // ---- RTS -----------------------------------------------------------------------------
 // s.partials must hold one key-sized value per tile (s.partials_capacity entries)
 template <typename T, int NT, int V>

@@ -87,6 +87,9 @@ void gps_destroy(gps_ctx* ctx);
 int gps_check(gps_ctx* ctx, void* stream);
 /* Tuning knobs (key/value); unknown keys return GPS_ERR_INVALID.  Keys:
  *   "csdl_variant"  0 = auto, 1 = register path, 2 = TMA ring, 3 = smem-resident tile
+ *   "fallback_variant" Decoupled Fallback kernels: 0 = auto (smem-resident tile above 2^21
+ *                   keys when no stalls are emulated, register tile otherwise), 1 = register
+ *                   tile, 2 = smem-resident tile
  *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)
  *   "desc_protocol" 0 = atom.exch + ld.relaxed (default), 1 = st.release + ld.acquire,
  *                   2 = st.relaxed + ld.relaxed

@@ -453,3 +453,32 @@ def test_caller_owned_scratch(gps, oracle):
         gps.PrefixSum(n, scratch=scratch[: need - 1])
     with pytest.raises(gps.GpsError):
         gps.PrefixSum(n, scratch=torch.empty(need + 256, dtype=torch.uint8, device="cuda")[16:])
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_fallback_variants_forced(gps, oracle, variant):
+    """Decoupled Fallback on the register tile (1) and on the shared-memory-resident tile (2),
+    each forced at every size: both kinds, uint32 bit-exact / float32 in tolerance, in place,
+    with and without emulated stalls (EmulatedDeadlocking.cuh:63-151)."""
+    ps = gps.PrefixSum(1 << 23)
+    ps.set_option("fallback_variant", variant)
+    for n in [1, 4095, 4096, 4097, 6143, 6145, 9 * 4096, 100_003, (1 << 22) + 77]:
+        x = oracle.random_u32(n, seed=600 + n)
+        for exclusive in (False, True):
+            want, _ = oracle.scan_u32(x, exclusive=exclusive, carry=11)
+            got = ps.scan(to_dev_u32(x), algo="csdl_fallback", exclusive=exclusive, carry=11)
+            ps.check()
+            assert np.array_equal(to_np_u32(got), want), (n, exclusive)
+            want0, _ = oracle.scan_u32(x, exclusive=exclusive)
+            for mask, spin in [(7, 4), (1, 1), (63, 2)]:
+                stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+                buf = to_dev_u32(x)
+                ps.scan_emulated_deadlock(buf, buf, exclusive=exclusive, stall_mask=mask, max_spin=spin, stats=stats)
+                ps.check()
+                assert np.array_equal(to_np_u32(buf), want0), (n, exclusive, mask)
+    xf = oracle.random_f32((1 << 22) + 5, seed=3)
+    got = ps.scan_emulated_deadlock(torch.from_numpy(xf).cuda(), stall_mask=7, max_spin=4).cpu().numpy()
+    ps.check()
+    errs, max_rel = oracle.check_f32(xf, got, rtol=F32_RTOL, atol=F32_ATOL)
+    assert errs == 0, max_rel
+    ps.close()
