@@ -232,7 +232,9 @@ def reference_cuda_kernels(log2n: int):
 def workload_name(args, n_gpus: int) -> str:
     if n_gpus == 1:
         return f"uint32 inclusive scan, 2^{args.log2_keys_per_gpu} random keys, 1 B200, {args.algo} (BASELINE configs[1])"
-    return (f"sharded uint32 inclusive scan, {n_gpus} x 2^{args.log2_keys_per_gpu} random keys, contiguous slices, "
+    per_gpu = (f"2^{args.log2_total} keys in total ({n_gpus} slices of 2^{args.log2_total} / {n_gpus})" if args.log2_total
+               else f"{n_gpus} x 2^{args.log2_keys_per_gpu} random keys")
+    return (f"sharded uint32 inclusive scan, {per_gpu}, contiguous slices, "
             f"carry over {'NVLink P2P stores' if args.carry == 'p2p' else 'NCCL all_gather'} (BASELINE configs[4] shape)")
 
 
