@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--algo", default="csdl", help="csdl | csdl_smem | csdl_reg | csdl_tma | rts | csdl_fallback")
+    ap.add_argument("--algo", default="csdl", help="csdl | csdl_blocked | csdl_smem | csdl_reg | csdl_tma | rts | csdl_fallback")
     ap.add_argument("--log2-keys-per-gpu", type=int, default=LOG2_KEYS_PER_GPU)
     ap.add_argument("--log2-total", type=int, default=0, help="N>1: total keys = 2^this (strong-scaling point)")
     ap.add_argument("--carry", default="p2p", choices=["p2p", "nccl"], help="N>1 carry exchange")

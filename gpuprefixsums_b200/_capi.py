@@ -21,6 +21,7 @@ GPS_OK = 0
 GPS_ERR_INVALID, GPS_ERR_ALIGNMENT, GPS_ERR_CUDA = -1, -2, -3
 GPS_ERR_WATCHDOG, GPS_ERR_MISMATCH, GPS_ERR_UNSUPPORTED = -4, -5, -6
 ALGO_CSDL, ALGO_CSDL_REG, ALGO_CSDL_TMA, ALGO_CSDL_FALLBACK, ALGO_RTS, ALGO_CSDL_SMEM = 0, 1, 2, 3, 4, 5
+ALGO_CSDL_BLOCKED = 6
 INCLUSIVE, EXCLUSIVE = 0, 1
 U32, F32, U64, F64, U32X4 = 0, 1, 2, 3, 4
 NO_STALL = 0xFFFFFFFF
@@ -33,6 +34,7 @@ ALGO_NAMES = {
     "csdl_fallback": ALGO_CSDL_FALLBACK,
     "rts": ALGO_RTS,
     "csdl_smem": ALGO_CSDL_SMEM,
+    "csdl_blocked": ALGO_CSDL_BLOCKED,
 }
 
 _vp, _u64, _u32, _i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int

@@ -54,6 +54,7 @@ constexpr uint32_t kHostChunkKeysDefault = 1u << 24;  // 64 MiB per pipeline chu
 constexpr int kHostBufs = 3;
 static_assert(GPS_REG_NT * GPS_REG_V * 4 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
 static_assert(GPS_TMA_NT * 16 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
+static_assert(GPS_BLOCKED_NT * GPS_BLOCKED_V * 4 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
 static_assert(GPS_SMEM_NT * GPS_SMEM_V * 4 >= (int)kMinTileKeys, "descriptor array sized for 4096-key tiles");
 static_assert(GPS_RTS_NT * GPS_RTS_V * 4 >= (int)kMinTileKeys, "partials array sized for 4096-key tiles");
 }  // namespace
@@ -70,6 +71,7 @@ struct gps_ctx {
     // cached launch geometry
     int tma_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [dtype][kind]
     bool smem_configured[2][2] = {{false, false}, {false, false}};
+    bool blocked_configured[2][2] = {{false, false}, {false, false}};
     bool smem_fb_configured[2][2] = {{false, false}, {false, false}};
     int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile
     bool wide_configured[5][2][2] = {};             // [dtype][kind][rts]
@@ -135,7 +137,9 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
     } else {
         if (algo == GPS_ALGO_CSDL) {
             const int v = c->csdl_variant ? c->csdl_variant : GPS_CSDL_DEFAULT_VARIANT;
-            algo = v == 2 ? GPS_ALGO_CSDL_TMA : v == 3 ? GPS_ALGO_CSDL_SMEM : GPS_ALGO_CSDL_REG;
+            algo = v == 2 ? GPS_ALGO_CSDL_TMA : v == 3 ? GPS_ALGO_CSDL_SMEM : v == 4 ? GPS_ALGO_CSDL_BLOCKED : GPS_ALGO_CSDL_REG;
+            // mid-size inputs: the lane-strided smem kernel's 16 KB tiles fill the machine sooner
+            if (algo == GPS_ALGO_CSDL_BLOCKED && n < GPS_BLOCKED_MIN_N) algo = GPS_ALGO_CSDL_SMEM;
             // small inputs are launch/latency bound: the register path with 16 KB tiles
             if (algo == GPS_ALGO_CSDL_SMEM && n <= GPS_REG_SMALL_MAX_N) algo = GPS_ALGO_CSDL_REG;
         }
@@ -150,6 +154,10 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
                     e = launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 else
                     e = launch_csdl_reg<T, GPS_REG_NT, GPS_REG_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                break;
+            case GPS_ALGO_CSDL_BLOCKED:
+                e = launch_csdl_blocked<T, GPS_BLOCKED_NT, GPS_BLOCKED_V, INCL, GPS_LOOKBACK_WIN>(
+                    c->s, in, out, n, cs, c->blocked_configured[dt_index<T>()][INCL ? 0 : 1], st);
                 break;
             case GPS_ALGO_CSDL_SMEM:
                 e = launch_csdl_smem<T, GPS_SMEM_NT, GPS_SMEM_V, INCL, GPS_LOOKBACK_WIN>(
@@ -464,7 +472,7 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
 {
     if (!c || !key) return fail(GPS_ERR_INVALID, "null argument");
     if (!strcmp(key, "csdl_variant")) {
-        if (value < 0 || value > 3) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..3");
+        if (value < 0 || value > 4) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..4");
         c->csdl_variant = (int)value;
     } else if (!strcmp(key, "fallback_variant")) {
         if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "fallback_variant must be 0..2");

@@ -115,11 +115,26 @@
 #define GPS_SORT_PAIRS_REGS 128
 #endif
 
-// GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = smem-resident tile.
-// Chosen by measurement at 2^28 keys: smem-resident tile 837,
-// register path 785-805, TMA ring 659 Gkeys/s
+// CSDL on the blocked shared-memory tile (gps_csdl_blocked.cuh): NT threads x V (odd) uint4
+// per thread, TMA bulk load + per-warp TMA bulk store
+#ifndef GPS_BLOCKED_NT
+#define GPS_BLOCKED_NT 256
+#endif
+#ifndef GPS_BLOCKED_V
+#define GPS_BLOCKED_V 9
+#endif
+// below this many keys GPS_ALGO_CSDL keeps the lane-strided smem kernel (16 KB tiles)
+#ifndef GPS_BLOCKED_MIN_N
+#define GPS_BLOCKED_MIN_N (1u << 26)
+#endif
+
+// GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = lane-strided smem-resident
+// tile, 4 = blocked smem-resident tile.  Chosen by measurement at 2^28 keys (DESIGN.md
+// sections 5 and 7): in a 30-launch burst blocked 840, smem 835, register 820, TMA ring 659
+// Gkeys/s; over 4000 back-to-back launches (board at its power limit) blocked 822, smem 783,
+// register 754 -- the blocked tile executes 0.43 x the instructions
 #ifndef GPS_CSDL_DEFAULT_VARIANT
-#define GPS_CSDL_DEFAULT_VARIANT 3
+#define GPS_CSDL_DEFAULT_VARIANT 4
 #endif
 
 // spin budget of GPS_ALGO_CSDL_FALLBACK (no emulated stalls): polls of a not-ready

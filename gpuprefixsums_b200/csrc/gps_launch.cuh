@@ -7,6 +7,7 @@
 #pragma once
 #include <algorithm>
 
+#include "gps_csdl_blocked.cuh"
 #include "gps_csdl_reg.cuh"
 #include "gps_csdl_smem.cuh"
 #include "gps_csdl_tma.cuh"
@@ -115,6 +116,24 @@ cudaError_t launch_csdl_smem(Scratch& s, const void* in, void* out, uint64_t n, 
                              bool& configured, cudaStream_t st)
 {
     auto kern = csdl_smem_kernel<T, NT, V, INCL, WIN, G, REGS>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
+    kern<<<p.num_tiles, NT, 0, st>>>(p);
+    if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
+    return cudaGetLastError();
+}
+
+// ---- CSDL blocked shared-memory tile (TMA bulk load + per-warp TMA bulk store) --------
+template <typename T, int NT, int V, bool INCL, int WIN = 1, int REGS = 40>
+cudaError_t launch_csdl_blocked(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                                bool& configured, cudaStream_t st)
+{
+    auto kern = csdl_blocked_kernel<T, NT, V, INCL, WIN, REGS>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              (int)cudaSharedmemCarveoutMaxShared);

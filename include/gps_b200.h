@@ -56,7 +56,8 @@ enum gps_algo {
     GPS_ALGO_CSDL_TMA = 2,      /*   TMA bulk copies into a shared-memory ring        */
     GPS_ALGO_CSDL_FALLBACK = 3, /* CSDL + Decoupled Fallback (no emulated stalls)     */
     GPS_ALGO_RTS = 4,           /* three-kernel Reduce-then-Scan                      */
-    GPS_ALGO_CSDL_SMEM = 5      /*   one TMA bulk load per CTA, tile resident in smem  */
+    GPS_ALGO_CSDL_SMEM = 5,     /*   one TMA bulk load per CTA, tile resident in smem  */
+    GPS_ALGO_CSDL_BLOCKED = 6   /*   same, blocked tile: one warp scan per tile, TMA store */
 };
 enum gps_kind { GPS_INCLUSIVE = 0, GPS_EXCLUSIVE = 1 };
 enum gps_dtype {
@@ -87,6 +88,7 @@ void gps_destroy(gps_ctx* ctx);
 int gps_check(gps_ctx* ctx, void* stream);
 /* Tuning knobs (key/value); unknown keys return GPS_ERR_INVALID.  Keys:
  *   "csdl_variant"  0 = auto, 1 = register path, 2 = TMA ring, 3 = smem-resident tile
+ *                   (lane-strided), 4 = smem-resident tile (blocked, TMA store)
  *   "fallback_variant" Decoupled Fallback kernels: 0 = auto (smem-resident tile above 2^21
  *                   keys when no stalls are emulated, register tile otherwise), 1 = register
  *                   tile, 2 = smem-resident tile

@@ -9,11 +9,12 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-ALGOS = ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"]
+ALGOS = ["csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"]
 # tile sizes in play: 4096 (smem path, small-input register path), 6144 (register path / RTS /
-# fallback), 8192 (TMA path)
+# fallback), 8192 (TMA path), 9216 (blocked path)
 EDGE_SIZES = [0, 1, 2, 3, 4, 5, 7, 8, 31, 32, 33, 127, 128, 129, 1023, 1024, 1025, 4095, 4096, 4097, 8191,
-              6143, 6144, 6145, 8192, 8193, 12287, 12288, 12289, 16384, 16385, 65535, 65536, 65537, 100_003, 1 << 20]
+              6143, 6144, 6145, 8192, 8193, 9215, 9216, 9217, 12287, 12288, 12289, 16384, 16385, 18431, 18432, 18433,
+              65535, 65536, 65537, 100_003, 1 << 20]
 # float32 tolerance: |gpu_i - ref_i| <= RTOL * sum_{j<=i}|x_j| + ATOL vs the float64
 # serial scan.  Observed max is ~1e-6 (reported by test_float_2p28_tolerance).
 F32_RTOL = 2e-5
@@ -104,7 +105,7 @@ def test_config0_2p20_random_vs_host_serial(ps, oracle):
 # ---------------------------------------------------------------------------------------
 # the reference's own protocol: all-ones, closed form, sizes 4096..8192 (+ around 8192-key tiles)
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "rts"])
+@pytest.mark.parametrize("algo", ["csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "rts"])
 @pytest.mark.parametrize("exclusive", [False, True])
 def test_reference_all_ones_sweep(gps, algo, exclusive):
     from gpuprefixsums_b200.dispatchers import (ChainedScanDecoupledLookbackDispatcher,
@@ -168,7 +169,7 @@ def test_rts_float_is_deterministic(ps, oracle):
 # ---------------------------------------------------------------------------------------
 # full size (2^28): closed form, properties, CUB and the reference's CUDA kernels
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
+@pytest.mark.parametrize("algo", ["csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
 def test_2p28_all_ones_closed_form(gps, ps, algo):
     n = 1 << 28
     buf = torch.empty(n, dtype=torch.int32, device="cuda")
@@ -189,7 +190,7 @@ def test_2p28_random_vs_cub_and_properties(gps, ps, oracle):
     gps.cub_scan(x, ref)  # CUB validated against the oracle on a prefix, then used as device oracle
     assert oracle.check_u32(head, to_np_u32(ref[: 1 << 16]))[0] == 0
     out = torch.empty_like(x)
-    for algo in ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"]:
+    for algo in ["csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"]:
         total = torch.zeros(1, dtype=torch.int32, device="cuda")
         ps.scan(x, out, algo=algo, total_out=total)
         ps.check()
@@ -297,7 +298,7 @@ def test_reduce_matches_oracle(ps, oracle):
         assert int(to_np_u32(got)[0]) == want
 
 
-@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
+@pytest.mark.parametrize("algo", ["csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"])
 def test_carry_slots_fold_into_lookback(gps, ps, oracle, algo):
     """Two 'ranks' on one GPU: totals published as tagged slots, tile 0 sums the upstream ones."""
     from gpuprefixsums_b200.sharded import pack_slot
@@ -376,7 +377,7 @@ def test_more_than_2p32_keys(gps, algo):
 # ---------------------------------------------------------------------------------------
 # scratch bookkeeping that replaces the reference's per-launch memsets
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ["csdl_smem", "csdl_reg", "csdl_tma", "csdl_fallback"])
+@pytest.mark.parametrize("algo", ["csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "csdl_fallback"])
 def test_epoch_and_ticket_counter_wraparound(gps, oracle, algo):
     """Descriptors are epoch-tagged and the ticket counter is never reset: both must
     survive their wrap (2^30 launches / 2^32 tickets)."""
@@ -440,7 +441,7 @@ def test_caller_owned_scratch(gps, oracle):
     ps = gps.PrefixSum(n, scratch=scratch)
     x = oracle.random_u32(n, seed=12)
     want, _ = oracle.scan_u32(x)
-    for algo in ["csdl", "csdl_reg", "csdl_tma", "csdl_smem", "csdl_fallback", "rts"]:
+    for algo in ["csdl", "csdl_blocked", "csdl_reg", "csdl_tma", "csdl_smem", "csdl_fallback", "rts"]:
         for _ in range(2):
             out = ps.scan(to_dev_u32(x), algo=algo)
             ps.check()

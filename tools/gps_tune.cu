@@ -432,6 +432,23 @@ static int run_all(Env& env, const char* filter)
             CarrySpec cs;
             return launch_csdl_smem<T, 256, 4, INCL, 1>(env.s, in, out, env.n, cs, cfg_c, 0);
         });
+        static bool cfg_d = false, cfg_e = false, cfg_f = false, cfg_g = false;
+        sv.emplace_back("sweep/csdl_blocked<256,9>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 256, 9, INCL, 1>(env.s, in, out, env.n, cs, cfg_d, 0);
+        });
+        sv.emplace_back("sweep/csdl_blocked<128,9>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 128, 9, INCL, 1>(env.s, in, out, env.n, cs, cfg_e, 0);
+        });
+        sv.emplace_back("sweep/csdl_blocked<128,5>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 128, 5, INCL, 1>(env.s, in, out, env.n, cs, cfg_f, 0);
+        });
+        sv.emplace_back("sweep/csdl_blocked<256,5>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 256, 5, INCL, 1>(env.s, in, out, env.n, cs, cfg_g, 0);
+        });
         sv.emplace_back("sweep/csdl_tma<512,S2>", [&](const void* in, void* out) {
             CarrySpec cs;
             return launch_csdl_tma<T, 512, 2, INCL, 1>(env.s, in, out, env.n, cs, occ_t, 0, 0);
