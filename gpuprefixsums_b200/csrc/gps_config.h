@@ -123,9 +123,11 @@
 #ifndef GPS_BLOCKED_V
 #define GPS_BLOCKED_V 9
 #endif
-// below this many keys GPS_ALGO_CSDL keeps the lane-strided smem kernel (16 KB tiles)
+// below this many keys GPS_ALGO_CSDL keeps the lane-strided smem kernel (16 KB tiles fill the
+// machine sooner: 2^26 keys 766 vs 738, 2^27 817 vs 806 Gkeys/s in a burst; 2^28 840 vs 844,
+// 2^29 853 vs 863, 2^30 850 vs 871 -- profiles/r01_size_sweep.txt)
 #ifndef GPS_BLOCKED_MIN_N
-#define GPS_BLOCKED_MIN_N (1u << 26)
+#define GPS_BLOCKED_MIN_N (1u << 27)
 #endif
 
 // GPS_ALGO_CSDL resolves to: 1 = register path, 2 = TMA ring, 3 = lane-strided smem-resident
