@@ -73,7 +73,10 @@ struct gps_ctx {
     bool smem_configured[2][2] = {{false, false}, {false, false}};
     bool blocked_configured[2][2] = {{false, false}, {false, false}};
     bool smem_fb_configured[2][2] = {{false, false}, {false, false}};
-    int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile
+    bool blocked_fb_configured[2][2] = {{false, false}, {false, false}};
+    bool rts_blocked_configured[2][2] = {{false, false}, {false, false}};
+    int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile, 3 blocked tile
+    int rts_variant = 0;            // 0 auto, 1 register-tile propagate, 2 blocked-tile propagate
     bool wide_configured[5][2][2] = {};             // [dtype][kind][rts]
     // host pipeline (lazy)
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
@@ -111,16 +114,21 @@ struct DeviceGuard {
 template <typename T>
 constexpr int dt_index() { return std::is_same<T, float>::value ? 1 : 0; }
 
-// Decoupled Fallback: by default the shared-memory-resident tile for large inputs without
-// emulated stalls (815 vs 747 Gkeys/s at 2^28; plain CSDL 829), the register tile below
-// GPS_REG_SMALL_MAX_N keys and whenever stalls are emulated (its slower polls spend the spin
-// budget later: 519 vs 455 Gkeys/s at mask 7 / spin 4); "fallback_variant" pins one
+// Decoupled Fallback, by default: from 2^27 keys the blocked shared-memory tile (836 Gkeys/s
+// without stalls at 2^28 -- plain CSDL 844 -- and 632 with mask 7 / spin 4); below that the
+// lane-strided smem tile when no stalls are emulated (822 vs 752 for the register tile) and
+// the register tile otherwise (its slower polls spend the spin budget later: 527 vs 458);
+// "fallback_variant" pins one
 template <typename T, bool INCL>
 cudaError_t launch_fallback(gps_ctx* c, const void* in, void* out, uint64_t n, const CarrySpec& cs,
                             const FallbackParams& f, cudaStream_t st)
 {
     const bool smem = c->fallback_variant == 2 ||
                       (c->fallback_variant == 0 && n > GPS_REG_SMALL_MAX_N && f.stall_mask == kNoStall);
+    const bool blocked = c->fallback_variant == 3 || (c->fallback_variant == 0 && n >= GPS_BLOCKED_MIN_N);
+    if (blocked)
+        return launch_csdl_blocked_fallback<T, GPS_BLOCKED_NT, GPS_BLOCKED_V, INCL>(
+            c->s, in, out, n, cs, f, c->blocked_fb_configured[dt_index<T>()][INCL ? 0 : 1], st);
     if (smem)
         return launch_csdl_smem_fallback<T, GPS_SMEM_NT, GPS_SMEM_V, INCL>(
             c->s, in, out, n, cs, f, c->smem_fb_configured[dt_index<T>()][INCL ? 0 : 1], st);
@@ -174,7 +182,11 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
                 break;
             }
             case GPS_ALGO_RTS:
-                e = launch_rts<T, GPS_RTS_NT, GPS_RTS_V, INCL>(c->s, in, out, n, cs, st);
+                if (c->rts_variant == 2 || (c->rts_variant == 0 && n >= GPS_BLOCKED_MIN_N))
+                    e = launch_rts_blocked<T, GPS_BLOCKED_NT, GPS_BLOCKED_V, INCL>(
+                        c->s, in, out, n, cs, c->rts_blocked_configured[dt_index<T>()][INCL ? 0 : 1], st);
+                else
+                    e = launch_rts<T, GPS_RTS_NT, GPS_RTS_V, INCL>(c->s, in, out, n, cs, st);
                 break;
             default:
                 return fail(GPS_ERR_INVALID, "unknown algo %d", algo);
@@ -475,8 +487,11 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
         if (value < 0 || value > 4) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..4");
         c->csdl_variant = (int)value;
     } else if (!strcmp(key, "fallback_variant")) {
-        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "fallback_variant must be 0..2");
+        if (value < 0 || value > 3) return fail(GPS_ERR_INVALID, "fallback_variant must be 0..3");
         c->fallback_variant = (int)value;
+    } else if (!strcmp(key, "rts_variant")) {
+        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "rts_variant must be 0..2");
+        c->rts_variant = (int)value;
     } else if (!strcmp(key, "debug_epoch")) {
         // test hook: jump the launch epoch (e.g. just below the 2^30 wrap)
         if (value < 0 || value >= (1ll << 30)) return fail(GPS_ERR_INVALID, "epoch out of range");

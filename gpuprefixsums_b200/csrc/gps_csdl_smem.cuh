@@ -16,6 +16,7 @@
 // chunk), so LDS.128 is bank-conflict free and STG.128 fully coalesced without any
 // transposition.  ~40 registers per thread; occupancy is set by shared memory instead.
 #pragma once
+#include "gps_csdl_blocked.cuh"
 #include "gps_csdl_reg.cuh"  // FallbackParams, LB_* states
 #include "gps_tile_reg.cuh"
 
@@ -413,6 +414,217 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     __syncthreads();
 
     smem_tile_finish<T, V, INCLUSIVE, G>(s_data, row0, vbase, full, p.n, p.out, lane, s_prefix + warp_prefix);
+}
+
+
+// ---- and on the blocked tile of gps_csdl_blocked.cuh (same protocol, same fallback re-read)
+template <typename T, int NT, int V, bool INCLUSIVE, int REGS = 40>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
+    csdl_blocked_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
+{
+    using Tile = BlockedTile<T, NT, V>;
+    constexpr int NW = Tile::NW;
+    constexpr uint32_t TILE_VEC = Tile::TILE_VEC;
+    __shared__ __align__(128) uint4 s_data[TILE_VEC];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ T s_warp[NW];
+    __shared__ T s_red[NW];
+    __shared__ T s_prefix;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_state;    // LB_DONE / LB_FALLBACK
+    __shared__ uint32_t s_fb_tile;  // tile to recompute
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        const uint32_t t = claim_tile(p);
+        s_tile = t;
+        Tile::issue_load(s_data, &s_bar, p.in, t, p.n);
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
+    const uint32_t v0 = tid * V;                     // this thread's first uint4 within the tile
+    const uint32_t row0 = warp * (32u * V) + lane;   // lane-strided start for the fallback re-read
+    if (!Tile::arrive(s_data, &s_bar, p.in, tile, p.n, full, v0)) {
+        atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
+
+    // ---- pass 1: thread total -> one warp scan per tile -> aggregate first
+    const T acc = Tile::thread_sum(s_data, v0);
+    const T tinc = warp_inclusive_scan(acc, lane);
+    const T thread_excl = warp_exclusive_of(tinc, acc, lane);
+    if (lane == 31) s_warp[warp] = tinc;
+    __syncthreads();
+    T warp_prefix = T(0), aggregate = T(0);
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+        const T w = s_warp[j];
+        if ((uint32_t)j < warp) warp_prefix += w;
+        aggregate += w;
+    }
+
+    // stall emulation: the tile refuses to publish until a successor's fallback published for
+    // it; the last tile never stalls (nobody could rescue it)
+    const bool stalled = f.stall_mask != kNoStall && (tile & f.stall_mask) == 0u && p.num_tiles > 1u &&
+                         tile != p.num_tiles - 1u;
+    T carry = T(0);
+    if (warp == 0) {
+        if (tile == 0) carry = acquire_carry<T>(p, lane);
+        if (lane == 0) {
+            if (stalled) {
+                uint32_t polls = 0;
+                while (!desc_valid(ld_relaxed_gpu(p.desc + tile), p.epoch)) {
+                    if (watchdog_tick(polls, p.status)) break;
+                }
+            }
+            const T v = tile ? aggregate : carry + aggregate;
+            atomicExch(reinterpret_cast<unsigned long long*>(p.desc + tile),
+                       (unsigned long long)pack_desc(to_bits(v), p.epoch, tile ? ST_AGGREGATE : ST_INCLUSIVE));
+            // in-place safety of the fallback: the descriptor is performed at L2 before any
+            // thread of this CTA overwrites the tile's input (fence + the barrier below), so a
+            // successor re-reading that input afterwards fails its CAS and discards the sum.
+            // Out of place the input is never overwritten and the descriptor carries its
+            // payload in the same word: no ordering against other memory is needed.
+            if (p.in == p.out) __threadfence();
+        }
+    }
+    __syncthreads();  // holds the whole block while stalled ("purely for emulation")
+
+    uint32_t n_spins = 0, n_fallbacks = 0, n_inserts = 0, n_windows = 0;
+    T prefix = carry;  // tile 0: done
+    if (tile != 0) {
+        int64_t top = (int64_t)tile - 1;
+        prefix = T(0);
+        while (true) {
+            if (warp == 0) {
+                uint32_t state = LB_DONE, spins = 0, polls = 0, fb = 0;
+                while (true) {
+                    const int64_t idx = top - (int64_t)lane;
+                    uint64_t d = pack_desc(0u, p.epoch, ST_INCLUSIVE);
+                    bool ready = true;
+                    if (idx >= 0) {
+                        d = ld_relaxed_gpu(p.desc + idx);  // payload and flag share the word
+                        ready = desc_valid(d, p.epoch);
+                    }
+                    ++n_windows;
+                    const uint32_t not_ready = __ballot_sync(kFullMask, !ready);
+                    const uint32_t first_nr = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
+                    const uint32_t below = first_nr >= 32u ? kFullMask : ((1u << first_nr) - 1u);
+                    const uint32_t incl = __ballot_sync(kFullMask, ready && desc_status(d) == ST_INCLUSIVE) & below;
+                    const T v = from_bits<T>(desc_value(d));
+                    if (incl) {
+                        const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
+                        prefix += warp_reduce(lane <= nearest ? v : T(0));
+                        break;
+                    }
+                    if (first_nr == 32u) {  // whole window ready, none inclusive
+                        prefix += warp_reduce(v);
+                        top -= 32;
+                        spins = 0;
+                        continue;
+                    }
+                    ++n_spins;
+                    const bool bail = watchdog_tick(polls, p.status);
+                    if (__any_sync(kFullMask, bail)) break;
+                    if (++spins < f.max_spin) {
+                        if (p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
+                        continue;
+                    }
+                    // budget exhausted: consume the ready tiles nearer than the blocker, fall
+                    // back on the blocker itself
+                    prefix += warp_reduce(lane < first_nr ? v : T(0));
+                    fb = (uint32_t)(top - (int64_t)first_nr);
+                    top = (int64_t)fb - 1;
+                    state = LB_FALLBACK;
+                    break;
+                }
+                if (lane == 0) {
+                    s_state = state;
+                    s_fb_tile = fb;
+                }
+            }
+            __syncthreads();
+            if (s_state == LB_DONE) break;
+
+            // ---- Decoupled Fallback: every thread helps to re-reduce tile fb from the INPUT
+            // (a fallback target is never the last tile => always full)
+            const uint32_t fb = s_fb_tile;
+            ++n_fallbacks;
+            {
+                const uint4* in4 = reinterpret_cast<const uint4*>(p.in) + (uint64_t)fb * TILE_VEC + row0;
+                T fs = T(0);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const uint4 r = ldg_stream(in4 + 32u * k);
+                    fs += (from_bits<T>(r.x) + from_bits<T>(r.y)) + (from_bits<T>(r.z) + from_bits<T>(r.w));
+                }
+                const T ws = warp_reduce(fs);
+                if (lane == 0) s_red[warp] = ws;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                T red = warp_reduce(lane < (uint32_t)NW ? s_red[lane] : T(0));
+                if (fb == 0) red += acquire_carry<T>(p, lane);  // tile 0 is INCLUSIVE incl. carry
+                uint32_t done = 0;
+                if (lane == 0) {
+                    const uint32_t st = fb ? ST_AGGREGATE : ST_INCLUSIVE;
+                    const uint64_t mine = pack_desc(to_bits(red), p.epoch, st);
+                    uint64_t seen = ld_relaxed_gpu(p.desc + fb);
+                    T use = red;
+                    uint32_t use_st = st;
+                    bool inserted = false;
+                    while (!desc_valid(seen, p.epoch)) {  // CAS from the stale word we observe to ours
+                        const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(p.desc + fb),
+                                                       (unsigned long long)seen, (unsigned long long)mine);
+                        if (old == seen) {
+                            inserted = true;
+                            break;
+                        }
+                        seen = old;
+                    }
+                    if (!inserted) {  // the owner (or another rescuer) got there first
+                        use = from_bits<T>(desc_value(seen));
+                        use_st = desc_status(seen);
+                    } else {
+                        ++n_inserts;
+                    }
+                    prefix += use;
+                    done = (use_st == ST_INCLUSIVE || fb == 0) ? 1u : 0u;
+                }
+                prefix = __shfl_sync(kFullMask, prefix, 0);
+                done = __shfl_sync(kFullMask, done, 0);
+                if (lane == 0) s_state = done ? LB_DONE : LB_FALLBACK;
+            }
+            __syncthreads();
+            if (s_state == LB_DONE) break;
+            __syncthreads();  // s_state is rewritten by the next look-back round
+        }
+    }
+
+    if (warp == 0 && lane == 0) {
+        const T inclusive = prefix + aggregate;
+        if (tile != 0)
+            atomicExch(reinterpret_cast<unsigned long long*>(p.desc + tile),
+                       (unsigned long long)pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
+        s_prefix = prefix;
+        if (tile == p.num_tiles - 1) write_total<T>(p, inclusive);
+        if (f.stats) {
+            if (n_spins) atomicAdd(f.stats + 0, n_spins);
+            if (n_inserts) atomicAdd(f.stats + 2, n_inserts);
+            if (n_windows) atomicAdd(f.stats + 3, n_windows);
+        }
+    }
+    if (tid == 0 && f.stats && n_fallbacks) atomicAdd(f.stats + 1, n_fallbacks);
+    __syncthreads();
+
+    Tile::template finish<INCLUSIVE>(s_data, v0, (s_prefix + warp_prefix) + thread_excl, p.out, tile, p.n, full, warp,
+                                     lane);
 }
 
 }  // namespace gps

@@ -205,6 +205,23 @@ cudaError_t launch_csdl_smem_fallback(Scratch& s, const void* in, void* out, uin
     return cudaGetLastError();
 }
 
+template <typename T, int NT, int V, bool INCL>
+cudaError_t launch_csdl_blocked_fallback(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                                         const FallbackParams& f, bool& configured, cudaStream_t st)
+{
+    auto kern = csdl_blocked_fallback_kernel<T, NT, V, INCL>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
+    kern<<<p.num_tiles, NT, 0, st>>>(p, f);
+    s.counter_base += p.num_tiles;
+    return cudaGetLastError();
+}
+
 // ---- RTS -----------------------------------------------------------------------------
 // s.partials must hold one key-sized value per tile (s.partials_capacity entries)
 template <typename T, int NT, int V>
@@ -237,6 +254,36 @@ cudaError_t launch_rts(Scratch& s, const void* in, void* out, uint64_t n, const 
     rts_reduce_kernel<T, NT, V><<<p.num_tiles, NT, 0, st>>>(p);
     rts_spine_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
     rts_propagate_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// RTS with the propagate kernel on the blocked shared-memory tile
+template <typename T, int NT, int V, bool INCL>
+cudaError_t launch_rts_blocked(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs, bool& configured,
+                               cudaStream_t st)
+{
+    auto kern = rts_propagate_blocked_kernel<T, NT, V, INCL>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    RtsParams p{};
+    cudaError_t e = rts_params<T, NT, V>(s, n, p);
+    if (e != cudaSuccess) return e;
+    p.in = in;
+    p.out = out;
+    p.carry_bits = cs.carry_bits;
+    p.slots = cs.slots;
+    p.n_slots = cs.n_slots;
+    p.n_carry = cs.n_carry;
+    p.slot_tag = cs.tag;
+    p.total_out = cs.total_out;
+    p.publish = cs.publish;
+    rts_reduce_kernel<T, NT, V><<<p.num_tiles, NT, 0, st>>>(p);
+    rts_spine_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
+    kern<<<p.num_tiles, NT, 0, st>>>(p);
     return cudaGetLastError();
 }
 

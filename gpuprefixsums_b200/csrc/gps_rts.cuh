@@ -14,6 +14,7 @@
 //                            the CSDL tile pipeline minus descriptors and look-back
 // Deterministic for float32 (fixed association order).  DRAM traffic 12 B/key.
 #pragma once
+#include "gps_csdl_blocked.cuh"
 #include "gps_tile_reg.cuh"
 
 namespace gps {
@@ -190,6 +191,46 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 24 + 4 * V))
         t.template store_full<INCLUSIVE>(p.out, vbase, prefix);
     else
         t.template store_partial<INCLUSIVE>(p.out, vbase, p.n, prefix);
+}
+
+// ---- kernel 3 on the blocked shared-memory tile (gps_csdl_blocked.cuh): TMA bulk load, one warp
+// scan per tile, per-warp TMA bulk store.  Pairs with rts_reduce_kernel<T, NT, V> (same tile
+// extent; the reduce may visit the keys in any order).
+template <typename T, int NT, int V, bool INCLUSIVE, int REGS = 40>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
+    rts_propagate_blocked_kernel(const __grid_constant__ RtsParams p)
+{
+    using Tile = BlockedTile<T, NT, V>;
+    constexpr int NW = Tile::NW;
+    __shared__ __align__(128) uint4 s_data[Tile::TILE_VEC];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ T s_warp[NW];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        Tile::issue_load(s_data, &s_bar, p.in, tile, p.n);
+    }
+    __syncthreads();
+    const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
+    const uint32_t v0 = tid * V;
+    const T tile_prefix = reinterpret_cast<const T*>(p.partials)[tile];
+    if (!Tile::arrive(s_data, &s_bar, p.in, tile, p.n, full, v0)) {
+        atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
+    const T acc = Tile::thread_sum(s_data, v0);
+    const T inc = warp_inclusive_scan(acc, lane);
+    const T thread_excl = warp_exclusive_of(inc, acc, lane);
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    T warp_prefix = T(0);
+#pragma unroll
+    for (int j = 0; j < NW; ++j)
+        if ((uint32_t)j < warp) warp_prefix += s_warp[j];
+    Tile::template finish<INCLUSIVE>(s_data, v0, (tile_prefix + warp_prefix) + thread_excl, p.out, tile, p.n, full, warp,
+                                     lane);
 }
 
 }  // namespace gps

@@ -89,9 +89,12 @@ int gps_check(gps_ctx* ctx, void* stream);
 /* Tuning knobs (key/value); unknown keys return GPS_ERR_INVALID.  Keys:
  *   "csdl_variant"  0 = auto, 1 = register path, 2 = TMA ring, 3 = smem-resident tile
  *                   (lane-strided), 4 = smem-resident tile (blocked, TMA store)
- *   "fallback_variant" Decoupled Fallback kernels: 0 = auto (smem-resident tile above 2^21
- *                   keys when no stalls are emulated, register tile otherwise), 1 = register
- *                   tile, 2 = smem-resident tile
+ *   "fallback_variant" Decoupled Fallback kernels: 0 = auto (blocked smem-resident tile from
+ *                   2^27 keys; below, the lane-strided smem tile above 2^21 keys when no stalls
+ *                   are emulated, else the register tile), 1 = register tile, 2 = smem-resident
+ *                   tile, 3 = blocked smem-resident tile
+ *   "rts_variant"   Reduce-then-Scan propagate kernel: 0 = auto (blocked tile from 2^27 keys),
+ *                   1 = register tile, 2 = blocked smem-resident tile
  *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)
  *   "desc_protocol" 0 = atom.exch + ld.relaxed (default), 1 = st.release + ld.acquire,
  *                   2 = st.relaxed + ld.relaxed

@@ -456,14 +456,15 @@ def test_caller_owned_scratch(gps, oracle):
         gps.PrefixSum(n, scratch=torch.empty(need + 256, dtype=torch.uint8, device="cuda")[16:])
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_fallback_variants_forced(gps, oracle, variant):
-    """Decoupled Fallback on the register tile (1) and on the shared-memory-resident tile (2),
+    """Decoupled Fallback on the register tile (1), the shared-memory-resident tile (2) and the
+    blocked shared-memory tile (3),
     each forced at every size: both kinds, uint32 bit-exact / float32 in tolerance, in place,
     with and without emulated stalls (EmulatedDeadlocking.cuh:63-151)."""
     ps = gps.PrefixSum(1 << 23)
     ps.set_option("fallback_variant", variant)
-    for n in [1, 4095, 4096, 4097, 6143, 6145, 9 * 4096, 100_003, (1 << 22) + 77]:
+    for n in [1, 4095, 4096, 4097, 6143, 6145, 9215, 9216, 9217, 9 * 4096, 9 * 9216, 100_003, (1 << 22) + 77]:
         x = oracle.random_u32(n, seed=600 + n)
         for exclusive in (False, True):
             want, _ = oracle.scan_u32(x, exclusive=exclusive, carry=11)
@@ -481,5 +482,32 @@ def test_fallback_variants_forced(gps, oracle, variant):
     got = ps.scan_emulated_deadlock(torch.from_numpy(xf).cuda(), stall_mask=7, max_spin=4).cpu().numpy()
     ps.check()
     errs, max_rel = oracle.check_f32(xf, got, rtol=F32_RTOL, atol=F32_ATOL)
+    assert errs == 0, max_rel
+    ps.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_rts_variants_forced(gps, oracle, variant):
+    """Reduce-then-Scan with the propagate kernel on the register tile (1) and on the blocked
+    shared-memory tile (2), each forced at every size; float32 deterministic in both."""
+    ps = gps.PrefixSum(1 << 23)
+    ps.set_option("rts_variant", variant)
+    for n in [0, 1, 6143, 6144, 6145, 9215, 9216, 9217, 18433, 100_003, (1 << 22) + 77]:
+        x = oracle.random_u32(n, seed=700 + n)
+        for exclusive in (False, True):
+            want, total = oracle.scan_u32(x, exclusive=exclusive, carry=3)
+            tot = torch.zeros(1, dtype=torch.int32, device="cuda")
+            got = ps.scan(to_dev_u32(x), algo="rts", exclusive=exclusive, carry=3, total_out=tot)
+            ps.check()
+            assert np.array_equal(to_np_u32(got), want), (n, exclusive)
+            assert int(tot.cpu().numpy().view(np.uint32)[0]) == total
+            if n:
+                buf = to_dev_u32(x)
+                ps.scan(buf, buf, algo="rts", exclusive=exclusive, carry=3)  # in place
+                assert np.array_equal(to_np_u32(buf), want), ("in place", n, exclusive)
+    xf = torch.from_numpy(oracle.random_f32((1 << 22) + 5, seed=8)).cuda()
+    a = ps.scan(xf, algo="rts").clone()
+    assert torch.equal(ps.scan(xf, algo="rts"), a)
+    errs, max_rel = oracle.check_f32(xf.cpu().numpy(), a.cpu().numpy(), rtol=F32_RTOL, atol=F32_ATOL)
     assert errs == 0, max_rel
     ps.close()

@@ -29,7 +29,7 @@ def timed(fn, iters=30):
     return round(n / (e0.elapsed_time(e1) / iters) / 1e6, 1)
 
 
-for variant, name in [(1, "reg"), (2, "smem")]:
+for variant, name in [(1, "reg"), (2, "smem"), (3, "blocked")]:
     ps.set_option("fallback_variant", variant)
     res[f"{name}_no_stall"] = timed(lambda: ps.scan(x, out, algo="csdl_fallback"))
     for mask, spin in [(7, 4), (63, 4), (7, 1)]:
@@ -38,4 +38,10 @@ for variant, name in [(1, "reg"), (2, "smem")]:
         res[f"{name}_mask{mask}_spin{spin}_stats_per_launch"] = [int(v) // 13 for v in stats.cpu()]
 ps.check()
 res["csdl_default"] = timed(lambda: ps.scan(x, out, algo="csdl"))
+for variant, name in [(1, "reg"), (2, "blocked")]:
+    ps.set_option("rts_variant", variant)
+    res[f"rts_{name}"] = timed(lambda: ps.scan(x, out, algo="rts"))
+    res[f"rts_{name}_500"] = timed(lambda: ps.scan(x, out, algo="rts"), 500)
+ps.set_option("fallback_variant", 0)
+res["fallback_auto_500"] = timed(lambda: ps.scan(x, out, algo="csdl_fallback"), 500)
 print(json.dumps(res))
