@@ -91,7 +91,7 @@ struct gps_ctx {
     uint64_t sort_desc_tiles = 0;
     uint32_t* sort_hist = nullptr;
     uint32_t sort_epoch = 0;
-    bool sort_configured[2] = {false, false};
+    bool sort_configured[4] = {false, false, false, false};  // [pairs + 2 * key-map variant]
     bool sort_hist_configured = false;
 };
 
@@ -315,12 +315,12 @@ constexpr uint32_t kSortTile = (uint32_t)GPS_SORT_NT * GPS_SORT_KPT;
 constexpr uint32_t kSortPairsTile = (uint32_t)GPS_SORT_PAIRS_NT * GPS_SORT_PAIRS_KPT;
 constexpr uint32_t kSortMinTile = kSortTile < kSortPairsTile ? kSortTile : kSortPairsTile;
 
-template <bool PAIRS>
+template <bool PAIRS, bool XFORM>
 cudaError_t launch_sort_pass(const SortParams& p, bool& configured, cudaStream_t st)
 {
     constexpr int NT = PAIRS ? GPS_SORT_PAIRS_NT : GPS_SORT_NT, KPT = PAIRS ? GPS_SORT_PAIRS_KPT : GPS_SORT_KPT;
     constexpr size_t smem = ((size_t)(PAIRS ? 2 : 1) * NT * KPT + (size_t)(NT / 32) * kRadix) * sizeof(uint32_t);
-    auto kern = sort_pass_kernel<NT, KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS, GPS_SORT_LB>;
+    auto kern = sort_pass_kernel<NT, KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS, GPS_SORT_LB, XFORM>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
@@ -592,7 +592,18 @@ uint64_t gps_sort_scratch_bytes(uint64_t n)
 int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp, const void* d_vals_in,
                  void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
 {
+    return gps_sort_keys32(c, GPS_KEY_U32, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n,
+                           end_bit, stream);
+}
+
+int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                    const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
+{
     if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    if (key_type != GPS_KEY_U32 && key_type != GPS_KEY_I32 && key_type != GPS_KEY_F32)
+        return fail(GPS_ERR_INVALID, "bad key type %d", key_type);
+    if (key_type != GPS_KEY_U32 && end_bit != 32)
+        return fail(GPS_ERR_INVALID, "int32 / float32 keys sort on all 32 bits (end_bit 32)");
     if (end_bit < 1 || end_bit > 32) return fail(GPS_ERR_INVALID, "end_bit %d outside 1..32", end_bit);
     if (n >= (1ull << 32)) return fail(GPS_ERR_INVALID, "gps_sort_u32 takes fewer than 2^32 keys");
     const bool pairs = d_vals_in || d_vals_out || d_vals_tmp;
@@ -630,7 +641,8 @@ int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_ke
             c->sort_hist_configured = true;
         }
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->s.sm_count, div_up(n, 4 * kHistThreads));
-        sort_hist_kernel<<<grid, kHistThreads, kHistSmemBytes, st>>>((const uint32_t*)d_keys_in, (uint32_t)n, hist, passes);
+        sort_hist_kernel<<<grid, kHistThreads, kHistSmemBytes, st>>>((const uint32_t*)d_keys_in, (uint32_t)n, hist, passes,
+                                                                     (uint32_t)key_type);
         sort_digit_base_kernel<<<passes, kRadix, 0, st>>>(hist, digit_base);
     }
     // ping-pong so that the last pass lands in `out`
@@ -656,8 +668,13 @@ int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_ke
         p.epoch = c->sort_epoch;
         p.num_tiles = tiles;
         p.status = c->s.status;
-        GPS_CUDA(pairs ? launch_sort_pass<true>(p, c->sort_configured[1], st)
-                       : launch_sort_pass<false>(p, c->sort_configured[0], st));
+        p.xform_in = pass == 0 ? (uint32_t)key_type : 0u;
+        p.xform_out = pass == passes - 1 ? (uint32_t)key_type : 0u;
+        const bool xf = p.xform_in || p.xform_out;
+        GPS_CUDA(pairs ? (xf ? launch_sort_pass<true, true>(p, c->sort_configured[3], st)
+                             : launch_sort_pass<true, false>(p, c->sort_configured[1], st))
+                       : (xf ? launch_sort_pass<false, true>(p, c->sort_configured[2], st)
+                             : launch_sort_pass<false, false>(p, c->sort_configured[0], st)));
         c->s.counter_base += tiles;  // one claim per CTA
         src_k = p.keys_out;
         src_v = p.vals_out;

@@ -38,7 +38,26 @@ struct SortParams {
     uint32_t epoch;
     uint32_t num_tiles;
     uint32_t* status;          // watchdog word
+    uint32_t xform_in;         // key type whose order-preserving map is applied on load (first pass), else 0
+    uint32_t xform_out;        // key type whose inverse map is applied on store (last pass), else 0
 };
+
+// Order-preserving maps onto uint32 (keys travel transformed between the passes):
+//   1 = int32: flip the sign bit; 2 = float32: flip every bit of negative values, the sign bit
+//   of the others (so -0.0 < +0.0 and NaNs sort by their bit pattern at both ends, as CUB does)
+enum : uint32_t { KEY_U32 = 0, KEY_I32 = 1, KEY_F32 = 2 };
+__host__ __device__ __forceinline__ uint32_t sort_key_map(uint32_t k, uint32_t type)
+{
+    if (type == KEY_I32) return k ^ 0x80000000u;
+    if (type == KEY_F32) return k ^ ((k >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    return k;
+}
+__host__ __device__ __forceinline__ uint32_t sort_key_unmap(uint32_t k, uint32_t type)
+{
+    if (type == KEY_I32) return k ^ 0x80000000u;
+    if (type == KEY_F32) return k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+    return k;
+}
 
 // digit = byte (shift / 8) of the key: one PRMT (selector 0x4440 + byte index: byte 0 <- that
 // byte of the key, bytes 1..3 <- byte 0 of the zero operand)
@@ -71,13 +90,14 @@ constexpr int kHistThreads = 1024;
 constexpr size_t kHistSmemBytes = (size_t)4 * kRadix * 32 * sizeof(uint32_t);
 
 __global__ void __launch_bounds__(kHistThreads, 1)
-    sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist, int passes)
+    sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist, int passes, uint32_t key_type)
 {
     extern __shared__ __align__(16) uint32_t s_hist[];  // [4 * 256][32]
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     for (uint32_t i = tid; i < 4u * kRadix * 32u; i += kHistThreads) s_hist[i] = 0u;
     __syncthreads();
     auto add = [&](uint32_t k) {
+        k = sort_key_map(k, key_type);
 #pragma unroll
         for (int p = 0; p < 4; ++p)
             if (p < passes) atomicAdd(&s_hist[((p * kRadix + ((k >> (8 * p)) & 0xFFu)) << 5) + lane], 1u);
@@ -174,7 +194,9 @@ __device__ __forceinline__ uint32_t sort_peers(uint32_t d)
 #endif
 }
 
-template <int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8>
+// XFORM: apply the key maps of p.xform_in / p.xform_out (first / last pass of int32 and float32
+// sorts); the uint32 instantiation carries none of that code
+template <int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8, bool XFORM = false>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kernel(const __grid_constant__ SortParams p)
 {
     static_assert(NT >= kRadix && NT % 32 == 0, "one thread per digit for the look-back");
@@ -218,11 +240,12 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
             return;
         }
     } else {
-        // last tile: pad with 0xFFFFFFFF -- digit 255 in every pass, ranked after every real key
-        // of the tile, so the padding occupies exactly the sorted-tile indices >= valid
+        // last tile: pad with (the preimage of) 0xFFFFFFFF -- digit 255 in every pass, ranked after
+        // every real key of the tile, so the padding occupies exactly the sorted-tile indices >= valid
+        const uint32_t pad = XFORM ? sort_key_unmap(0xFFFFFFFFu, p.xform_in) : 0xFFFFFFFFu;
 #pragma unroll 1
         for (uint32_t i = tid; i < TILE; i += NT) {
-            s_keys[i] = i < valid ? p.keys_in[tile_base + i] : 0xFFFFFFFFu;
+            s_keys[i] = i < valid ? p.keys_in[tile_base + i] : pad;
             if constexpr (PAIRS) s_vals[i] = i < valid ? p.vals_in[tile_base + i] : 0u;
         }
         __syncthreads();
@@ -231,7 +254,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     // ---- keys to registers, warp-striped: key j of lane l is element warp*32*KPT + j*32 + l
     uint32_t key[KPT];
 #pragma unroll
-    for (int j = 0; j < KPT; ++j) key[j] = s_keys[warp * WARP_KEYS + j * 32 + lane];
+    for (int j = 0; j < KPT; ++j) {
+        key[j] = s_keys[warp * WARP_KEYS + j * 32 + lane];
+        if constexpr (XFORM) key[j] = sort_key_map(key[j], p.xform_in);
+    }
     // ---- warp-level multi-split: rank of each key among the warp's keys of the same digit,
     // in (j, lane) order == original order (stability)
     uint32_t pos[KPT];
@@ -347,7 +373,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
         const uint32_t kk = s_keys[i];
         const uint32_t g = s_goff[sort_digit(kk, p.shift)] + i;
         if (full || i < valid) {
-            p.keys_out[g] = kk;
+            p.keys_out[g] = XFORM ? sort_key_unmap(kk, p.xform_out) : kk;
             if constexpr (PAIRS) p.vals_out[g] = s_vals[i];
         }
     }

@@ -148,15 +148,18 @@ class PrefixSum:
                                 _stream_ptr(stream, self.device)))
         return out
 
-    def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None, *, end_bit: int = 32,
+    def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None, *, end_bit: int = 32, key_type: str = "u32",
              keys_out: Optional[torch.Tensor] = None, values_out: Optional[torch.Tensor] = None,
              stream: Optional[torch.cuda.Stream] = None):
-        """Stable ascending LSD radix sort of uint32 keys (int32 bit pattern) on their low
-        `end_bit` bits, optionally moving a 32-bit payload; returns keys or (keys, values)."""
-        if keys.dtype not in (torch.int32, torch.uint32) or not keys.is_cuda or not keys.is_contiguous():
-            raise TypeError("sort: keys must be a contiguous int32/uint32 CUDA tensor")
+        """Stable ascending LSD radix sort of 32-bit keys, optionally moving a 32-bit payload;
+        returns keys or (keys, values).  key_type: "u32" (default: the bit pattern as unsigned,
+        on the low `end_bit` bits), "i32" (signed order) or "f32" (numeric order, float32 keys)."""
+        kt = {"u32": 0, "i32": 1, "f32": 2}[key_type]
+        want = (torch.float32,) if kt == 2 else (torch.int32, torch.uint32)
+        if keys.dtype not in want or not keys.is_cuda or not keys.is_contiguous():
+            raise TypeError(f"sort: keys must be a contiguous CUDA tensor of dtype {want}")
         ko = torch.empty_like(keys) if keys_out is None else keys_out
-        kt = torch.empty_like(keys)
+        ktmp = torch.empty_like(keys)
         if values is not None:
             if values.numel() != keys.numel() or values.element_size() != 4 or not values.is_contiguous():
                 raise TypeError("sort: values must be 32-bit, contiguous, one per key")
@@ -165,7 +168,7 @@ class PrefixSum:
             vptrs = (values.data_ptr(), vo.data_ptr(), vt.data_ptr())
         else:
             vo, vptrs = None, (None, None, None)
-        check(lib.gps_sort_u32(self._ctx, keys.data_ptr(), ko.data_ptr(), kt.data_ptr(), *vptrs, keys.numel(),
+        check(lib.gps_sort_keys32(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs, keys.numel(),
                                int(end_bit), _stream_ptr(stream, self.device)))
         return ko if values is None else (ko, vo)
 

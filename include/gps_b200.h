@@ -151,6 +151,15 @@ int gps_scan_wide(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in,
  * n < 2^32.  The ctx keeps the sort's own scratch (gps_sort_scratch_bytes(n) bytes, grown on
  * demand).  Asynchronous on `stream`; gps_check reports a tripped watchdog. */
 uint64_t gps_sort_scratch_bytes(uint64_t n);
+/* key types of gps_sort_keys32: int32 and float32 keys are mapped onto uint32 order on the
+ * way in (first pass) and back on the way out (last pass): ascending numeric order, -0.0
+ * before +0.0, NaNs at both ends by bit pattern (the convention of cub::DeviceRadixSort);
+ * both sort on all 32 bits (end_bit must be 32). */
+enum gps_key_type { GPS_KEY_U32 = 0, GPS_KEY_I32 = 1, GPS_KEY_F32 = 2 };
+int gps_sort_keys32(gps_ctx* ctx, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                    const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,
+                    int end_bit, void* stream);
+/* = gps_sort_keys32(GPS_KEY_U32, ...) */
 int gps_sort_u32(gps_ctx* ctx, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
                  const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,
                  int end_bit, void* stream);

@@ -187,6 +187,31 @@ uint64_t oracle_check_f64(const double *in, const double *cand, uint64_t n, int 
  * GPUSorting), so this is pinned in tests/test_oracle.py against numpy's stable sort instead
  * of reference vectors.  tmp_* are caller-provided work arrays of n elements; the result
  * lands in keys_out / vals_out.  vals_* may all be NULL. */
+/* int32 / float32 keys: the usual order-preserving maps onto uint32 (flip the sign bit; for
+ * floats flip every bit of negative values) around the same radix passes */
+static uint32_t oracle_key_map(uint32_t k, int type)
+{
+    if (type == 1) return k ^ 0x80000000u;
+    if (type == 2) return k ^ ((k >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    return k;
+}
+static uint32_t oracle_key_unmap(uint32_t k, int type)
+{
+    if (type == 1) return k ^ 0x80000000u;
+    if (type == 2) return k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+    return k;
+}
+void oracle_sort_u32(const uint32_t *keys_in, uint32_t *keys_out, uint32_t *keys_tmp, const uint32_t *vals_in,
+                     uint32_t *vals_out, uint32_t *vals_tmp, uint64_t n, int end_bit);
+/* key_type 0 = uint32, 1 = int32, 2 = float32 (bit patterns); keys_map is a work array of n keys */
+void oracle_sort_keys32(int key_type, const uint32_t *keys_in, uint32_t *keys_out, uint32_t *keys_tmp,
+                        uint32_t *keys_map, const uint32_t *vals_in, uint32_t *vals_out, uint32_t *vals_tmp, uint64_t n)
+{
+    for (uint64_t i = 0; i < n; ++i) keys_map[i] = oracle_key_map(keys_in[i], key_type);
+    oracle_sort_u32(keys_map, keys_out, keys_tmp, vals_in, vals_out, vals_tmp, n, 32);
+    for (uint64_t i = 0; i < n; ++i) keys_out[i] = oracle_key_unmap(keys_out[i], key_type);
+}
+
 void oracle_sort_u32(const uint32_t *keys_in, uint32_t *keys_out, uint32_t *keys_tmp, const uint32_t *vals_in,
                      uint32_t *vals_out, uint32_t *vals_tmp, uint64_t n, int end_bit)
 {

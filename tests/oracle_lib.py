@@ -51,6 +51,8 @@ class Oracle:
                                          C.POINTER(C.c_double)]
         lib.oracle_sort_u32.restype = None
         lib.oracle_sort_u32.argtypes = [C.c_void_p] * 6 + [C.c_uint64, C.c_int]
+        lib.oracle_sort_keys32.restype = None
+        lib.oracle_sort_keys32.argtypes = [C.c_int] + [C.c_void_p] * 7 + [C.c_uint64]
         lib.oracle_validate_ones.restype = C.c_uint64
         lib.oracle_validate_ones.argtypes = [_u32p, C.c_uint64, C.c_int]
         lib.oracle_init_random_d3d12.restype = None
@@ -126,6 +128,20 @@ class Oracle:
         vo, vt = np.empty_like(vals), np.empty_like(vals)
         self.lib.oracle_sort_u32(ptr(keys), ptr(ko), ptr(kt), ptr(vals), ptr(vo), ptr(vt), keys.size, end_bit)
         return ko, vo
+
+    def sort_keys32(self, keys: np.ndarray, vals: np.ndarray | None = None, key_type: str = "u32"):
+        """keys: int32 / float32 / uint32 array; sorted by numeric order of that type (stable)."""
+        kt = {"u32": 0, "i32": 1, "f32": 2}[key_type]
+        bits = np.ascontiguousarray(keys).view(np.uint32)
+        ko, ktmp, kmap = np.empty_like(bits), np.empty_like(bits), np.empty_like(bits)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        vo = vt = None
+        if vals is not None:
+            vals = np.ascontiguousarray(vals, dtype=np.uint32)
+            vo, vt = np.empty_like(vals), np.empty_like(vals)
+        self.lib.oracle_sort_keys32(kt, ptr(bits), ptr(ko), ptr(ktmp), ptr(kmap), ptr(vals), ptr(vo), ptr(vt), bits.size)
+        ko = ko.view(keys.dtype)
+        return ko if vals is None else (ko, vo)
 
     def validate_ones(self, scan: np.ndarray, exclusive: bool) -> int:
         return self.lib.oracle_validate_ones(np.ascontiguousarray(scan, dtype=np.uint32), scan.size, int(exclusive))

@@ -135,3 +135,32 @@ def test_sort_2p28_sortedness_and_multiset():
     assert int((sx * sx).sum()) == int((so * so).sum())  # wraps mod 2^64 identically
     del sx, so
     big.close()
+
+
+def test_sort_int32_and_float32_keys(ps, oracle):
+    """Signed and floating-point keys (order-preserving maps applied in the first / last pass):
+    bit-exact against the oracle incl. -0.0, infinities and NaN bit patterns; pairs stable."""
+    rng = np.random.default_rng(12)
+    for n in [1, 10_239, 10_241, 300_007]:
+        vals = np.arange(n, dtype=np.uint32)
+        ki = rng.integers(-2**31, 2**31, size=n, dtype=np.int64).astype(np.int32)
+        ko, vo = ps.sort(torch.from_numpy(ki).cuda(), dev(vals), key_type="i32")
+        ps.check()
+        wk, wv = oracle.sort_keys32(ki, vals, "i32")
+        assert np.array_equal(ko.cpu().numpy(), wk) and np.array_equal(host(vo), wv), n
+        assert np.array_equal(wk, np.sort(ki))
+        bits = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)  # every float pattern incl. NaN
+        kf = bits.view(np.float32).copy()
+        if n > 8:
+            kf[:6] = [0.0, -0.0, np.inf, -np.inf, 1.5, -1.5]
+        ko, vo = ps.sort(torch.from_numpy(kf).cuda(), dev(vals), key_type="f32")
+        ps.check()
+        wk, wv = oracle.sort_keys32(kf, vals, "f32")
+        assert np.array_equal(ko.cpu().numpy().view(np.uint32), wk.view(np.uint32)) and np.array_equal(host(vo), wv), n
+        finite = kf[np.isfinite(kf)]
+        out_finite = ko.cpu().numpy()
+        out_finite = out_finite[np.isfinite(out_finite)]
+        assert np.array_equal(out_finite, np.sort(finite))  # numeric order (-0.0 == 0.0 for numpy)
+    import gpuprefixsums_b200 as gps
+    with pytest.raises(gps.GpsError):
+        ps.sort(torch.zeros(8, dtype=torch.float32, device="cuda"), key_type="f32", end_bit=16)

@@ -46,6 +46,8 @@ gps.cub_sort(keys, ref, vals, refv)
 res["pairs_equal_cub"] = bool(torch.equal(ko, ref) and torch.equal(vo, refv))
 res["cub_keys"] = timed(lambda: gps.cub_sort(keys, ref))
 res["cub_pairs"] = timed(lambda: gps.cub_sort(keys, ref, vals, refv))
+kf = keys.view(torch.float32)
+res["gps_keys_f32"] = timed(lambda: ps.sort(kf, key_type="f32"))
 res["gps_keys_16bit"] = timed(lambda: ps.sort(keys, keys_out=ko, end_bit=16))
 ps.close()
 print(json.dumps(res))
