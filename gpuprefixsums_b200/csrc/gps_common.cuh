@@ -5,14 +5,16 @@
 //                     WarpReduceSum, uint4 helpers
 //   ChainedScanDecoupledLookback.cuh:19-23,50-77   flag encoding + LookbackWarp
 // Differences that matter on B200:
-//   * tile descriptor is ONE 64-bit word {value:32 | epoch:30 | status:2} written with
-//     st.release.gpu / read with ld.acquire.gpu, so the aggregate is a full 32-bit
-//     value (the reference packs 30 bits next to the flag and silently truncates
-//     totals >= 2^30) and float32 bit patterns travel unchanged;
+//   * tile descriptor is ONE 64-bit word {value:32 | epoch:30 | status:2}, so the aggregate is
+//     a full 32-bit value (the reference packs 30 bits next to the flag and silently
+//     truncates totals >= 2^30) and float32 bit patterns travel unchanged.  Because payload
+//     and flag share the word, publish = atom.exch.relaxed.gpu and poll = ld.relaxed.gpu by
+//     default (measured fastest, see desc_publish below); st.release.gpu / ld.acquire.gpu
+//     stay selectable;
 //   * the epoch tag makes descriptors of earlier launches read as NOT_READY, so no
 //     cudaMemset per launch (reference: ...Dispatcher.cuh:172-175);
-//   * polls are gpu-scope acquire loads, not `volatile` (.SYS) loads, and only the
-//     publishing lane orders its store -- no block-wide __threadfence().
+//   * polls are gpu-scope loads, not `volatile` (.SYS) loads, and no block-wide
+//     __threadfence() is needed (the reference fences in every thread).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
