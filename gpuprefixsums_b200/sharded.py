@@ -146,3 +146,48 @@ class ShardedScan:
                                                          torch.cuda.current_stream().cuda_stream))
         return self.ps.scan_carry_slots(inp, out, base, self.world, self.rank, tag, algo=algo,
                                         exclusive=exclusive)
+
+    # ---- host buffers in, host buffers out, pipelined across calls ---------------------
+    def scan_host(self, h_in: torch.Tensor, h_out: torch.Tensor, *, algo="csdl", exclusive: bool = False) -> None:
+        """This rank's slice from (pinned) host memory to (pinned) host memory, ASYNCHRONOUS:
+        H2D, reduce + scan, and D2H run on three streams over two device buffer pairs, so
+        the copy-in of call k+1 overlaps the copy-out of call k (a scan needs its whole
+        slice -- and every upstream total -- before it can write anything, so inside one call
+        the two directions cannot overlap).  Call ``synchronize_host()`` before reading
+        ``h_out`` or re-using ``h_in``.  The slot protocol is unchanged: all compute of a rank
+        stays in order on one stream."""
+        n = h_in.numel()
+        if h_in.is_cuda or h_out.is_cuda or h_out.numel() != n:
+            raise ValueError("scan_host takes two CPU tensors of equal size")
+        if getattr(self, "_hp", None) is None or self._hp["x"][0].numel() < n or self._hp["x"][0].dtype != h_in.dtype:
+            mk = lambda: torch.empty(n, dtype=h_in.dtype, device=self.device)  # noqa: E731
+            ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]  # noqa: E731
+            self._hp = {"x": [mk(), mk()], "out": [mk(), mk()], "k": 0,
+                        "s_h2d": torch.cuda.Stream(self.device), "s_cmp": torch.cuda.Stream(self.device),
+                        "s_d2h": torch.cuda.Stream(self.device), "ev_h2d": ev(), "ev_cmp": ev(), "ev_d2h": ev()}
+        hp = self._hp
+        b = hp["k"] & 1
+        first = hp["k"] < 2
+        hp["k"] += 1
+        x, out = hp["x"][b][:n], hp["out"][b][:n]
+        with torch.cuda.stream(hp["s_h2d"]):
+            if not first:
+                hp["s_h2d"].wait_event(hp["ev_cmp"][b])  # x[b] is free once the scan two calls ago is done
+            x.copy_(h_in, non_blocking=True)
+            hp["ev_h2d"][b].record(hp["s_h2d"])
+        with torch.cuda.stream(hp["s_cmp"]):
+            hp["s_cmp"].wait_event(hp["ev_h2d"][b])
+            if not first:
+                hp["s_cmp"].wait_event(hp["ev_d2h"][b])  # out[b] is free once it went back to the host
+            self.scan(x, out, algo=algo, exclusive=exclusive)
+            hp["ev_cmp"][b].record(hp["s_cmp"])
+        with torch.cuda.stream(hp["s_d2h"]):
+            hp["s_d2h"].wait_event(hp["ev_cmp"][b])
+            h_out.copy_(out, non_blocking=True)
+            hp["ev_d2h"][b].record(hp["s_d2h"])
+
+    def synchronize_host(self) -> None:
+        hp = getattr(self, "_hp", None)
+        if hp is not None:
+            for key in ("s_h2d", "s_cmp", "s_d2h"):
+                hp[key].synchronize()

@@ -81,6 +81,16 @@ def _rank_main(rank: int, world: int, port: int, n_total: int, mode: str, algo: 
             full = oracle.random_u32(n_total, seed=5)
             want, _ = oracle.scan_u32(full, exclusive=bool(step & 1))
             ok = ok and np.array_equal(out.cpu().numpy().view(np.uint32), want[lo:hi])
+        # host buffers in -> host buffers out, asynchronous and pipelined across calls
+        h_in = x.cpu().pin_memory()
+        h_outs = [torch.empty_like(h_in).pin_memory() for _ in range(5)]
+        for k, h_out in enumerate(h_outs):
+            sh.scan_host(h_in, h_out, algo=algo, exclusive=bool(k & 1))
+        sh.synchronize_host()
+        sh.ps.check()
+        for k, h_out in enumerate(h_outs):
+            want, _ = oracle.scan_u32(full, exclusive=bool(k & 1))
+            ok = ok and np.array_equal(h_out.numpy().view(np.uint32), want[lo:hi])
         dist.barrier()
         sh.close()
         q.put((rank, ok))
