@@ -339,19 +339,23 @@ def run_ours(args) -> None:
     h_in.copy_(x)
     h_out = torch.empty(n_local, dtype=torch.int32).pin_memory()
     if world == 1:
-        e2e_step = lambda: ps.scan_host(h_in, h_out, algo=args.algo)  # noqa: E731
+        e2e_step = lambda: ps.scan_host(h_in, h_out, algo=args.algo, wait=False)  # noqa: E731  (queued; synced below)
     else:
         e2e_step = lambda: sh.scan_host(h_in, h_out, algo=args.algo)  # noqa: E731  (asynchronous, see sharded.py)
     for _ in range(2):
         e2e_step()
     if world > 1:
         sh.synchronize_host()
+    else:
+        ps.host_sync()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     if world > 1:
         sh.synchronize_host()
+    else:
+        ps.host_sync()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -388,7 +392,7 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * n_total,
                     "d2h_bytes_per_step": 4 * n_total, "steps": e2e_steps,
-                    "path": "gps_scan_host (pinned host buffers, chunked H2D/scan/D2H pipeline)" if world == 1
+                    "path": "gps_scan_host_async per step + one gps_host_sync (pinned host buffers, chunked H2D/scan/D2H pipeline, staging buffers rotate across calls)" if world == 1
                     else "ShardedScan.scan_host: pinned H2D, reduce + scan, D2H per rank on three streams, copy-in of step k+1 overlapping copy-out of step k"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,

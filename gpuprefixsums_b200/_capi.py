@@ -61,6 +61,8 @@ SIGNATURES = {
     "gps_reduce_publish": (_i32, [_vp, _i32, _vp, _u64, C.POINTER(_vp), _u32, _u32, _vp, _vp]),
     "gps_scan_emulated_deadlock": (_i32, [_vp, _i32, _i32, _vp, _vp, _u64, _u32, _u32, _vp, _vp]),
     "gps_scan_host": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
+    "gps_scan_host_async": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
+    "gps_host_sync": (_i32, [_vp]),
     "gps_init_ones": (_i32, [_vp, _u64, _i32, _vp]),
     "gps_init_random": (_i32, [_vp, _u64, _i32, _u64, _u32, _u64, _vp]),
     "gps_validate_ones": (_i32, [_vp, _u64, _i32, _u32, C.POINTER(_u64)]),

@@ -85,6 +85,9 @@ struct gps_ctx {
     uint64_t* chain_slots = nullptr;  // 2 tagged slots chaining chunk totals
     uint32_t chain_tag = 0;
     void* chain_total = nullptr;
+    cudaEvent_t ev_total = nullptr;
+    bool ev_total_pending = false;
+    uint64_t host_chunk_seq = 0;    // chunks issued so far (staging buffer rotation across calls)
     // radix sort (lazy, grows on demand): 256 descriptors per tile shared by all passes,
     // 4 x 256 histogram + 4 x 256 digit bases
     uint64_t* sort_desc = nullptr;
@@ -460,6 +463,7 @@ void gps_destroy(gps_ctx* c)
     if (c->sort_desc) cudaFree(c->sort_desc);
     if (c->sort_hist) cudaFree(c->sort_hist);
     if (c->chain_total) cudaFree(c->chain_total);
+    if (c->ev_total) cudaEventDestroy(c->ev_total);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -773,11 +777,12 @@ static int host_pipeline_init(gps_ctx* c)
     GPS_CUDA(cudaMalloc(&c->chain_slots, 2 * sizeof(uint64_t)));
     GPS_CUDA(cudaMemset(c->chain_slots, 0, 2 * sizeof(uint64_t)));
     GPS_CUDA(cudaMalloc(&c->chain_total, 16));
+    GPS_CUDA(cudaEventCreateWithFlags(&c->ev_total, cudaEventDisableTiming));
     return GPS_OK;
 }
 
-int gps_scan_host(gps_ctx* c, int algo, int kind, int dtype, const void* h_in, void* h_out,
-                  uint64_t n, uint32_t carry_in_bits, void* h_total_out)
+int gps_scan_host_async(gps_ctx* c, int algo, int kind, int dtype, const void* h_in, void* h_out,
+                        uint64_t n, uint32_t carry_in_bits, void* h_total_out)
 {
     if (!c) return fail(GPS_ERR_INVALID, "null ctx");
     if (n && (!h_in || !h_out)) return fail(GPS_ERR_INVALID, "null host pointer");
@@ -791,11 +796,12 @@ int gps_scan_host(gps_ctx* c, int algo, int kind, int dtype, const void* h_in, v
     char* dst = static_cast<char*>(h_out);
     uint32_t prev_tag = 0;
     for (uint64_t k = 0; k < n_chunks; ++k) {
-        const int b = (int)(k % kHostBufs);
+        const uint64_t seq = c->host_chunk_seq++;  // staging buffers rotate ACROSS calls, so the first
+        const int b = (int)(seq % kHostBufs);      // copy-in of a call overlaps the last copy-out of the previous one
         const uint64_t off = k * chunk;
         const uint64_t len = std::min<uint64_t>(chunk, n - off);
         // the staging buffer is free once its previous contents went back to the host
-        if (k >= (uint64_t)kHostBufs) GPS_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));
+        if (seq >= (uint64_t)kHostBufs) GPS_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));
         if (len) GPS_CUDA(cudaMemcpyAsync(c->stage[b], src + off * 4, len * 4, cudaMemcpyHostToDevice, c->s_h2d));
         GPS_CUDA(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
         GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_h2d[b], 0));
@@ -813,7 +819,12 @@ int gps_scan_host(gps_ctx* c, int algo, int kind, int dtype, const void* h_in, v
         cs.publish.n = 1;
         cs.publish.dst[0] = c->chain_slots + (k & 1);
         cs.publish.tag = tag;
-        if (k + 1 == n_chunks) cs.total_out = c->chain_total;
+        if (k + 1 == n_chunks) {
+            cs.total_out = c->chain_total;
+            // the previous call's copy of chain_total to the host must have been performed
+            if (c->ev_total_pending) GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_total, 0));
+            c->ev_total_pending = false;
+        }
         rc = dispatch_scan(c, algo, kind, dtype, c->stage[b], c->stage[b], len, cs, c->s_cmp);
         if (rc) return rc;
         GPS_CUDA(cudaEventRecord(c->ev_cmp[b], c->s_cmp));
@@ -821,14 +832,32 @@ int gps_scan_host(gps_ctx* c, int algo, int kind, int dtype, const void* h_in, v
         if (len) GPS_CUDA(cudaMemcpyAsync(dst + off * 4, c->stage[b], len * 4, cudaMemcpyDeviceToHost, c->s_d2h));
         GPS_CUDA(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
     }
-    if (h_total_out) {
-        GPS_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_cmp[(n_chunks - 1) % kHostBufs], 0));
+    if (h_total_out) {  // queued behind the last chunk's copy-out, which already waits for its scan
         GPS_CUDA(cudaMemcpyAsync(h_total_out, c->chain_total, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        GPS_CUDA(cudaEventRecord(c->ev_total, c->s_d2h));
+        c->ev_total_pending = true;
     }
-    GPS_CUDA(cudaStreamSynchronize(c->s_d2h));
-    GPS_CUDA(cudaStreamSynchronize(c->s_cmp));
     return GPS_OK;
 }
+
+int gps_host_sync(gps_ctx* c)
+{
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    if (!c->stage[0]) return GPS_OK;
+    DeviceGuard g(c->device);
+    GPS_CUDA(cudaStreamSynchronize(c->s_h2d));
+    GPS_CUDA(cudaStreamSynchronize(c->s_cmp));
+    GPS_CUDA(cudaStreamSynchronize(c->s_d2h));
+    return GPS_OK;
+}
+
+int gps_scan_host(gps_ctx* c, int algo, int kind, int dtype, const void* h_in, void* h_out,
+                  uint64_t n, uint32_t carry_in_bits, void* h_total_out)
+{
+    const int rc = gps_scan_host_async(c, algo, kind, dtype, h_in, h_out, n, carry_in_bits, h_total_out);
+    return rc ? rc : gps_host_sync(c);
+}
+
 
 // ---------------------------------------------------------------------------------
 // harness kernels

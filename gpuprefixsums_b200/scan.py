@@ -213,15 +213,20 @@ class PrefixSum:
         return out
 
     def scan_host(self, h_in: torch.Tensor, h_out: Optional[torch.Tensor] = None, *, algo="csdl",
-                  exclusive: bool = False, carry=0) -> torch.Tensor:
-        """Host buffers in, host buffers out (pinned recommended); synchronous."""
+                  exclusive: bool = False, carry=0, wait: bool = True) -> torch.Tensor:
+        """Host buffers in, host buffers out (pinned recommended).  wait=False returns once the
+        work is queued (consecutive calls then overlap their copies); host_sync() waits."""
         if h_in.is_cuda or not h_in.is_contiguous():
             raise ValueError("scan_host takes contiguous CPU tensors")
         if h_out is None:
             h_out = torch.empty_like(h_in, pin_memory=h_in.is_pinned())
-        check(lib.gps_scan_host(self._ctx, _algo(algo), _kind(exclusive), _dtype_code(h_in), h_in.data_ptr(),
-                                h_out.data_ptr(), h_in.numel(), carry_bits(carry, h_in.dtype), None))
+        fn = lib.gps_scan_host if wait else lib.gps_scan_host_async
+        check(fn(self._ctx, _algo(algo), _kind(exclusive), _dtype_code(h_in), h_in.data_ptr(),
+                 h_out.data_ptr(), h_in.numel(), carry_bits(carry, h_in.dtype), None))
         return h_out
+
+    def host_sync(self) -> None:
+        check(lib.gps_host_sync(self._ctx))
 
 
 # ---- harness helpers (UtilityKernels.cuh:15-38 equivalents) --------------------------

@@ -206,6 +206,12 @@ int gps_scan_emulated_deadlock(gps_ctx* ctx, int kind, int dtype, const void* d_
  * h_in / h_out should be pinned for full PCIe bandwidth (pageable works). */
 int gps_scan_host(gps_ctx* ctx, int algo, int kind, int dtype, const void* h_in,
                   void* h_out, uint64_t n, uint32_t carry_in_bits, void* h_total_out);
+/* The same without the final wait: returns once everything is queued.  Consecutive calls share
+ * the staging-buffer rotation, so the first copy-in of a call overlaps the last copy-out of
+ * the previous one.  gps_host_sync waits for all queued host-buffer work of the ctx. */
+int gps_scan_host_async(gps_ctx* ctx, int algo, int kind, int dtype, const void* h_in,
+                  void* h_out, uint64_t n, uint32_t carry_in_bits, void* h_total_out);
+int gps_host_sync(gps_ctx* ctx);
 
 /* ---- harness kernels: UtilityKernels.cuh:15-38 -------------------------------- */
 int gps_init_ones(void* d, uint64_t n, int dtype, void* stream);               /* InitOne  */

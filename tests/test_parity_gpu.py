@@ -334,6 +334,19 @@ def test_scan_host_pipeline(gps, oracle):
             h_out = ps.scan_host(h_in, exclusive=exclusive, carry=3)
             want, _ = oracle.scan_u32(x, exclusive=exclusive, carry=3)
             assert np.array_equal(h_out.numpy().view(np.uint32), want), (n, exclusive)
+    # queued calls (wait=False) of different sizes and kinds share the staging rotation
+    cases = []
+    for k, n in enumerate([(1 << 20) + 3, 7, 1 << 21, (1 << 22) + 4099, 1 << 20, 12345]):
+        x = oracle.random_u32(n, seed=70 + k)
+        h_in = torch.from_numpy(x.view(np.int32)).pin_memory()
+        h_out = torch.empty_like(h_in).pin_memory()
+        ps.scan_host(h_in, h_out, exclusive=bool(k & 1), carry=k, wait=False)
+        cases.append((x, h_in, h_out, bool(k & 1), k))
+    ps.host_sync()
+    ps.check()
+    for x, _, h_out, exclusive, carry in cases:
+        want, _ = oracle.scan_u32(x, exclusive=exclusive, carry=carry)
+        assert np.array_equal(h_out.numpy().view(np.uint32), want), (x.size, exclusive)
     ps.close()
 
 
