@@ -34,7 +34,7 @@
 
 namespace gps {
 
-struct u32x4 {
+struct __align__(16) u32x4 {  // 16-byte aligned: one LDG.128 / STG.128 per element
     uint32_t a, b, c, d;
 };
 __device__ __forceinline__ u32x4 operator+(u32x4 x, u32x4 y)
@@ -412,22 +412,24 @@ __global__ void __launch_bounds__(NT) wide_reduce_kernel(const __grid_constant__
     const uint4* in4 = reinterpret_cast<const uint4*>(p.in);
     const E* in1 = reinterpret_cast<const E*>(p.in);
     const uint64_t vbase = (uint64_t)tile * S::TILE_VEC + (uint64_t)warp * S::WARP_VEC + lane;  // lane-strided
-    Vec t[V];
+    E acc = wide_zero<E>();
+    if (full) {  // hoisted: V independent 128-bit loads back to back, then the sum
+        Vec t[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-        const uint64_t v = vbase + 32u * k;
-        if (full || (v + 1u) * KPV <= p.n) {
-            t[k].u = ldg_stream(in4 + v);
-        } else {
+        for (int k = 0; k < V; ++k) t[k].u = ldg_stream(in4 + vbase + 32u * k);
 #pragma unroll
-            for (int c = 0; c < KPV; ++c) t[k].e[c] = (v * KPV + c < p.n) ? in1[v * KPV + c] : wide_zero<E>();
+        for (int k = 0; k < V; ++k)
+#pragma unroll
+            for (int c = 0; c < KPV; ++c) acc = acc + t[k].e[c];
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < V; ++k) {
+            const uint64_t v = vbase + 32u * k;
+#pragma unroll
+            for (int c = 0; c < KPV; ++c)
+                if (v * KPV + c < p.n) acc = acc + in1[v * KPV + c];
         }
     }
-    E acc = wide_zero<E>();
-#pragma unroll
-    for (int k = 0; k < V; ++k)
-#pragma unroll
-        for (int c = 0; c < KPV; ++c) acc = acc + t[k].e[c];
     const E ws = wide_warp_reduce(acc);
     if (lane == 0) s_red[warp] = ws;
     __syncthreads();
@@ -451,15 +453,19 @@ __global__ void __launch_bounds__(1024) wide_spine_kernel(const __grid_constant_
     E* partials = reinterpret_cast<E*>(p.partials);
     E running = p.carry;
     uint32_t it = 0;
+    auto load_chunk = [&](uint32_t base, E (&dst)[ITEMS]) {
+        const uint32_t i0 = base + threadIdx.x * ITEMS;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) dst[i] = (i0 + i < p.num_tiles) ? partials[i0 + i] : wide_zero<E>();
+    };
+    E v[ITEMS], nxt[ITEMS];
+    load_chunk(0, v);
     for (uint32_t base = 0; base < p.num_tiles; base += CHUNK, ++it) {
         const uint32_t i0 = base + threadIdx.x * ITEMS;
-        E v[ITEMS];
+        if (base + CHUNK < p.num_tiles) load_chunk(base + CHUNK, nxt);  // in flight while this chunk is scanned
         E tsum = wide_zero<E>();
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            v[i] = (i0 + i < p.num_tiles) ? partials[i0 + i] : wide_zero<E>();
-            tsum = tsum + v[i];
-        }
+        for (int i = 0; i < ITEMS; ++i) tsum = tsum + v[i];
         const E inc = wide_warp_inclusive_scan(tsum);
         const E lane_excl = wide_exclusive_of(inc, tsum, lane);
         E* sw = s_warp[it & 1u];
@@ -485,6 +491,8 @@ __global__ void __launch_bounds__(1024) wide_spine_kernel(const __grid_constant_
             run = run + v[i];
         }
         running = running + total;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) v[i] = nxt[i];
     }
     if (threadIdx.x == 0 && p.total_out) *reinterpret_cast<E*>(p.total_out) = running;
 }
