@@ -90,7 +90,10 @@
 // Measured at 2^28 random keys on B200 (profiles/r01_sort_sweep.txt), Gkeys/s keys / pairs:
 // <256,16> LB 4: 50.0 / 44.9 (default); LB 1: 48.7 / 42.4; LB 8: 45.7 / 42.3; LB 16: 37.8 / 38.3;
 // <256,12>: 38.8 / 36.8; <512,8>: 34.4 (keys); <384,12>: 37.0 (keys);
-// cub::DeviceRadixSort (CCCL 2.8.2, onesweep) on the same box: 44.5 / 35.2
+// cub::DeviceRadixSort (CCCL 2.8.2, onesweep) on the same box: 44.5 / 35.2.
+// Later: dynamic shared memory, <256,40> tiles, conflict-free histogram: 65.8 / 50.0; ranks packed
+// two per register so that 3 CTAs fit per SM (84 registers): keys <256,40> 74.4 (<256,32> r64 72.5,
+// <256,44> 69.4, <256,48> r96 69.9), pairs <256,32> 55.7 (<256,28> 53.9, <256,40> r128 50.0)
 #ifndef GPS_SORT_NT
 #define GPS_SORT_NT 256
 #endif
@@ -98,7 +101,7 @@
 #define GPS_SORT_KPT 40
 #endif
 #ifndef GPS_SORT_REGS
-#define GPS_SORT_REGS 128
+#define GPS_SORT_REGS 84
 #endif
 // descriptors fetched per look-back round trip (per digit)
 #ifndef GPS_SORT_LB
@@ -109,10 +112,10 @@
 #define GPS_SORT_PAIRS_NT GPS_SORT_NT
 #endif
 #ifndef GPS_SORT_PAIRS_KPT
-#define GPS_SORT_PAIRS_KPT GPS_SORT_KPT
+#define GPS_SORT_PAIRS_KPT 32
 #endif
 #ifndef GPS_SORT_PAIRS_REGS
-#define GPS_SORT_PAIRS_REGS 128
+#define GPS_SORT_PAIRS_REGS 84
 #endif
 
 // CSDL on the blocked shared-memory tile (gps_csdl_blocked.cuh): NT threads x V (odd) uint4

@@ -260,7 +260,14 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     }
     // ---- warp-level multi-split: rank of each key among the warp's keys of the same digit,
     // in (j, lane) order == original order (stability)
-    uint32_t pos[KPT];
+    // ranks / positions are < TILE <= 65536: two per register (registers decide the occupancy)
+    static_assert(TILE <= 65536 && KPT % 2 == 0, "16-bit packed positions");
+    uint32_t pos2[KPT / 2] = {};
+    auto get_pos = [&](int j) -> uint32_t { return (j & 1) ? (pos2[j >> 1] >> 16) : (pos2[j >> 1] & 0xFFFFu); };
+    auto set_pos = [&](int j, uint32_t v) {
+        pos2[j >> 1] = (j & 1) ? __byte_perm(pos2[j >> 1], v, 0x5410)   // high half <- v, low half kept
+                               : __byte_perm(v, pos2[j >> 1], 0x7610);  // low half <- v, high half kept
+    };
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
         const uint32_t d = sort_digit(key[j], p.shift);
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
         __syncwarp();
         if (below == 0u) s_whist[warp][d] = pre + __popc(peers);
         __syncwarp();
-        pos[j] = pre + below;
+        set_pos(j, pre + below);
     }
     __syncthreads();  // every warp counted; s_keys no longer needed in its loaded order
 
@@ -301,8 +308,9 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     // ---- keys into shared memory in digit order
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
-        pos[j] += s_whist[warp][sort_digit(key[j], p.shift)];
-        s_keys[pos[j]] = key[j];
+        const uint32_t q = get_pos(j) + s_whist[warp][sort_digit(key[j], p.shift)];
+        set_pos(j, q);
+        s_keys[q] = key[j];
     }
     if constexpr (PAIRS) {
         // the payload takes the same permutation, in place in its own buffer (no registers are
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
         for (int j = 0; j < KPT; ++j) val[j] = s_vals[warp * WARP_KEYS + j * 32 + lane];
         __syncthreads();
 #pragma unroll
-        for (int j = 0; j < KPT; ++j) s_vals[pos[j]] = val[j];
+        for (int j = 0; j < KPT; ++j) s_vals[get_pos(j)] = val[j];
     }
 
     // ---- chained scan across tiles, one look-back per digit (thread d walks digit d)

@@ -1,6 +1,6 @@
 """GPU parity for the radix-sort consumer: keys bit-exact against the oracle's
 stable LSD sort (itself pinned on numpy), pairs in the unique stable order; ragged sizes around
-the 10240-key tile, few distinct keys, already-sorted / reversed / constant inputs, partial bit
+the 10240-key (keys) and 8192-key (pairs) tiles, few distinct keys, already-sorted / reversed / constant inputs, partial bit
 ranges, in == out, back-to-back sorts on one ctx (epoch-tagged descriptors, no clearing)."""
 import numpy as np
 import pytest
@@ -8,7 +8,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [1, 2, 3, 31, 255, 256, 257, 4095, 4097, 10_239, 10_240, 10_241, 20_479, 20_481, 100_003, (1 << 20) + 7,
+SIZES = [1, 2, 3, 31, 255, 256, 257, 4095, 4097, 8191, 8192, 8193, 10_239, 10_240, 10_241, 16_385, 20_479, 20_481,
+         100_003, (1 << 20) + 7,
          (1 << 22) + 4099]
 
 
