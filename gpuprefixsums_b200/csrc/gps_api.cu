@@ -87,6 +87,9 @@ struct gps_ctx {
     void* chain_total = nullptr;
     cudaEvent_t ev_total = nullptr;
     bool ev_total_pending = false;
+    cudaStream_t last_stream = nullptr;  // stream of the previous launch that used the scratch
+    bool has_last_stream = false;
+    cudaEvent_t ev_order = nullptr;
     uint64_t host_chunk_seq = 0;    // chunks issued so far (staging buffer rotation across calls)
     // radix sort (lazy, grows on demand): 256 descriptors per tile shared by all passes,
     // 4 x 256 histogram + 4 x 256 digit bases
@@ -113,6 +116,13 @@ struct DeviceGuard {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// The scratch of a ctx (ticket counter, descriptors, partials) is consumed in LAUNCH order: the
+// host-side counter_base / epoch bookkeeping assumes the kernels of a ctx also EXECUTE in that
+// order.  Launches on one stream do; when a launch arrives on a different stream than the
+// previous one (e.g. gps_scan on the caller's stream, then the host pipeline on its own
+// streams), it is ordered behind the previous launch with an event.
+int enter_stream(gps_ctx* c, cudaStream_t st);
 
 template <typename T>
 constexpr int dt_index() { return std::is_same<T, float>::value ? 1 : 0; }
@@ -217,12 +227,29 @@ int check_scan_args(gps_ctx* c, int kind, int dtype, const void* in, void* out, 
     return GPS_OK;
 }
 
+int enter_stream(gps_ctx* c, cudaStream_t st)
+{
+    if (c->has_last_stream && c->last_stream != st) {
+        if (!c->ev_order) GPS_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+        // (a caller who destroyed the previous stream has necessarily drained it: ignore the error)
+        if (cudaEventRecord(c->ev_order, c->last_stream) == cudaSuccess)
+            GPS_CUDA(cudaStreamWaitEvent(st, c->ev_order, 0));
+        else
+            cudaGetLastError();
+    }
+    c->last_stream = st;
+    c->has_last_stream = true;
+    return GPS_OK;
+}
+
 int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, void* out, uint64_t n,
                   const CarrySpec& cs, cudaStream_t st)
 {
     int rc = check_scan_args(c, kind, dtype, in, out, n);
     if (rc) return rc;
     DeviceGuard g(c->device);
+    rc = enter_stream(c, st);
+    if (rc) return rc;
     if (dtype == GPS_U32)
         return kind == GPS_INCLUSIVE ? dispatch_scan_tk<uint32_t, true>(c, algo, in, out, n, cs, st)
                                      : dispatch_scan_tk<uint32_t, false>(c, algo, in, out, n, cs, st);
@@ -464,6 +491,7 @@ void gps_destroy(gps_ctx* c)
     if (c->sort_hist) cudaFree(c->sort_hist);
     if (c->chain_total) cudaFree(c->chain_total);
     if (c->ev_total) cudaEventDestroy(c->ev_total);
+    if (c->ev_order) cudaEventDestroy(c->ev_order);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_cmp) cudaStreamDestroy(c->s_cmp);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -564,6 +592,7 @@ int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, v
     if (!aligned16(d_in) || !aligned16(d_out)) return fail(GPS_ERR_ALIGNMENT, "data pointers must be 16-byte aligned");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = enter_stream(c, st)) return rc;
     const bool incl = kind == GPS_INCLUSIVE;
     bool& cfg = c->wide_configured[dtype][incl ? 0 : 1][algo == GPS_ALGO_RTS ? 1 : 0];
     switch (dtype) {
@@ -623,6 +652,7 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         return fail(GPS_ERR_INVALID, "in == out needs an even number of digit passes (end_bit 9..16 or 25..32)");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = enter_stream(c, st)) return rc;
     const uint32_t tiles = (uint32_t)div_up(n, pairs ? kSortPairsTile : kSortTile);
     if (tiles > c->sort_desc_tiles) {  // grow (synchronous, rare)
         GPS_CUDA(cudaDeviceSynchronize());
@@ -717,6 +747,8 @@ int gps_reduce_publish(gps_ctx* c, int dtype, const void* d_in, uint64_t n,
     if (rc) return rc;
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
+    rc = enter_stream(c, st);
+    if (rc) return rc;
     const cudaError_t e =
         dtype == GPS_U32
             ? launch_reduce<uint32_t, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, st)
@@ -745,6 +777,8 @@ int gps_scan_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void* d_in
     CarrySpec cs;
     FallbackParams f{stall_mask, max_spin, d_stats};
     cudaStream_t st = (cudaStream_t)stream;
+    rc = enter_stream(c, st);
+    if (rc) return rc;
     cudaError_t e;
     if (dtype == GPS_U32)
         e = kind == GPS_INCLUSIVE

@@ -81,6 +81,10 @@ int gps_device_info(int device, char* name, int* sm_count, uint64_t* l2_bytes,
  * ChainedScanDecoupledLookbackDispatcher.cuh:28-34,158-163 (m_index,
  * m_threadBlockReduction), ReduceThenScanDispatcher.cuh:27-33,152-156.  Unlike the
  * reference the ctx does not own the data buffer. */
+/* Threading / streams: a ctx is thread-compatible, not thread-safe (one host thread at a time).
+ * Its scratch is consumed in launch order; launches may go to any stream -- when consecutive
+ * launches of one ctx use different streams the library orders them with an event (so they
+ * serialise).  For concurrent scans use one ctx per stream. */
 int gps_create(gps_ctx** ctx, int device, uint64_t max_n);
 void gps_destroy(gps_ctx* ctx);
 /* Synchronises `stream` and reports GPS_ERR_WATCHDOG if any launch since the last

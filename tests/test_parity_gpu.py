@@ -524,3 +524,34 @@ def test_rts_variants_forced(gps, oracle, variant):
     errs, max_rel = oracle.check_f32(xf.cpu().numpy(), a.cpu().numpy(), rtol=F32_RTOL, atol=F32_ATOL)
     assert errs == 0, max_rel
     ps.close()
+
+
+def test_one_ctx_on_several_streams(gps, oracle):
+    """Consecutive launches of one ctx on DIFFERENT streams (no synchronisation by the caller):
+    the library orders them, so the shared ticket counter / descriptors stay consistent.
+    (Found by compute-sanitizer: a sort on the default stream followed by the host pipeline
+    on its own streams used to race on the ticket counter.)"""
+    ps = gps.PrefixSum(1 << 22)
+    n = (1 << 21) + 77
+    x = oracle.random_u32(n, seed=91)
+    want, _ = oracle.scan_u32(x)
+    d = to_dev_u32(x)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    torch.cuda.synchronize()
+    outs = []
+    for it in range(12):
+        st = streams[it % 3]
+        with torch.cuda.stream(st):
+            outs.append(ps.scan(d, algo=["csdl_reg", "csdl_smem", "rts", "csdl_blocked"][it % 4], stream=st))
+            if it % 4 == 1:
+                outs.append(ps.sort(d))  # current stream = st
+    h_in = torch.from_numpy(x.view(np.int32)).pin_memory()
+    h_out = ps.scan_host(h_in, wait=False)  # the pipeline's own streams
+    ps.host_sync()
+    torch.cuda.synchronize()
+    ps.check()
+    for o in outs:
+        if o.numel() == n and not np.array_equal(to_np_u32(o), want):
+            assert np.array_equal(to_np_u32(o), np.sort(x))
+    assert np.array_equal(h_out.numpy().view(np.uint32), want)
+    ps.close()
