@@ -633,10 +633,11 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
                     const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
 {
     if (!c) return fail(GPS_ERR_INVALID, "null ctx");
-    if (key_type != GPS_KEY_U32 && key_type != GPS_KEY_I32 && key_type != GPS_KEY_F32)
+    const int base_type = key_type & ~GPS_KEY_DESCENDING;
+    if (base_type != GPS_KEY_U32 && base_type != GPS_KEY_I32 && base_type != GPS_KEY_F32)
         return fail(GPS_ERR_INVALID, "bad key type %d", key_type);
     if (key_type != GPS_KEY_U32 && end_bit != 32)
-        return fail(GPS_ERR_INVALID, "int32 / float32 keys sort on all 32 bits (end_bit 32)");
+        return fail(GPS_ERR_INVALID, "int32 / float32 / descending sorts use all 32 bits (end_bit 32)");
     if (end_bit < 1 || end_bit > 32) return fail(GPS_ERR_INVALID, "end_bit %d outside 1..32", end_bit);
     if (n >= (1ull << 32)) return fail(GPS_ERR_INVALID, "gps_sort_u32 takes fewer than 2^32 keys");
     const bool pairs = d_vals_in || d_vals_out || d_vals_tmp;

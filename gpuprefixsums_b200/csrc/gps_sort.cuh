@@ -45,17 +45,21 @@ struct SortParams {
 // Order-preserving maps onto uint32 (keys travel transformed between the passes):
 //   1 = int32: flip the sign bit; 2 = float32: flip every bit of negative values, the sign bit
 //   of the others (so -0.0 < +0.0 and NaNs sort by their bit pattern at both ends, as CUB does)
-enum : uint32_t { KEY_U32 = 0, KEY_I32 = 1, KEY_F32 = 2 };
+//   | KEY_DESC: descending order = the complement of the ascending map (still stable)
+enum : uint32_t { KEY_U32 = 0, KEY_I32 = 1, KEY_F32 = 2, KEY_TYPE_MASK = 0xFFu, KEY_DESC = 0x100u };
 __host__ __device__ __forceinline__ uint32_t sort_key_map(uint32_t k, uint32_t type)
 {
-    if (type == KEY_I32) return k ^ 0x80000000u;
-    if (type == KEY_F32) return k ^ ((k >> 31) ? 0xFFFFFFFFu : 0x80000000u);
-    return k;
+    const uint32_t t = type & KEY_TYPE_MASK;
+    if (t == KEY_I32) k ^= 0x80000000u;
+    if (t == KEY_F32) k ^= ((k >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    return (type & KEY_DESC) ? ~k : k;
 }
 __host__ __device__ __forceinline__ uint32_t sort_key_unmap(uint32_t k, uint32_t type)
 {
-    if (type == KEY_I32) return k ^ 0x80000000u;
-    if (type == KEY_F32) return k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+    if (type & KEY_DESC) k = ~k;
+    const uint32_t t = type & KEY_TYPE_MASK;
+    if (t == KEY_I32) k ^= 0x80000000u;
+    if (t == KEY_F32) k ^= ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu);
     return k;
 }
 

@@ -149,6 +149,7 @@ class PrefixSum:
         return out
 
     def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None, *, end_bit: int = 32, key_type: str = "u32",
+             descending: bool = False,
              keys_out: Optional[torch.Tensor] = None, values_out: Optional[torch.Tensor] = None,
              stream: Optional[torch.cuda.Stream] = None):
         """Stable ascending LSD radix sort of 32-bit keys, optionally moving a 32-bit payload;
@@ -156,6 +157,8 @@ class PrefixSum:
         on the low `end_bit` bits), "i32" (signed order) or "f32" (numeric order, float32 keys)."""
         kt = {"u32": 0, "i32": 1, "f32": 2}[key_type]
         want = (torch.float32,) if kt == 2 else (torch.int32, torch.uint32)
+        if descending:
+            kt |= 0x100
         if keys.dtype not in want or not keys.is_cuda or not keys.is_contiguous():
             raise TypeError(f"sort: keys must be a contiguous CUDA tensor of dtype {want}")
         ko = torch.empty_like(keys) if keys_out is None else keys_out

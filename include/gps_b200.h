@@ -159,7 +159,12 @@ uint64_t gps_sort_scratch_bytes(uint64_t n);
  * way in (first pass) and back on the way out (last pass): ascending numeric order, -0.0
  * before +0.0, NaNs at both ends by bit pattern (the convention of cub::DeviceRadixSort);
  * both sort on all 32 bits (end_bit must be 32). */
-enum gps_key_type { GPS_KEY_U32 = 0, GPS_KEY_I32 = 1, GPS_KEY_F32 = 2 };
+enum gps_key_type {
+    GPS_KEY_U32 = 0,
+    GPS_KEY_I32 = 1,
+    GPS_KEY_F32 = 2,
+    GPS_KEY_DESCENDING = 0x100 /* OR-ed to a type: descending order (stable; end_bit must be 32) */
+};
 int gps_sort_keys32(gps_ctx* ctx, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
                     const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,
                     int end_bit, void* stream);

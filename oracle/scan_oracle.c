@@ -191,14 +191,17 @@ uint64_t oracle_check_f64(const double *in, const double *cand, uint64_t n, int 
  * floats flip every bit of negative values) around the same radix passes */
 static uint32_t oracle_key_map(uint32_t k, int type)
 {
-    if (type == 1) return k ^ 0x80000000u;
-    if (type == 2) return k ^ ((k >> 31) ? 0xFFFFFFFFu : 0x80000000u);
-    return k;
+    const int t = type & 0xFF;
+    if (t == 1) k ^= 0x80000000u;
+    if (t == 2) k ^= ((k >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+    return (type & 0x100) ? ~k : k; /* 0x100: descending = complement of the ascending map */
 }
 static uint32_t oracle_key_unmap(uint32_t k, int type)
 {
-    if (type == 1) return k ^ 0x80000000u;
-    if (type == 2) return k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu);
+    const int t = type & 0xFF;
+    if (type & 0x100) k = ~k;
+    if (t == 1) k ^= 0x80000000u;
+    if (t == 2) k ^= ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu);
     return k;
 }
 void oracle_sort_u32(const uint32_t *keys_in, uint32_t *keys_out, uint32_t *keys_tmp, const uint32_t *vals_in,

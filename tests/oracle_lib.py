@@ -129,9 +129,10 @@ class Oracle:
         self.lib.oracle_sort_u32(ptr(keys), ptr(ko), ptr(kt), ptr(vals), ptr(vo), ptr(vt), keys.size, end_bit)
         return ko, vo
 
-    def sort_keys32(self, keys: np.ndarray, vals: np.ndarray | None = None, key_type: str = "u32"):
+    def sort_keys32(self, keys: np.ndarray, vals: np.ndarray | None = None, key_type: str = "u32",
+                    descending: bool = False):
         """keys: int32 / float32 / uint32 array; sorted by numeric order of that type (stable)."""
-        kt = {"u32": 0, "i32": 1, "f32": 2}[key_type]
+        kt = {"u32": 0, "i32": 1, "f32": 2}[key_type] | (0x100 if descending else 0)
         bits = np.ascontiguousarray(keys).view(np.uint32)
         ko, ktmp, kmap = np.empty_like(bits), np.empty_like(bits), np.empty_like(bits)
         ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None

@@ -162,6 +162,12 @@ def test_sort_int32_and_float32_keys(ps, oracle):
         out_finite = ko.cpu().numpy()
         out_finite = out_finite[np.isfinite(out_finite)]
         assert np.array_equal(out_finite, np.sort(finite))  # numeric order (-0.0 == 0.0 for numpy)
+        for kt, k in (("u32", ki.view(np.uint32)), ("i32", ki), ("f32", kf)):  # descending, stable
+            kdev = torch.from_numpy(k.view(np.float32 if kt == "f32" else np.int32)).cuda()
+            ko, vo = ps.sort(kdev, dev(vals), key_type=kt, descending=True)
+            ps.check()
+            wk, wv = oracle.sort_keys32(k, vals, kt, descending=True)
+            assert np.array_equal(ko.cpu().numpy().view(np.uint32), wk.view(np.uint32)) and np.array_equal(host(vo), wv), (n, kt)
     import gpuprefixsums_b200 as gps
     with pytest.raises(gps.GpsError):
         ps.sort(torch.zeros(8, dtype=torch.float32, device="cuda"), key_type="f32", end_bit=16)
