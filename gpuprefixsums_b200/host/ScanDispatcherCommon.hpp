@@ -50,7 +50,7 @@ class ScanDispatcherCommon {
               "gps_malloc");
     }
 
-    ~ScanDispatcherCommon()
+    virtual ~ScanDispatcherCommon()
     {
         if (m_scan) gps_free(m_scan);
         if (m_ctx) gps_destroy(m_ctx);

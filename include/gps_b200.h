@@ -6,7 +6,7 @@
  * surface is four header-defined C++ dispatcher classes that launch kernels with
  * <<< >>> directly.  Every entry point below replaces one of those private launch /
  * harness methods; the C++ classes with the reference's names live in
- * gpuprefixsums_b200/host/*.hpp and call only this ABI.  File:line citations are
+ * gpuprefixsums_b200/host/ (the .hpp files) and call only this ABI.  File:line citations are
  * relative to /root/reference/GPUPrefixSumsCUDA/.
  *
  * Conventions
