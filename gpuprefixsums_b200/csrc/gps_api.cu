@@ -122,7 +122,7 @@ struct DeviceGuard {
 // order.  Launches on one stream do; when a launch arrives on a different stream than the
 // previous one (e.g. gps_scan on the caller's stream, then the host pipeline on its own
 // streams), it is ordered behind the previous launch with an event.
-int enter_stream(gps_ctx* c, cudaStream_t st);
+int enter_stream(gps_ctx* c, cudaStream_t st, bool replay_safe = false);
 
 template <typename T>
 constexpr int dt_index() { return std::is_same<T, float>::value ? 1 : 0; }
@@ -227,8 +227,20 @@ int check_scan_args(gps_ctx* c, int kind, int dtype, const void* in, void* out, 
     return GPS_OK;
 }
 
-int enter_stream(gps_ctx* c, cudaStream_t st)
+int enter_stream(gps_ctx* c, cudaStream_t st, bool replay_safe)
 {
+    // CUDA graph capture: the chained kernels bake the launch epoch and the ticket base into
+    // their parameters, so a REPLAYED graph would see the previous replay's descriptors as valid
+    // and hand out stale tile numbers.  Refuse instead of returning wrong results; Reduce-then-
+    // Scan keeps no such state and may be captured.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
+    if (cap != cudaStreamCaptureStatusNone) {
+        if (!replay_safe)
+            return fail(GPS_ERR_UNSUPPORTED,
+                        "stream is being captured into a CUDA graph: only GPS_ALGO_RTS launches are replay-safe");
+        return GPS_OK;  // ordering inside a capture is the caller's graph structure
+    }
     if (c->has_last_stream && c->last_stream != st) {
         if (!c->ev_order) GPS_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
         // (a caller who destroyed the previous stream has necessarily drained it: ignore the error)
@@ -248,7 +260,7 @@ int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, voi
     int rc = check_scan_args(c, kind, dtype, in, out, n);
     if (rc) return rc;
     DeviceGuard g(c->device);
-    rc = enter_stream(c, st);
+    rc = enter_stream(c, st, algo == GPS_ALGO_RTS);
     if (rc) return rc;
     if (dtype == GPS_U32)
         return kind == GPS_INCLUSIVE ? dispatch_scan_tk<uint32_t, true>(c, algo, in, out, n, cs, st)
@@ -592,7 +604,7 @@ int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, v
     if (!aligned16(d_in) || !aligned16(d_out)) return fail(GPS_ERR_ALIGNMENT, "data pointers must be 16-byte aligned");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = enter_stream(c, st)) return rc;
+    if (int rc = enter_stream(c, st, algo == GPS_ALGO_RTS)) return rc;
     const bool incl = kind == GPS_INCLUSIVE;
     bool& cfg = c->wide_configured[dtype][incl ? 0 : 1][algo == GPS_ALGO_RTS ? 1 : 0];
     switch (dtype) {
@@ -748,7 +760,7 @@ int gps_reduce_publish(gps_ctx* c, int dtype, const void* d_in, uint64_t n,
     if (rc) return rc;
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = enter_stream(c, st);
+    rc = enter_stream(c, st, true);  // no epoch / ticket state: replay-safe
     if (rc) return rc;
     const cudaError_t e =
         dtype == GPS_U32

@@ -84,7 +84,10 @@ int gps_device_info(int device, char* name, int* sm_count, uint64_t* l2_bytes,
 /* Threading / streams: a ctx is thread-compatible, not thread-safe (one host thread at a time).
  * Its scratch is consumed in launch order; launches may go to any stream -- when consecutive
  * launches of one ctx use different streams the library orders them with an event (so they
- * serialise).  For concurrent scans use one ctx per stream. */
+ * serialise).  For concurrent scans use one ctx per stream.
+ * CUDA graphs: GPS_ALGO_RTS scans (gps_scan, gps_scan_wide) and gps_reduce* may be captured and
+ * replayed; the chained kernels and the sort keep a launch epoch and a ticket base on the host
+ * and return GPS_ERR_UNSUPPORTED when their stream is being captured. */
 int gps_create(gps_ctx** ctx, int device, uint64_t max_n);
 void gps_destroy(gps_ctx* ctx);
 /* Synchronises `stream` and reports GPS_ERR_WATCHDOG if any launch since the last

@@ -555,3 +555,32 @@ def test_one_ctx_on_several_streams(gps, oracle):
             assert np.array_equal(to_np_u32(o), np.sort(x))
     assert np.array_equal(h_out.numpy().view(np.uint32), want)
     ps.close()
+
+
+def test_cuda_graph_capture(gps, oracle):
+    """Reduce-then-Scan launches are replay-safe and may be captured into a CUDA graph; the
+    chained kernels keep host-side epoch / ticket state and refuse a capturing stream."""
+    ps = gps.PrefixSum(1 << 22)
+    n = (1 << 21) + 9
+    d_in = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros_like(d_in)
+    ps.scan(d_in, d_out, algo="rts")  # warm-up outside the capture (function attributes etc.)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ps.scan(d_in, d_out, algo="rts", exclusive=True, carry=5)
+        with pytest.raises(gps.GpsError) as e:
+            ps.scan(d_in, d_out, algo="csdl")
+        assert e.value.code == -6
+    for seed in (1, 2, 3):
+        x = oracle.random_u32(n, seed=seed)
+        d_in.copy_(to_dev_u32(x))
+        g.replay()
+        torch.cuda.synchronize()
+        want, _ = oracle.scan_u32(x, exclusive=True, carry=5)
+        assert np.array_equal(to_np_u32(d_out), want), seed
+    out = ps.scan(d_in, algo="csdl")  # the ctx still works normally afterwards
+    ps.check()
+    want, _ = oracle.scan_u32(x)
+    assert np.array_equal(to_np_u32(out), want)
+    ps.close()
