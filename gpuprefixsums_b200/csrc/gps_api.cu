@@ -303,9 +303,9 @@ int launch_wide(gps_ctx* c, int algo, const void* in, void* out, uint64_t n, con
     p.total_out = total_out;
     if ((uint64_t)p.num_tiles * 2 * S::W > s.wdesc_words || p.num_tiles > s.partials_capacity)
         return fail(GPS_ERR_INVALID, "n exceeds ctx capacity");
+    const bool pdl = s.flags & PF_PDL;
     if (p.num_tiles == 0) {  // only the carry travels
-        wide_spine_kernel<E><<<1, 1024, 0, st>>>(p);
-        GPS_CUDA(cudaGetLastError());
+        GPS_CUDA(launch_scan_kernel(wide_spine_kernel<E>, 1, 1024, 0, st, pdl, p));
         return GPS_OK;
     }
     if (algo == GPS_ALGO_RTS) {
@@ -315,9 +315,9 @@ int launch_wide(gps_ctx* c, int algo, const void* in, void* out, uint64_t n, con
                                           (int)cudaSharedmemCarveoutMaxShared));
             configured = true;
         }
-        wide_reduce_kernel<E, GPS_WIDE_NT, GPS_WIDE_V><<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
-        wide_spine_kernel<E><<<1, 1024, 0, st>>>(p);
-        kern<<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+        GPS_CUDA(launch_scan_kernel(wide_reduce_kernel<E, GPS_WIDE_NT, GPS_WIDE_V>, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p));
+        GPS_CUDA(launch_scan_kernel(wide_spine_kernel<E>, 1, 1024, 0, st, pdl, p));
+        GPS_CUDA(launch_scan_kernel(kern, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p));
     } else {
         auto kern = wide_scan_kernel<E, GPS_WIDE_NT, GPS_WIDE_V, INCL, true, GPS_WIDE_REGS>;
         if (!configured) {
@@ -330,7 +330,7 @@ int launch_wide(gps_ctx* c, int algo, const void* in, void* out, uint64_t n, con
             s.wepoch = 1;
         }
         p.epoch = s.wepoch;
-        kern<<<p.num_tiles, GPS_WIDE_NT, 0, st>>>(p);
+        GPS_CUDA(launch_scan_kernel(kern, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p));
         s.counter_base += p.num_tiles;  // one claim per CTA
     }
     GPS_CUDA(cudaGetLastError());
@@ -358,7 +358,7 @@ constexpr uint32_t kSortPairsTile = (uint32_t)GPS_SORT_PAIRS_NT * GPS_SORT_PAIRS
 constexpr uint32_t kSortMinTile = kSortTile < kSortPairsTile ? kSortTile : kSortPairsTile;
 
 template <bool PAIRS, bool XFORM>
-cudaError_t launch_sort_pass(const SortParams& p, bool& configured, cudaStream_t st)
+cudaError_t launch_sort_pass(const SortParams& p, bool& configured, bool pdl, cudaStream_t st)
 {
     constexpr int NT = PAIRS ? GPS_SORT_PAIRS_NT : GPS_SORT_NT, KPT = PAIRS ? GPS_SORT_PAIRS_KPT : GPS_SORT_KPT;
     constexpr size_t smem = ((size_t)(PAIRS ? 2 : 1) * NT * KPT + (size_t)(NT / 32) * kRadix) * sizeof(uint32_t);
@@ -370,8 +370,7 @@ cudaError_t launch_sort_pass(const SortParams& p, bool& configured, cudaStream_t
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    kern<<<p.num_tiles, NT, smem, st>>>(p);
-    return cudaSuccess;
+    return launch_scan_kernel(kern, p.num_tiles, NT, smem, st, pdl, p);
 }
 }  // namespace
 
@@ -460,6 +459,7 @@ int gps_create_with_scratch(gps_ctx** out, int device, uint64_t max_n, void* d_s
     c->device = device;
     c->max_n = max_n;
     c->s.sm_count = prop.multiProcessorCount;
+    c->s.flags |= PF_PDL;  // programmatic dependent launch by default (option "pdl")
     c->owns_scratch = d_scratch == nullptr;
     cudaError_t e = cudaSuccess;
     if (c->owns_scratch) e = cudaMalloc(&c->scratch_base, (size_t)L.total);
@@ -533,6 +533,10 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     } else if (!strcmp(key, "fallback_variant")) {
         if (value < 0 || value > 3) return fail(GPS_ERR_INVALID, "fallback_variant must be 0..3");
         c->fallback_variant = (int)value;
+    } else if (!strcmp(key, "pdl")) {
+        // programmatic dependent launch for the CSDL kernels (register / smem / blocked tiles)
+        if (value != 0 && value != 1) return fail(GPS_ERR_INVALID, "pdl must be 0 or 1");
+        c->s.flags = (c->s.flags & ~PF_PDL) | (value ? PF_PDL : 0u);
     } else if (!strcmp(key, "rts_variant")) {
         if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "rts_variant must be 0..2");
         c->rts_variant = (int)value;
@@ -718,10 +722,11 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         p.xform_in = pass == 0 ? (uint32_t)key_type : 0u;
         p.xform_out = pass == passes - 1 ? (uint32_t)key_type : 0u;
         const bool xf = p.xform_in || p.xform_out;
-        GPS_CUDA(pairs ? (xf ? launch_sort_pass<true, true>(p, c->sort_configured[3], st)
-                             : launch_sort_pass<true, false>(p, c->sort_configured[1], st))
-                       : (xf ? launch_sort_pass<false, true>(p, c->sort_configured[2], st)
-                             : launch_sort_pass<false, false>(p, c->sort_configured[0], st)));
+        const bool pdl = c->s.flags & PF_PDL;
+        GPS_CUDA(pairs ? (xf ? launch_sort_pass<true, true>(p, c->sort_configured[3], pdl, st)
+                             : launch_sort_pass<true, false>(p, c->sort_configured[1], pdl, st))
+                       : (xf ? launch_sort_pass<false, true>(p, c->sort_configured[2], pdl, st)
+                             : launch_sort_pass<false, false>(p, c->sort_configured[0], pdl, st)));
         c->s.counter_base += tiles;  // one claim per CTA
         src_k = p.keys_out;
         src_v = p.vals_out;

@@ -82,6 +82,7 @@ enum : uint32_t {
     PF_POLL_ACQUIRE = 256u,      // poll with ld.acquire.gpu (else ld.relaxed.gpu)
     PF_LOOKBACK_WAIT_ALL = 512u, // experiment: consume a window only when all 32 are ready
     PF_LOOKBACK_SINGLE = 1024u,  // one-thread look-back (reference LookbackSingle, CSDL.cuh:28-47)
+    PF_PDL = 4096u,              // host: launch with programmatic stream serialization (see pdl_entry)
 };
 
 enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
@@ -282,6 +283,21 @@ __device__ __forceinline__ void bulk_wait()
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may have its CTAs made resident while the previous kernel of the stream is still
+// draining.  Every scan kernel starts with pdl_entry(): it lets ITS successor do the same as
+// soon as all of this grid's CTAs have started, then waits until the predecessor grid has
+// completed and its memory is visible -- so nothing a scan reads or claims (input, ticket
+// counter, descriptors) is touched early; what overlaps is the launch latency and the CTA
+// ramp-up.  Both instructions are no-ops for a normally launched kernel.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_entry()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
+    pdl_entry();
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);

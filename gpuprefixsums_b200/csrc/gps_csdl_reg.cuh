@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 24 + 4 * V)) csdl_reg_
     __shared__ T s_warp[NW];
     __shared__ T s_prefix;
     __shared__ uint32_t s_tile;
+    pdl_entry();
 
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
@@ -111,6 +112,7 @@ template <typename T, int NT, int V, bool INCLUSIVE>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
     csdl_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
 {
+    pdl_entry();
     using Tile = RegTile<T, NT, V>;
     constexpr int NW = Tile::NW;
     __shared__ T s_warp[NW];

@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
+    pdl_entry();
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -191,6 +192,7 @@ template <typename T, int NT, int V, bool INCLUSIVE, int G = 4, int REGS = 40>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     csdl_smem_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
 {
+    pdl_entry();
     constexpr int NW = NT / 32;
     constexpr uint32_t TILE_VEC = NT * V;
     constexpr uint32_t TILE_KEYS = TILE_VEC * 4;
@@ -422,6 +424,7 @@ template <typename T, int NT, int V, bool INCLUSIVE, int REGS = 40>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     csdl_blocked_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
 {
+    pdl_entry();
     using Tile = BlockedTile<T, NT, V>;
     constexpr int NW = Tile::NW;
     constexpr uint32_t TILE_VEC = Tile::TILE_VEC;

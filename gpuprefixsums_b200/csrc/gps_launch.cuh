@@ -17,6 +17,29 @@ namespace gps {
 
 inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
+// <<< >>> or, with `pdl`, cudaLaunchKernelEx with the programmatic-stream-serialization
+// attribute (the kernel must begin with pdl_entry(), gps_common.cuh)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_scan_kernel(void (*kern)(KArgs...), uint32_t grid, uint32_t block, size_t smem, cudaStream_t st,
+                               bool pdl, const Args&... args)
+{
+    if (!pdl) {
+        kern<<<grid, block, smem, st>>>(args...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // device scratch of one context + the host-side counters that replace memsets
 struct Scratch {
     uint64_t* desc = nullptr;     // tile descriptors (zero-initialised once)
@@ -85,6 +108,7 @@ inline ScanParams make_scan_params(Scratch& s, const void* in, void* out, uint64
 template <typename T>
 __global__ void carry_only_kernel(const __grid_constant__ ScanParams p)
 {
+    pdl_entry();
     const T c = acquire_carry<T>(p, lane_id());
     if (threadIdx.x == 0) write_total<T>(p, c);
 }
@@ -93,8 +117,7 @@ template <typename T>
 cudaError_t launch_carry_only(Scratch& s, const CarrySpec& cs, cudaStream_t st)
 {
     ScanParams p = make_scan_params(s, nullptr, nullptr, 0, 4096, cs, st);
-    carry_only_kernel<T><<<1, 32, 0, st>>>(p);
-    return cudaGetLastError();
+    return launch_scan_kernel(carry_only_kernel<T>, 1, 32, 0, st, s.flags & PF_PDL, p);
 }
 
 // ---- CSDL register path --------------------------------------------------------------
@@ -104,9 +127,10 @@ cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, c
 {
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
-    csdl_reg_kernel<T, NT, V, INCL, WIN, PROF><<<p.num_tiles, NT, 0, st>>>(p);
+    const cudaError_t e =
+        launch_scan_kernel(csdl_reg_kernel<T, NT, V, INCL, WIN, PROF>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
     if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
-    return cudaGetLastError();
+    return e;
 }
 
 // ---- CSDL shared-memory-resident tile (one TMA bulk load per CTA) ---------------------
@@ -123,9 +147,9 @@ cudaError_t launch_csdl_smem(Scratch& s, const void* in, void* out, uint64_t n, 
         configured = true;
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
-    kern<<<p.num_tiles, NT, 0, st>>>(p);
+    const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
     if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
-    return cudaGetLastError();
+    return e;
 }
 
 // ---- CSDL blocked shared-memory tile (TMA bulk load + per-warp TMA bulk store) --------
@@ -141,9 +165,9 @@ cudaError_t launch_csdl_blocked(Scratch& s, const void* in, void* out, uint64_t 
         configured = true;
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
-    kern<<<p.num_tiles, NT, 0, st>>>(p);
+    const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
     if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
-    return cudaGetLastError();
+    return e;
 }
 
 // ---- CSDL TMA path -------------------------------------------------------------------
@@ -182,9 +206,9 @@ cudaError_t launch_csdl_fallback(Scratch& s, const void* in, void* out, uint64_t
 {
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
-    csdl_fallback_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p, f);
+    const cudaError_t e = launch_scan_kernel(csdl_fallback_kernel<T, NT, V, INCL>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
     s.counter_base += p.num_tiles;
-    return cudaGetLastError();
+    return e;
 }
 
 // the same on the shared-memory-resident tile (gps_csdl_smem.cuh)
@@ -200,9 +224,9 @@ cudaError_t launch_csdl_smem_fallback(Scratch& s, const void* in, void* out, uin
         configured = true;
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
-    kern<<<p.num_tiles, NT, 0, st>>>(p, f);
+    const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
     s.counter_base += p.num_tiles;
-    return cudaGetLastError();
+    return e;
 }
 
 template <typename T, int NT, int V, bool INCL>
@@ -217,9 +241,9 @@ cudaError_t launch_csdl_blocked_fallback(Scratch& s, const void* in, void* out, 
         configured = true;
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
-    kern<<<p.num_tiles, NT, 0, st>>>(p, f);
+    const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
     s.counter_base += p.num_tiles;
-    return cudaGetLastError();
+    return e;
 }
 
 // ---- RTS -----------------------------------------------------------------------------
@@ -251,10 +275,11 @@ cudaError_t launch_rts(Scratch& s, const void* in, void* out, uint64_t n, const 
     p.slot_tag = cs.tag;
     p.total_out = cs.total_out;
     p.publish = cs.publish;
-    rts_reduce_kernel<T, NT, V><<<p.num_tiles, NT, 0, st>>>(p);
-    rts_spine_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
-    rts_propagate_kernel<T, NT, V, INCL><<<p.num_tiles, NT, 0, st>>>(p);
-    return cudaGetLastError();
+    const bool pdl = s.flags & PF_PDL;
+    e = launch_scan_kernel(rts_reduce_kernel<T, NT, V>, p.num_tiles, NT, 0, st, pdl, p);
+    if (e == cudaSuccess) e = launch_scan_kernel(rts_spine_kernel<T>, 1, kSpineThreads, 0, st, pdl, p);
+    if (e == cudaSuccess) e = launch_scan_kernel(rts_propagate_kernel<T, NT, V, INCL>, p.num_tiles, NT, 0, st, pdl, p);
+    return e;
 }
 
 // RTS with the propagate kernel on the blocked shared-memory tile
@@ -281,10 +306,11 @@ cudaError_t launch_rts_blocked(Scratch& s, const void* in, void* out, uint64_t n
     p.slot_tag = cs.tag;
     p.total_out = cs.total_out;
     p.publish = cs.publish;
-    rts_reduce_kernel<T, NT, V><<<p.num_tiles, NT, 0, st>>>(p);
-    rts_spine_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
-    kern<<<p.num_tiles, NT, 0, st>>>(p);
-    return cudaGetLastError();
+    const bool pdl = s.flags & PF_PDL;
+    e = launch_scan_kernel(rts_reduce_kernel<T, NT, V>, p.num_tiles, NT, 0, st, pdl, p);
+    if (e == cudaSuccess) e = launch_scan_kernel(rts_spine_kernel<T>, 1, kSpineThreads, 0, st, pdl, p);
+    if (e == cudaSuccess) e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, pdl, p);
+    return e;
 }
 
 template <typename T, int NT, int V>
@@ -297,9 +323,10 @@ cudaError_t launch_reduce(Scratch& s, const void* in, uint64_t n, void* total_ou
     p.in = in;
     p.total_out = total_out;
     p.publish = pl;
-    if (p.num_tiles) rts_reduce_kernel<T, NT, V><<<p.num_tiles, NT, 0, st>>>(p);
-    rts_fold_kernel<T><<<1, kSpineThreads, 0, st>>>(p);
-    return cudaGetLastError();
+    const bool pdl = s.flags & PF_PDL;
+    if (p.num_tiles) e = launch_scan_kernel(rts_reduce_kernel<T, NT, V>, p.num_tiles, NT, 0, st, pdl, p);
+    if (e == cudaSuccess) e = launch_scan_kernel(rts_fold_kernel<T>, 1, kSpineThreads, 0, st, pdl, p);
+    return e;
 }
 
 }  // namespace gps

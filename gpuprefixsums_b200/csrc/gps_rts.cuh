@@ -52,6 +52,7 @@ template <typename T, int NT, int V>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 16 + 4 * V))
     rts_reduce_kernel(const __grid_constant__ RtsParams p)
 {
+    pdl_entry();
     using Tile = RegTile<T, NT, V>;
     __shared__ T s_red[NT / 32];
     const uint32_t lane = lane_id();
@@ -92,6 +93,7 @@ constexpr int kSpineItems = 8;
 template <typename T>
 __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_constant__ RtsParams p)
 {
+    pdl_entry();
     constexpr int NW = kSpineThreads / 32;
     constexpr uint32_t CHUNK = kSpineThreads * kSpineItems;
     __shared__ T s_warp[2][NW];
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_c
 template <typename T>
 __global__ void __launch_bounds__(kSpineThreads) rts_fold_kernel(const __grid_constant__ RtsParams p)
 {
+    pdl_entry();
     __shared__ T s_red[kSpineThreads / 32];
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
@@ -167,6 +170,7 @@ template <typename T, int NT, int V, bool INCLUSIVE>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 24 + 4 * V))
     rts_propagate_kernel(const __grid_constant__ RtsParams p)
 {
+    pdl_entry();
     using Tile = RegTile<T, NT, V>;
     constexpr int NW = Tile::NW;
     __shared__ T s_warp[NW];
@@ -200,6 +204,7 @@ template <typename T, int NT, int V, bool INCLUSIVE, int REGS = 40>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     rts_propagate_blocked_kernel(const __grid_constant__ RtsParams p)
 {
+    pdl_entry();
     using Tile = BlockedTile<T, NT, V>;
     constexpr int NW = Tile::NW;
     __shared__ __align__(128) uint4 s_data[Tile::TILE_VEC];

@@ -203,6 +203,7 @@ __device__ __forceinline__ uint32_t sort_peers(uint32_t d)
 template <int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8, bool XFORM = false>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kernel(const __grid_constant__ SortParams p)
 {
+    pdl_entry();
     static_assert(NT >= kRadix && NT % 32 == 0, "one thread per digit for the look-back");
     constexpr int NW = NT / 32;
     constexpr uint32_t TILE = NT * KPT;

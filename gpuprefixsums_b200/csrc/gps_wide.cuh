@@ -267,6 +267,7 @@ template <typename E, int NT, int V, bool INCLUSIVE, bool CHAINED, int REGS = 40
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     wide_scan_kernel(const __grid_constant__ WideParams<E> p)
 {
+    pdl_entry();
     using S = WideShape<E, NT, V>;
     using Vec = typename S::Vec;
     constexpr int W = S::W, KPV = S::KPV, NW = S::NW;
@@ -402,6 +403,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
 template <typename E, int NT, int V>
 __global__ void __launch_bounds__(NT) wide_reduce_kernel(const __grid_constant__ WideParams<E> p)
 {
+    pdl_entry();
     using S = WideShape<E, NT, V>;
     using Vec = typename S::Vec;
     constexpr int KPV = S::KPV;
@@ -446,6 +448,7 @@ __global__ void __launch_bounds__(NT) wide_reduce_kernel(const __grid_constant__
 template <typename E>
 __global__ void __launch_bounds__(1024) wide_spine_kernel(const __grid_constant__ WideParams<E> p)
 {
+    pdl_entry();
     constexpr int NW = 32, ITEMS = 4;
     constexpr uint32_t CHUNK = 1024 * ITEMS;
     __shared__ __align__(16) E s_warp[2][NW];

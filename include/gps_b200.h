@@ -107,6 +107,9 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   2 = st.relaxed + ld.relaxed
  *   "lookback"      0 = warp-parallel (default, LookbackWarp), 1 = single thread
  *                   (LookbackSingle, ChainedScanDecoupledLookback.cuh:28-47)
+ *   "pdl"           1 = launch the scan kernels with programmatic stream serialization (default:
+ *                   their CTAs become resident while the stream's previous kernel drains and
+ *                   wait for it to complete before touching memory), 0 = plain launches
  *   "poll_sleep_ns" nanosleep between unsuccessful descriptor polls (default 0)
  *   "host_chunk_keys" chunk size of gps_scan_host (default 2^24; before first use) */
 int gps_set_option(gps_ctx* ctx, const char* key, int64_t value);

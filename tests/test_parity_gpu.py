@@ -584,3 +584,23 @@ def test_cuda_graph_capture(gps, oracle):
     want, _ = oracle.scan_u32(x)
     assert np.array_equal(to_np_u32(out), want)
     ps.close()
+
+
+def test_programmatic_dependent_launch(gps, oracle):
+    """Option "pdl": the CSDL kernels launched with programmatic stream serialization (their
+    CTAs become resident while the previous kernel drains and wait for it at pdl_entry) --
+    back-to-back dependent scans in place must stay bit-exact."""
+    ps = gps.PrefixSum(1 << 23)
+    ps.set_option("pdl", 1)
+    for algo in ["csdl_reg", "csdl_smem", "csdl_blocked", "csdl"]:
+        for n in [1000, 100_003, (1 << 22) + 77]:
+            x = oracle.random_u32(n, seed=n)
+            buf = to_dev_u32(x)
+            for _ in range(4):  # each scan consumes the previous one's output
+                ps.scan(buf, buf, algo=algo)
+            ps.check()
+            want = x
+            for _ in range(4):
+                want, _ = oracle.scan_u32(want)
+            assert np.array_equal(to_np_u32(buf), want), (algo, n)
+    ps.close()

@@ -584,7 +584,7 @@ int main(int argc, char** argv)
 {
     Env env;
     const char* filter = nullptr;
-    bool sweep = false;
+    bool sweep = false, pdl = false;
     int max_log2n = 30;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--log2n") && i + 1 < argc) env.n = 1ull << atoi(argv[++i]);
@@ -596,6 +596,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--sweep")) sweep = true;
         else if (!strcmp(argv[i], "--max-log2n") && i + 1 < argc) max_log2n = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--exclusive")) env.exclusive = true;
+        else if (!strcmp(argv[i], "--pdl")) pdl = true;
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
             return 2;
@@ -610,6 +611,7 @@ int main(int argc, char** argv)
     CK(cudaMalloc(&env.ref, bytes));
     CK(cudaMalloc(&env.work, bytes));
     env.s.sm_count = prop.multiProcessorCount;
+    if (pdl) env.s.flags |= PF_PDL;
     env.s.desc_tiles = (uint32_t)div_up(env.n, 2048) + 1;
     CK(cudaMalloc(&env.s.desc, (size_t)env.s.desc_tiles * 8));
     CK(cudaMemset(env.s.desc, 0, (size_t)env.s.desc_tiles * 8));
