@@ -47,7 +47,8 @@ enum gps_status {
     GPS_ERR_WATCHDOG = -4,  /* a look-back spin exceeded its poll budget (reported by */
                             /* gps_check; the kernel bails out instead of hanging)   */
     GPS_ERR_MISMATCH = -5,  /* validation helper found wrong results                 */
-    GPS_ERR_UNSUPPORTED = -6
+    GPS_ERR_UNSUPPORTED = -6 /* not an sm_100 device; a chained kernel or the sort on a stream that */
+                             /* is being captured into a CUDA graph (use GPS_ALGO_RTS there)       */
 };
 
 enum gps_algo {
