@@ -87,6 +87,11 @@ struct gps_ctx {
     void* chain_total = nullptr;
     cudaEvent_t ev_total = nullptr;
     bool ev_total_pending = false;
+    // shadow scratch for launches that are being captured into a CUDA graph (see CaptureScope)
+    uint64_t* g_desc = nullptr;
+    uint64_t* g_wdesc = nullptr;
+    uint64_t* g_sort_desc = nullptr;
+    uint32_t* g_counter = nullptr;
     cudaStream_t last_stream = nullptr;  // stream of the previous launch that used the scratch
     bool has_last_stream = false;
     cudaEvent_t ev_order = nullptr;
@@ -122,7 +127,7 @@ struct DeviceGuard {
 // order.  Launches on one stream do; when a launch arrives on a different stream than the
 // previous one (e.g. gps_scan on the caller's stream, then the host pipeline on its own
 // streams), it is ordered behind the previous launch with an event.
-int enter_stream(gps_ctx* c, cudaStream_t st, bool replay_safe = false);
+int enter_stream(gps_ctx* c, cudaStream_t st, bool* capturing = nullptr);
 
 // The sharded path (reduce + publish, scan with carry slots) measures 1.5 % SLOWER with
 // programmatic dependent launch (2 GPUs, 2^28 keys each: 0.4825 vs 0.4752 ms per step), so its
@@ -237,20 +242,12 @@ int check_scan_args(gps_ctx* c, int kind, int dtype, const void* in, void* out, 
     return GPS_OK;
 }
 
-int enter_stream(gps_ctx* c, cudaStream_t st, bool replay_safe)
+int enter_stream(gps_ctx* c, cudaStream_t st, bool* capturing)
 {
-    // CUDA graph capture: the chained kernels bake the launch epoch and the ticket base into
-    // their parameters, so a REPLAYED graph would see the previous replay's descriptors as valid
-    // and hand out stale tile numbers.  Refuse instead of returning wrong results; Reduce-then-
-    // Scan keeps no such state and may be captured.
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) cudaGetLastError();
-    if (cap != cudaStreamCaptureStatusNone) {
-        if (!replay_safe)
-            return fail(GPS_ERR_UNSUPPORTED,
-                        "stream is being captured into a CUDA graph: only GPS_ALGO_RTS launches are replay-safe");
-        return GPS_OK;  // ordering inside a capture is the caller's graph structure
-    }
+    if (capturing) *capturing = cap != cudaStreamCaptureStatusNone;
+    if (cap != cudaStreamCaptureStatusNone) return GPS_OK;  // ordering inside a capture is the caller's graph structure
     if (c->has_last_stream && c->last_stream != st) {
         if (!c->ev_order) GPS_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
         // (a caller who destroyed the previous stream has necessarily drained it: ignore the error)
@@ -264,14 +261,68 @@ int enter_stream(gps_ctx* c, cudaStream_t st, bool replay_safe)
     return GPS_OK;
 }
 
+// CUDA graph capture.  The chained kernels (and the sort) normally take a launch epoch and a
+// ticket base from host-side counters baked into their parameters -- a REPLAYED graph would see
+// the previous replay's descriptors as valid and hand out stale tile numbers.  A captured launch
+// therefore runs on a SHADOW scratch (own descriptor arrays and ticket counter, allocated with
+// the ctx) which the captured sequence itself clears first, with constant epochs and a zero
+// ticket base: every replay starts from the same state.  (The clear is the reference's own
+// per-launch memset, ChainedScanDecoupledLookbackDispatcher.cuh:172-175 -- paid only here.)
+// The host-side counters of the ctx are untouched, so plain launches continue unaffected.
+struct CaptureScope {
+    gps_ctx* c = nullptr;
+    Scratch saved;
+    uint64_t* saved_sort_desc = nullptr;
+    uint32_t saved_sort_epoch = 0;
+    bool active = false;
+    int begin(gps_ctx* ctx, cudaStream_t st, uint64_t desc_words, uint64_t wdesc_words, uint64_t sort_words)
+    {
+        c = ctx;
+        saved = c->s;
+        saved_sort_desc = c->sort_desc;
+        saved_sort_epoch = c->sort_epoch;
+        active = true;
+        if (sort_words && !c->g_sort_desc)
+            return fail(GPS_ERR_UNSUPPORTED, "capture needs one gps_sort call of at least this size outside the capture first");
+        desc_words = std::min<uint64_t>(desc_words, c->s.desc_tiles);
+        wdesc_words = std::min<uint64_t>(wdesc_words, c->s.wdesc_words);
+        GPS_CUDA(cudaMemsetAsync(c->g_counter, 0, 64, st));
+        if (desc_words) GPS_CUDA(cudaMemsetAsync(c->g_desc, 0, desc_words * sizeof(uint64_t), st));
+        if (wdesc_words) GPS_CUDA(cudaMemsetAsync(c->g_wdesc, 0, wdesc_words * sizeof(uint64_t), st));
+        if (sort_words) GPS_CUDA(cudaMemsetAsync(c->g_sort_desc, 0, sort_words * sizeof(uint64_t), st));
+        c->s.desc = c->g_desc;
+        c->s.wdesc = c->g_wdesc;
+        c->s.counter = c->g_counter;
+        c->s.counter_base = 0;
+        c->s.epoch = 0;   // next_epoch() -> 1, 2, ... in capture order
+        c->s.wepoch = 0;
+        c->sort_desc = c->g_sort_desc;
+        c->sort_epoch = 0;
+        return GPS_OK;
+    }
+    ~CaptureScope()
+    {
+        if (!active) return;
+        c->s = saved;
+        c->sort_desc = saved_sort_desc;
+        c->sort_epoch = saved_sort_epoch;
+    }
+};
+
 int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, void* out, uint64_t n,
                   const CarrySpec& cs, cudaStream_t st)
 {
     int rc = check_scan_args(c, kind, dtype, in, out, n);
     if (rc) return rc;
     DeviceGuard g(c->device);
-    rc = enter_stream(c, st, algo == GPS_ALGO_RTS);
+    bool capturing = false;
+    rc = enter_stream(c, st, &capturing);
     if (rc) return rc;
+    CaptureScope cap;
+    if (capturing && algo != GPS_ALGO_RTS) {
+        rc = cap.begin(c, st, div_up(n, 2048) + 1, 0, 0);
+        if (rc) return rc;
+    }
     if (dtype == GPS_U32)
         return kind == GPS_INCLUSIVE ? dispatch_scan_tk<uint32_t, true>(c, algo, in, out, n, cs, st)
                                      : dispatch_scan_tk<uint32_t, false>(c, algo, in, out, n, cs, st);
@@ -424,7 +475,7 @@ namespace {
 // one device allocation (the ctx's own, or the caller's), carved into 256-byte aligned segments
 struct ScratchLayout {
     uint64_t desc_tiles, partials_capacity, wdesc_words;
-    uint64_t off_desc, off_partials, off_wdesc, off_counter, total;
+    uint64_t off_desc, off_partials, off_wdesc, off_counter, off_gdesc, off_gwdesc, off_gcounter, total;
 };
 inline uint64_t align256(uint64_t v) { return (v + 255u) & ~(uint64_t)255u; }
 ScratchLayout scratch_layout(uint64_t max_n)
@@ -437,7 +488,11 @@ ScratchLayout scratch_layout(uint64_t max_n)
     L.off_partials = align256(L.off_desc + L.desc_tiles * sizeof(uint64_t));
     L.off_wdesc = align256(L.off_partials + L.partials_capacity * 16);  // up to 16-byte elements
     L.off_counter = align256(L.off_wdesc + L.wdesc_words * sizeof(uint64_t));
-    L.total = L.off_counter + 256;
+    // shadow descriptors / ticket counter for launches captured into a CUDA graph (CaptureScope)
+    L.off_gdesc = L.off_counter + 256;
+    L.off_gwdesc = align256(L.off_gdesc + L.desc_tiles * sizeof(uint64_t));
+    L.off_gcounter = align256(L.off_gwdesc + L.wdesc_words * sizeof(uint64_t));
+    L.total = L.off_gcounter + 256;
     return L;
 }
 }  // namespace
@@ -489,6 +544,9 @@ int gps_create_with_scratch(gps_ctx** out, int device, uint64_t max_n, void* d_s
     c->s.wdesc_words = L.wdesc_words;
     c->s.counter = reinterpret_cast<uint32_t*>(base + L.off_counter);
     c->s.status = c->s.counter + 1;
+    c->g_desc = reinterpret_cast<uint64_t*>(base + L.off_gdesc);
+    c->g_wdesc = reinterpret_cast<uint64_t*>(base + L.off_gwdesc);
+    c->g_counter = reinterpret_cast<uint32_t*>(base + L.off_gcounter);
     *out = c;
     return GPS_OK;
 }
@@ -510,6 +568,7 @@ void gps_destroy(gps_ctx* c)
     }
     if (c->chain_slots) cudaFree(c->chain_slots);
     if (c->sort_desc) cudaFree(c->sort_desc);
+    if (c->g_sort_desc) cudaFree(c->g_sort_desc);
     if (c->sort_hist) cudaFree(c->sort_hist);
     if (c->chain_total) cudaFree(c->chain_total);
     if (c->ev_total) cudaEventDestroy(c->ev_total);
@@ -618,7 +677,11 @@ int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, v
     if (!aligned16(d_in) || !aligned16(d_out)) return fail(GPS_ERR_ALIGNMENT, "data pointers must be 16-byte aligned");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = enter_stream(c, st, algo == GPS_ALGO_RTS)) return rc;
+    bool capturing = false;
+    if (int rc = enter_stream(c, st, &capturing)) return rc;
+    CaptureScope cap;
+    if (capturing && algo != GPS_ALGO_RTS)
+        if (int rc = cap.begin(c, st, 0, (div_up(n * es, kWideTileBytes) + 1) * 8, 0)) return rc;
     const bool incl = kind == GPS_INCLUSIVE;
     bool& cfg = c->wide_configured[dtype][incl ? 0 : 1][algo == GPS_ALGO_RTS ? 1 : 0];
     switch (dtype) {
@@ -679,8 +742,14 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         return fail(GPS_ERR_INVALID, "in == out needs an even number of digit passes (end_bit 9..16 or 25..32)");
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = enter_stream(c, st)) return rc;
+    bool capturing = false;
+    if (int rc = enter_stream(c, st, &capturing)) return rc;
     const uint32_t tiles = (uint32_t)div_up(n, pairs ? kSortPairsTile : kSortTile);
+    if (capturing && tiles > c->sort_desc_tiles)
+        return fail(GPS_ERR_UNSUPPORTED, "capture needs one gps_sort call of at least this size outside the capture first");
+    CaptureScope cap;
+    if (capturing)
+        if (int rc = cap.begin(c, st, 0, 0, (uint64_t)tiles * kRadix)) return rc;
     if (tiles > c->sort_desc_tiles) {  // grow (synchronous, rare)
         GPS_CUDA(cudaDeviceSynchronize());
         if (c->sort_desc) cudaFree(c->sort_desc);
@@ -688,6 +757,9 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         c->sort_desc_tiles = 0;
         GPS_CUDA(cudaMalloc(&c->sort_desc, (size_t)tiles * kRadix * sizeof(uint64_t)));
         GPS_CUDA(cudaMemset(c->sort_desc, 0, (size_t)tiles * kRadix * sizeof(uint64_t)));
+        if (c->g_sort_desc) cudaFree(c->g_sort_desc);  // shadow for captured sorts (CaptureScope)
+        c->g_sort_desc = nullptr;
+        GPS_CUDA(cudaMalloc(&c->g_sort_desc, (size_t)tiles * kRadix * sizeof(uint64_t)));
         c->sort_desc_tiles = tiles;
         c->sort_epoch = 0;
     }
@@ -777,7 +849,7 @@ int gps_reduce_publish(gps_ctx* c, int dtype, const void* d_in, uint64_t n,
     if (rc) return rc;
     DeviceGuard g(c->device);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = enter_stream(c, st, true);  // no epoch / ticket state: replay-safe
+    rc = enter_stream(c, st);  // no epoch / ticket state: replay-safe as it is
     if (rc) return rc;
     NoPdlScope plain(c->s.flags);
     const cudaError_t e =
@@ -808,8 +880,14 @@ int gps_scan_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void* d_in
     CarrySpec cs;
     FallbackParams f{stall_mask, max_spin, d_stats};
     cudaStream_t st = (cudaStream_t)stream;
-    rc = enter_stream(c, st);
+    bool capturing = false;
+    rc = enter_stream(c, st, &capturing);
     if (rc) return rc;
+    CaptureScope cap;
+    if (capturing) {
+        rc = cap.begin(c, st, div_up(n, 2048) + 1, 0, 0);
+        if (rc) return rc;
+    }
     cudaError_t e;
     if (dtype == GPS_U32)
         e = kind == GPS_INCLUSIVE

@@ -47,8 +47,7 @@ enum gps_status {
     GPS_ERR_WATCHDOG = -4,  /* a look-back spin exceeded its poll budget (reported by */
                             /* gps_check; the kernel bails out instead of hanging)   */
     GPS_ERR_MISMATCH = -5,  /* validation helper found wrong results                 */
-    GPS_ERR_UNSUPPORTED = -6 /* not an sm_100 device; a chained kernel or the sort on a stream that */
-                             /* is being captured into a CUDA graph (use GPS_ALGO_RTS there)       */
+    GPS_ERR_UNSUPPORTED = -6 /* not an sm_100 device; a captured sort larger than any sort run before */
 };
 
 enum gps_algo {
@@ -86,9 +85,13 @@ int gps_device_info(int device, char* name, int* sm_count, uint64_t* l2_bytes,
  * Its scratch is consumed in launch order; launches may go to any stream -- when consecutive
  * launches of one ctx use different streams the library orders them with an event (so they
  * serialise).  For concurrent scans use one ctx per stream.
- * CUDA graphs: GPS_ALGO_RTS scans (gps_scan, gps_scan_wide) and gps_reduce* may be captured and
- * replayed; the chained kernels and the sort keep a launch epoch and a ticket base on the host
- * and return GPS_ERR_UNSUPPORTED when their stream is being captured. */
+ * CUDA graphs: gps_scan, gps_scan_wide, gps_scan_emulated_deadlock, gps_sort_* and gps_reduce*
+ * may be captured and replayed.  Reduce-then-Scan keeps no launch state; for the chained kernels
+ * and the sort a captured launch runs on a shadow scratch of the ctx that the captured sequence
+ * clears first (constant epochs, zero ticket base), so every replay starts from the same state
+ * and plain launches of the ctx are unaffected.  Make one call of each kind outside the capture
+ * first (function attributes and the sort's lazily sized scratch cannot be set up while
+ * capturing); captured launches of ONE ctx must be ordered with respect to each other. */
 int gps_create(gps_ctx** ctx, int device, uint64_t max_n);
 void gps_destroy(gps_ctx* ctx);
 /* Synchronises `stream` and reports GPS_ERR_WATCHDOG if any launch since the last
