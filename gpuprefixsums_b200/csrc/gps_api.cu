@@ -92,6 +92,10 @@ struct gps_ctx {
     uint64_t* g_wdesc = nullptr;
     uint64_t* g_sort_desc = nullptr;
     uint32_t* g_counter = nullptr;
+    unsigned long long cap_id = 0;  // capture sequence the cap_* counters belong to
+    bool cap_valid = false;
+    int cap_cleared = 0;            // CaptureScope::Kind bits whose shadow array this capture already clears
+    uint32_t cap_epoch = 0, cap_wepoch = 0, cap_sort_epoch = 0, cap_counter_base = 0;
     cudaStream_t last_stream = nullptr;  // stream of the previous launch that used the scratch
     bool has_last_stream = false;
     cudaEvent_t ev_order = nullptr;
@@ -265,44 +269,64 @@ int enter_stream(gps_ctx* c, cudaStream_t st, bool* capturing)
 // ticket base from host-side counters baked into their parameters -- a REPLAYED graph would see
 // the previous replay's descriptors as valid and hand out stale tile numbers.  A captured launch
 // therefore runs on a SHADOW scratch (own descriptor arrays and ticket counter, allocated with
-// the ctx) which the captured sequence itself clears first, with constant epochs and a zero
-// ticket base: every replay starts from the same state.  (The clear is the reference's own
-// per-launch memset, ChainedScanDecoupledLookbackDispatcher.cuh:172-175 -- paid only here.)
-// The host-side counters of the ctx are untouched, so plain launches continue unaffected.
+// the ctx).  The FIRST captured launch of a capture sequence (per kind: scan / wide / sort)
+// records a clear of that shadow array (and of the ticket counter) into the graph; the launches
+// that follow in the same capture take consecutive epochs and ticket bases tracked per capture.
+// Every replay thus starts from the same cleared state and no two launches of one replay share
+// an epoch -- one memset per graph, not per scan (the reference clears per launch,
+// ChainedScanDecoupledLookbackDispatcher.cuh:172-175).  The host-side counters of the ctx are
+// untouched, so plain launches continue unaffected.
 struct CaptureScope {
     gps_ctx* c = nullptr;
     Scratch saved;
     uint64_t* saved_sort_desc = nullptr;
     uint32_t saved_sort_epoch = 0;
     bool active = false;
-    int begin(gps_ctx* ctx, cudaStream_t st, uint64_t desc_words, uint64_t wdesc_words, uint64_t sort_words)
+    enum Kind { SCAN = 1, WIDE = 2, SORT = 4 };
+    int begin(gps_ctx* ctx, cudaStream_t st, int kind)
     {
         c = ctx;
+        cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+        unsigned long long id = 0;
+        GPS_CUDA(cudaStreamGetCaptureInfo(st, &status, &id));
+        if (kind == SORT && !c->g_sort_desc)
+            return fail(GPS_ERR_UNSUPPORTED, "capture needs one gps_sort call of at least this size outside the capture first");
+        if (id != c->cap_id || !c->cap_valid) {  // a new capture sequence
+            c->cap_id = id;
+            c->cap_valid = true;
+            c->cap_cleared = 0;
+            c->cap_epoch = c->cap_wepoch = c->cap_sort_epoch = 0;
+            c->cap_counter_base = 0;
+            GPS_CUDA(cudaMemsetAsync(c->g_counter, 0, 64, st));
+        }
+        if (!(c->cap_cleared & kind)) {
+            if (kind == SCAN) GPS_CUDA(cudaMemsetAsync(c->g_desc, 0, (size_t)c->s.desc_tiles * sizeof(uint64_t), st));
+            if (kind == WIDE) GPS_CUDA(cudaMemsetAsync(c->g_wdesc, 0, (size_t)c->s.wdesc_words * sizeof(uint64_t), st));
+            if (kind == SORT)
+                GPS_CUDA(cudaMemsetAsync(c->g_sort_desc, 0, (size_t)c->sort_desc_tiles * kRadix * sizeof(uint64_t), st));
+            c->cap_cleared |= kind;
+        }
         saved = c->s;
         saved_sort_desc = c->sort_desc;
         saved_sort_epoch = c->sort_epoch;
         active = true;
-        if (sort_words && !c->g_sort_desc)
-            return fail(GPS_ERR_UNSUPPORTED, "capture needs one gps_sort call of at least this size outside the capture first");
-        desc_words = std::min<uint64_t>(desc_words, c->s.desc_tiles);
-        wdesc_words = std::min<uint64_t>(wdesc_words, c->s.wdesc_words);
-        GPS_CUDA(cudaMemsetAsync(c->g_counter, 0, 64, st));
-        if (desc_words) GPS_CUDA(cudaMemsetAsync(c->g_desc, 0, desc_words * sizeof(uint64_t), st));
-        if (wdesc_words) GPS_CUDA(cudaMemsetAsync(c->g_wdesc, 0, wdesc_words * sizeof(uint64_t), st));
-        if (sort_words) GPS_CUDA(cudaMemsetAsync(c->g_sort_desc, 0, sort_words * sizeof(uint64_t), st));
         c->s.desc = c->g_desc;
         c->s.wdesc = c->g_wdesc;
         c->s.counter = c->g_counter;
-        c->s.counter_base = 0;
-        c->s.epoch = 0;   // next_epoch() -> 1, 2, ... in capture order
-        c->s.wepoch = 0;
+        c->s.counter_base = c->cap_counter_base;
+        c->s.epoch = c->cap_epoch;
+        c->s.wepoch = c->cap_wepoch;
         c->sort_desc = c->g_sort_desc;
-        c->sort_epoch = 0;
+        c->sort_epoch = c->cap_sort_epoch;
         return GPS_OK;
     }
     ~CaptureScope()
     {
         if (!active) return;
+        c->cap_counter_base = c->s.counter_base;  // what this launch consumed, for the next one
+        c->cap_epoch = c->s.epoch;
+        c->cap_wepoch = c->s.wepoch;
+        c->cap_sort_epoch = c->sort_epoch;
         c->s = saved;
         c->sort_desc = saved_sort_desc;
         c->sort_epoch = saved_sort_epoch;
@@ -320,7 +344,7 @@ int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, voi
     if (rc) return rc;
     CaptureScope cap;
     if (capturing && algo != GPS_ALGO_RTS) {
-        rc = cap.begin(c, st, div_up(n, 2048) + 1, 0, 0);
+        rc = cap.begin(c, st, CaptureScope::SCAN);
         if (rc) return rc;
     }
     if (dtype == GPS_U32)
@@ -681,7 +705,7 @@ int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, v
     if (int rc = enter_stream(c, st, &capturing)) return rc;
     CaptureScope cap;
     if (capturing && algo != GPS_ALGO_RTS)
-        if (int rc = cap.begin(c, st, 0, (div_up(n * es, kWideTileBytes) + 1) * 8, 0)) return rc;
+        if (int rc = cap.begin(c, st, CaptureScope::WIDE)) return rc;
     const bool incl = kind == GPS_INCLUSIVE;
     bool& cfg = c->wide_configured[dtype][incl ? 0 : 1][algo == GPS_ALGO_RTS ? 1 : 0];
     switch (dtype) {
@@ -749,7 +773,7 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         return fail(GPS_ERR_UNSUPPORTED, "capture needs one gps_sort call of at least this size outside the capture first");
     CaptureScope cap;
     if (capturing)
-        if (int rc = cap.begin(c, st, 0, 0, (uint64_t)tiles * kRadix)) return rc;
+        if (int rc = cap.begin(c, st, CaptureScope::SORT)) return rc;
     if (tiles > c->sort_desc_tiles) {  // grow (synchronous, rare)
         GPS_CUDA(cudaDeviceSynchronize());
         if (c->sort_desc) cudaFree(c->sort_desc);
@@ -885,7 +909,7 @@ int gps_scan_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void* d_in
     if (rc) return rc;
     CaptureScope cap;
     if (capturing) {
-        rc = cap.begin(c, st, div_up(n, 2048) + 1, 0, 0);
+        rc = cap.begin(c, st, CaptureScope::SCAN);
         if (rc) return rc;
     }
     cudaError_t e;

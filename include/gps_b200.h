@@ -87,9 +87,10 @@ int gps_device_info(int device, char* name, int* sm_count, uint64_t* l2_bytes,
  * serialise).  For concurrent scans use one ctx per stream.
  * CUDA graphs: gps_scan, gps_scan_wide, gps_scan_emulated_deadlock, gps_sort_* and gps_reduce*
  * may be captured and replayed.  Reduce-then-Scan keeps no launch state; for the chained kernels
- * and the sort a captured launch runs on a shadow scratch of the ctx that the captured sequence
- * clears first (constant epochs, zero ticket base), so every replay starts from the same state
- * and plain launches of the ctx are unaffected.  Make one call of each kind outside the capture
+ * and the sort a captured launch runs on a shadow scratch of the ctx: the first captured launch
+ * of a capture records a clear of it into the graph, the following ones take consecutive epochs
+ * and ticket bases, so every replay starts from the same state and plain launches of the ctx are
+ * unaffected.  Make one call of each kind outside the capture
  * first (function attributes and the sort's lazily sized scratch cannot be set up while
  * capturing); captured launches of ONE ctx must be ordered with respect to each other. */
 int gps_create(gps_ctx** ctx, int device, uint64_t max_n);
