@@ -306,7 +306,10 @@ cudaError_t launch_rts_blocked(Scratch& s, const void* in, void* out, uint64_t n
     p.slot_tag = cs.tag;
     p.total_out = cs.total_out;
     p.publish = cs.publish;
-    const bool pdl = s.flags & PF_PDL;
+    // plain launches: this variant serves the large inputs, where programmatic dependent launch
+    // costs 1.6 % (2^28 keys: 554 / 551 Gkeys/s without, 546 / 542 with -- tools/rts_ab.py), as it
+    // does for the sharded reduce + scan pair
+    const bool pdl = false;
     e = launch_scan_kernel(rts_reduce_kernel<T, NT, V>, p.num_tiles, NT, 0, st, pdl, p);
     if (e == cudaSuccess) e = launch_scan_kernel(rts_spine_kernel<T>, 1, kSpineThreads, 0, st, pdl, p);
     if (e == cudaSuccess) e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, pdl, p);
