@@ -47,7 +47,7 @@ def test_compare_at_2p28(oracle, ref_shim):
     def rate(ms):
         return n / (ms * 1e-3) / 1e9
 
-    for name, algo in [("ours_csdl (smem-resident tile, default)", "csdl"), ("ours_csdl_reg", "csdl_reg"),
+    for name, algo in [("ours_csdl (default: blocked smem-resident tile)", "csdl"), ("ours_csdl_reg", "csdl_reg"),
                        ("ours_csdl_tma", "csdl_tma"),
                        ("ours_rts", "rts"), ("ours_csdl_fallback (no stalls)", "csdl_fallback")]:
         res[name] = rate(_time_ours(ps, gps, algo, buf, batch))
@@ -73,8 +73,8 @@ def test_compare_at_2p28(oracle, ref_shim):
     with open(os.path.join(ROOT, "gpurun_out", "compare.json"), "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps(res, indent=1))
-    assert res["ours_csdl (smem-resident tile, default)"] > res["reference_csdl"]
-    assert res["ours_csdl (smem-resident tile, default)"] > res["cub_device_scan"]
+    assert res["ours_csdl (default: blocked smem-resident tile)"] > res["reference_csdl"]
+    assert res["ours_csdl (default: blocked smem-resident tile)"] > res["cub_device_scan"]
     ps.close()
 
 
