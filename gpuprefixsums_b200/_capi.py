@@ -92,6 +92,10 @@ SIGNATURES = {
     "gps_sharded_destroy": (None, [_vp]),
     "gps_sharded_scan": (_i32, [_vp, _i32, _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_u64), _i32,
                                 C.POINTER(C.c_float)]),
+    "gps_sharded_ctx": (_vp, [_vp, _i32]),
+    "gps_sharded_scan_host": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
+    "gps_sharded_scan_host_async": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
+    "gps_sharded_host_sync": (_i32, [_vp]),
 }
 
 

@@ -611,8 +611,15 @@ int gps_check(gps_ctx* c, void* stream)
     uint32_t st = 0;
     GPS_CUDA(cudaMemcpy(&st, c->s.status, sizeof(st), cudaMemcpyDeviceToHost));
     if (st) {
+        // CTAs that bailed out may have skipped ticket claims: bring the host's ticket base back
+        // in step with the device counter once everything has drained
+        GPS_CUDA(cudaDeviceSynchronize());
+        uint32_t counter = 0;
+        GPS_CUDA(cudaMemcpy(&counter, c->s.counter, sizeof(counter), cudaMemcpyDeviceToHost));
+        c->s.counter_base = counter;
         GPS_CUDA(cudaMemset(c->s.status, 0, sizeof(uint32_t)));
-        return fail(GPS_ERR_WATCHDOG, "look-back poll budget exceeded (status 0x%x): results invalid", st);
+        return fail(GPS_ERR_WATCHDOG, "%s (status 0x%x): results invalid",
+                    (st & STATUS_SLOT_TIMEOUT) ? "a carry slot never arrived" : "look-back poll budget exceeded", st);
     }
     return GPS_OK;
 }
@@ -664,6 +671,11 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     } else if (!strcmp(key, "poll_sleep_ns")) {
         if (value < 0 || value > 100000) return fail(GPS_ERR_INVALID, "poll_sleep_ns out of range");
         c->s.poll_sleep_ns = (uint32_t)value;
+    } else if (!strcmp(key, "slot_wait_polls")) {
+        // polls tile 0 / the spine may spend on one carry slot before giving up (0 = default 2^26,
+        // more than a minute); tests use a small value to exercise the timeout path
+        if (value < 0 || value > 0xFFFFFFFFll) return fail(GPS_ERR_INVALID, "slot_wait_polls out of range");
+        c->s.slot_poll_limit = (uint32_t)value;
     } else if (!strcmp(key, "host_chunk_keys")) {
         if (value < 4096 || (uint64_t)value > (1ull << 30)) return fail(GPS_ERR_INVALID, "host_chunk_keys out of range");
         if (c->stage[0]) return fail(GPS_ERR_INVALID, "host pipeline already initialised");
@@ -762,6 +774,9 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
     if (d_keys_tmp == d_keys_in || d_keys_tmp == d_keys_out || (pairs && (d_vals_tmp == d_vals_in || d_vals_tmp == d_vals_out)))
         return fail(GPS_ERR_INVALID, "the tmp buffer must be distinct from in and out");
     const int passes = (end_bit + 7) / 8;
+    // bits of the last digit that take part: a sort on end_bit bits orders by key & (2^end_bit - 1)
+    // and nothing else (cub's end_bit), so the last pass masks its digit when end_bit % 8 != 0
+    const uint32_t last_mask = (end_bit & 7) ? ((1u << (end_bit & 7)) - 1u) : 0xFFu;
     if ((passes & 1) && (d_keys_in == d_keys_out || (pairs && d_vals_in == d_vals_out)))
         return fail(GPS_ERR_INVALID, "in == out needs an even number of digit passes (end_bit 9..16 or 25..32)");
     DeviceGuard g(c->device);
@@ -799,7 +814,7 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         }
         const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->s.sm_count, div_up(n, 4 * kHistThreads));
         sort_hist_kernel<<<grid, kHistThreads, kHistSmemBytes, st>>>((const uint32_t*)d_keys_in, (uint32_t)n, hist, passes,
-                                                                     (uint32_t)key_type);
+                                                                     (uint32_t)key_type, last_mask);
         sort_digit_base_kernel<<<passes, kRadix, 0, st>>>(hist, digit_base);
     }
     // ping-pong so that the last pass lands in `out`
@@ -827,7 +842,8 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         p.status = c->s.status;
         p.xform_in = pass == 0 ? (uint32_t)key_type : 0u;
         p.xform_out = pass == passes - 1 ? (uint32_t)key_type : 0u;
-        const bool xf = p.xform_in || p.xform_out;
+        p.digit_mask = pass == passes - 1 ? last_mask : 0xFFu;
+        const bool xf = p.xform_in || p.xform_out || p.digit_mask != 0xFFu;
         const bool pdl = c->s.flags & PF_PDL;
         GPS_CUDA(pairs ? (xf ? launch_sort_pass<true, true>(p, c->sort_configured[3], pdl, st)
                              : launch_sort_pass<true, false>(p, c->sort_configured[1], pdl, st))
@@ -1281,7 +1297,40 @@ struct gps_shard_group {
     std::vector<uint64_t*> slots;   // per GPU: 2 parities x n slots
     std::vector<cudaEvent_t> ev0, ev1;
     uint32_t tag = 0;
+    // host-buffer pipeline (gps_sharded_scan_host*): chunk q of the stream of chunks goes to GPU
+    // q % n; its scan publishes the running total into slot [(q / n) & 1] of GPU (q + 1) % n
+    uint64_t host_seq = 0;          // chunks issued so far, over all calls
+    uint32_t host_tag = 0;
+    std::vector<cudaEvent_t> ev_call;  // per GPU; [ev_call_idx] = last scan of the previous call
+    int ev_call_idx = -1;              // (orders call boundaries), -1 = none yet
 };
+
+namespace {
+constexpr int kHostChainSlot0 = 2 * kMaxPublish;  // two more words behind the 2 x kMaxPublish carry slots
+
+// status words of every ctx of the group after its work has drained: a tripped look-back or
+// slot watchdog means wrong results -- report it, clear it and bring the ticket base back in step
+int sharded_status(gps_shard_group* g)
+{
+    int rc = GPS_OK;
+    for (int i = 0; i < g->n; ++i) {
+        gps_ctx* c = g->ctx[i];
+        cudaSetDevice(g->devices[i]);
+        uint32_t st[2] = {0, 0};  // {counter, status} are adjacent
+        if (cudaMemcpy(st, c->s.counter, sizeof(st), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            rc = fail(GPS_ERR_CUDA, "device %d: status read failed: %s", g->devices[i], cudaGetErrorString(cudaGetLastError()));
+            continue;
+        }
+        if (st[1]) {
+            cudaMemset(c->s.status, 0, sizeof(uint32_t));
+            c->s.counter_base = st[0];
+            rc = fail(GPS_ERR_WATCHDOG, "device %d: %s (status 0x%x): results invalid", g->devices[i],
+                      (st[1] & STATUS_SLOT_TIMEOUT) ? "a carry slot never arrived" : "look-back poll budget exceeded", st[1]);
+        }
+    }
+    return rc;
+}
+}  // namespace
 
 extern "C" {
 
@@ -1298,6 +1347,7 @@ int gps_sharded_create(gps_shard_group** out, int n_gpus, const int* devices, ui
     g->slots.assign(n_gpus, nullptr);
     g->ev0.assign(n_gpus, nullptr);
     g->ev1.assign(n_gpus, nullptr);
+    g->ev_call.assign(n_gpus, nullptr);
     int prev = 0;
     cudaGetDevice(&prev);
     int rc = GPS_OK;
@@ -1323,10 +1373,11 @@ int gps_sharded_create(gps_shard_group** out, int n_gpus, const int* devices, ui
         }
         if (rc) break;
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->stream[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc(&g->slots[i], 2 * kMaxPublish * sizeof(uint64_t));
-        if (e == cudaSuccess) e = cudaMemset(g->slots[i], 0, 2 * kMaxPublish * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMalloc(&g->slots[i], (2 * kMaxPublish + 2) * sizeof(uint64_t));
+        if (e == cudaSuccess) e = cudaMemset(g->slots[i], 0, (2 * kMaxPublish + 2) * sizeof(uint64_t));
         if (e == cudaSuccess) e = cudaEventCreate(&g->ev0[i]);
         if (e == cudaSuccess) e = cudaEventCreate(&g->ev1[i]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->ev_call[i], cudaEventDisableTiming);
         if (e != cudaSuccess) rc = fail(GPS_ERR_CUDA, "sharded setup on device %d: %s", devices[i], cudaGetErrorString(e));
     }
     cudaSetDevice(prev);
@@ -1345,6 +1396,7 @@ void gps_sharded_destroy(gps_shard_group* g)
     cudaGetDevice(&prev);
     for (int i = 0; i < g->n; ++i) {
         cudaSetDevice(g->devices[i]);
+        if (g->ev_call[i]) cudaEventDestroy(g->ev_call[i]);
         if (g->stream[i]) cudaStreamDestroy(g->stream[i]);
         if (g->slots[i]) cudaFree(g->slots[i]);
         if (g->ev0[i]) cudaEventDestroy(g->ev0[i]);
@@ -1416,8 +1468,134 @@ int gps_sharded_scan(gps_shard_group* g, int algo, int kind, int dtype, const vo
     (void)t0;
     (void)t1;
     if (h_ms) *h_ms = worst;
+    if (!rc) rc = sharded_status(g);  // a carry slot that never arrived must not pass silently
     cudaSetDevice(prev);
     return rc;
+}
+
+gps_ctx* gps_sharded_ctx(gps_shard_group* g, int index)
+{
+    return (g && index >= 0 && index < g->n) ? g->ctx[index] : nullptr;
+}
+
+// One host array, all GPUs of the group, one call.  The array is cut into chunks of
+// "host_chunk_keys"; chunk q of the running sequence goes to GPU q % G: copy-in, scan, copy-out on
+// that GPU's three streams over its rotating staging buffers, exactly as gps_scan_host does on one
+// GPU.  The scan of chunk q seeds itself from the tagged running total its predecessor's last tile
+// stored into THIS GPU's slot over NVLink (st.release.sys -> ld.acquire.sys in tile 0's carry
+// acquisition) and publishes its own inclusive total to the next GPU's slot: the chunks' scans
+// form one chain across the GPUs (~20 us per 64 MiB link) while G copy-ins and G copy-outs run
+// concurrently -- 8 B/key of HBM traffic per key, no reduce pre-pass, no host synchronisation and
+// no collective.  (The device-resident sharded scan needs its reduce pass because all slices are
+// already there and must be scanned at once; here PCIe is three orders of magnitude slower than
+// the chain.)
+int gps_sharded_scan_host_async(gps_shard_group* g, int algo, int kind, int dtype, const void* h_in,
+                                void* h_out, uint64_t n, uint32_t carry_in_bits, void* h_total_out)
+{
+    if (!g) return fail(GPS_ERR_INVALID, "null group");
+    if (n && (!h_in || !h_out)) return fail(GPS_ERR_INVALID, "null host pointer");
+    if (kind != GPS_INCLUSIVE && kind != GPS_EXCLUSIVE) return fail(GPS_ERR_INVALID, "bad kind %d", kind);
+    if (dtype != GPS_U32 && dtype != GPS_F32) return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
+    const int G = g->n;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    struct Restore {
+        int dev;
+        ~Restore() { cudaSetDevice(dev); }
+    } restore{prev};
+    uint64_t chunk = ~0ull;
+    for (int i = 0; i < G; ++i) {
+        gps_ctx* c = g->ctx[i];
+        GPS_CUDA(cudaSetDevice(g->devices[i]));
+        if (int rc = host_pipeline_init(c)) return rc;
+        chunk = std::min(chunk, std::min<uint64_t>(c->host_chunk_keys, std::max<uint64_t>(c->max_n, 4096)));
+    }
+    const uint64_t n_chunks = std::max<uint64_t>(1, div_up(n, chunk));
+    const char* src = static_cast<const char*>(h_in);
+    char* dst = static_cast<char*>(h_out);
+    uint32_t prev_tag = 0;
+    for (uint64_t k = 0; k < n_chunks; ++k) {
+        const uint64_t q = g->host_seq++;
+        const int gi = (int)(q % (uint64_t)G);
+        gps_ctx* c = g->ctx[gi];
+        GPS_CUDA(cudaSetDevice(g->devices[gi]));
+        const uint64_t seq = c->host_chunk_seq++;
+        const int b = (int)(seq % kHostBufs);
+        const uint64_t off = k * chunk;
+        const uint64_t len = std::min<uint64_t>(chunk, n - off);
+        if (seq >= (uint64_t)kHostBufs) GPS_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_d2h[b], 0));
+        if (len) GPS_CUDA(cudaMemcpyAsync(c->stage[b], src + off * 4, len * 4, cudaMemcpyHostToDevice, c->s_h2d));
+        GPS_CUDA(cudaEventRecord(c->ev_h2d[b], c->s_h2d));
+        GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_h2d[b], 0));
+        CarrySpec cs;
+        if (++g->host_tag == 0) ++g->host_tag;  // 0 is the "never written" tag
+        const uint32_t tag = g->host_tag;
+        if (k == 0) {
+            cs.carry_bits = carry_in_bits;
+            // call boundary: the chain restarts here, so order it behind the previous call's last scan
+            // (a slot is only reused once its previous reader has run, which the chain guarantees
+            // inside a call and this event guarantees across calls)
+            if (g->ev_call_idx >= 0) GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, g->ev_call[g->ev_call_idx], 0));
+        } else {  // the slot the previous chunk's scan publishes into, on THIS GPU
+            cs.slots = g->slots[gi] + kHostChainSlot0 + (((q - 1) / (uint64_t)G) & 1u);
+            cs.n_slots = cs.n_carry = 1;
+            cs.tag = prev_tag;
+            // two "GPUs" of the group that are one physical device (tests on a single-GPU box): a
+            // scan spinning on its slot could keep its predecessor from ever becoming resident,
+            // so there the chain is also a stream dependency
+            const int pi = (int)((q - 1) % (uint64_t)G);
+            if (pi != gi && g->devices[pi] == g->devices[gi])
+                GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, g->ctx[pi]->ev_cmp[(g->ctx[pi]->host_chunk_seq - 1) % kHostBufs], 0));
+        }
+        prev_tag = tag;
+        if (k + 1 < n_chunks) {
+            cs.publish.n = 1;
+            cs.publish.dst[0] = g->slots[(gi + 1) % G] + kHostChainSlot0 + ((q / (uint64_t)G) & 1u);
+            cs.publish.tag = tag;
+        } else {
+            cs.total_out = c->chain_total;
+            if (c->ev_total_pending) GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_total, 0));
+            c->ev_total_pending = false;
+        }
+        if (int rc = dispatch_scan(c, algo, kind, dtype, c->stage[b], c->stage[b], len, cs, c->s_cmp)) return rc;
+        GPS_CUDA(cudaEventRecord(c->ev_cmp[b], c->s_cmp));
+        GPS_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_cmp[b], 0));
+        if (len) GPS_CUDA(cudaMemcpyAsync(dst + off * 4, c->stage[b], len * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        GPS_CUDA(cudaEventRecord(c->ev_d2h[b], c->s_d2h));
+        if (k + 1 == n_chunks) {
+            if (h_total_out) {
+                GPS_CUDA(cudaMemcpyAsync(h_total_out, c->chain_total, 4, cudaMemcpyDeviceToHost, c->s_d2h));
+                GPS_CUDA(cudaEventRecord(c->ev_total, c->s_d2h));
+                c->ev_total_pending = true;
+            }
+            GPS_CUDA(cudaEventRecord(g->ev_call[gi], c->s_cmp));
+            g->ev_call_idx = gi;
+        }
+    }
+    return GPS_OK;
+}
+
+int gps_sharded_host_sync(gps_shard_group* g)
+{
+    if (!g) return fail(GPS_ERR_INVALID, "null group");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    int rc = GPS_OK;
+    for (int i = 0; i < g->n; ++i) {
+        cudaSetDevice(g->devices[i]);
+        const int r = gps_host_sync(g->ctx[i]);
+        if (r && !rc) rc = r;
+    }
+    if (!rc) rc = sharded_status(g);
+    cudaSetDevice(prev);
+    return rc;
+}
+
+int gps_sharded_scan_host(gps_shard_group* g, int algo, int kind, int dtype, const void* h_in, void* h_out,
+                          uint64_t n, uint32_t carry_in_bits, void* h_total_out)
+{
+    const int rc = gps_sharded_scan_host_async(g, algo, kind, dtype, h_in, h_out, n, carry_in_bits, h_total_out);
+    return rc ? rc : gps_sharded_host_sync(g);
 }
 
 }  // extern "C"

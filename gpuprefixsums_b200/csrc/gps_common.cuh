@@ -49,6 +49,7 @@ struct ScanParams {
     uint32_t n_slots;         // slots polled until their tag == slot_tag
     uint32_t n_carry;         // the first n_carry of them are summed into the carry
     uint32_t slot_tag;
+    uint32_t slot_poll_limit; // polls a carry slot may take (0 = kSlotPollsDefault)
     void* total_out;          // optional: carry + sum of all keys
     PublishList publish;      // optional: tagged total for downstream consumers
     uint32_t* status;         // watchdog / error word (bit 0 = poll budget exceeded)
@@ -86,7 +87,7 @@ enum : uint32_t {
 };
 
 enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
-enum : uint32_t { STATUS_WATCHDOG = 1u };
+enum : uint32_t { STATUS_WATCHDOG = 1u, STATUS_SLOT_TIMEOUT = 2u };
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 // CTAs per SM the scan kernels are compiled for: as many as fit at `regs` registers/thread
 constexpr int min_ctas_per_sm(int nt, int regs = 40) { return 65536 / (nt * regs) > 0 ? 65536 / (nt * regs) : 1; }
@@ -413,22 +414,35 @@ __device__ __forceinline__ bool watchdog_tick(uint32_t& polls, uint32_t* status)
 // Called by a full warp.  Slots may live in this GPU's memory and be written by peer
 // GPUs over NVLink (st.release.sys), hence system scope.
 // ---------------------------------------------------------------------------------
+// The wait for a slot has its OWN poll budget, far larger than the look-back watchdog: the writer
+// is another GPU / process / pipeline stage that may legitimately be seconds late (lazy module
+// load on its first call, a slower copy-in, a paused process).  After the first 1024 polls the
+// back-off grows to 1 us, so the default budget of 2^26 polls is more than a minute.  A slot that
+// never arrives sets STATUS_SLOT_TIMEOUT (reported by gps_check / gps_sharded_* as
+// GPS_ERR_WATCHDOG) and contributes NOTHING -- never the mismatched word.
+constexpr uint32_t kSlotPollsDefault = 1u << 26;
 template <typename T>
 __device__ __forceinline__ T acquire_carry(const ScanParams& p, uint32_t lane)
 {
     T carry = from_bits<T>(p.carry_bits);
+    const uint32_t budget = p.slot_poll_limit ? p.slot_poll_limit : kSlotPollsDefault;
     for (uint32_t base = 0; base < p.n_slots; base += 32) {
         const uint32_t i = base + lane;
         T v = T(0);
         if (i < p.n_slots) {
             uint32_t polls = 0;
             uint64_t s = ld_acquire_sys(p.slots + i);
+            bool ok = true;
             while ((uint32_t)(s >> 32) != p.slot_tag) {
-                if (watchdog_tick(polls, p.status)) break;
-                __nanosleep(64);
+                if (++polls >= budget) {
+                    atomicOr(p.status, STATUS_WATCHDOG | STATUS_SLOT_TIMEOUT);
+                    ok = false;
+                    break;
+                }
+                __nanosleep(polls < 1024u ? 64u : 1000u);
                 s = ld_acquire_sys(p.slots + i);
             }
-            if (i < p.n_carry) v = from_bits<T>((uint32_t)s);
+            if (ok && i < p.n_carry) v = from_bits<T>((uint32_t)s);
         }
         carry += warp_reduce(v);
     }

@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
+        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
     const uint32_t v0 = tid * V;  // this thread's first uint4 within the tile
     if (!Tile::arrive(s_data, &s_bar, p.in, tile, p.n, full, v0)) {  // never expected; do not hang the GPU

@@ -39,6 +39,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 24 + 4 * V)) csdl_reg_
         __syncthreads();
         tile = s_tile;
     }
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
+        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
     const uint64_t vbase = Tile::vec_base(tile, warp, lane);
 
@@ -128,6 +132,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
     if (threadIdx.x == 0) s_tile = claim_tile(p);
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
+        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
     const uint64_t vbase = Tile::vec_base(tile, warp, lane);
 

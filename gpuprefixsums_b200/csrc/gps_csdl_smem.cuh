@@ -120,6 +120,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
+        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const bool full = ((uint64_t)tile + 1u) * TILE_KEYS <= p.n;
     const uint32_t row0 = warp * (32u * V) + lane;  // this thread's uint4 of row 0 (index in tile)
     const uint64_t vbase = (uint64_t)tile * TILE_VEC + row0;
@@ -223,6 +227,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
+        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const bool full = ((uint64_t)tile + 1u) * TILE_KEYS <= p.n;
     const uint32_t row0 = warp * (32u * V) + lane;
     const uint64_t vbase = (uint64_t)tile * TILE_VEC + row0;
@@ -450,6 +458,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
+        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
     const uint32_t v0 = tid * V;                     // this thread's first uint4 within the tile
     const uint32_t row0 = warp * (32u * V) + lane;   // lane-strided start for the fallback re-read

@@ -52,6 +52,7 @@ struct Scratch {
     uint32_t epoch = 0;
     int sm_count = 148;
     uint32_t poll_sleep_ns = 0;
+    uint32_t slot_poll_limit = 0;  // 0 = kSlotPollsDefault (option "slot_wait_polls")
     uint32_t flags = 0;
     unsigned long long* prof = nullptr;  // optional profiling counters (tuning harness)
     // wide-element chained scan (gps_wide.cuh): 2*W words per tile, own epoch counter
@@ -95,6 +96,7 @@ inline ScanParams make_scan_params(Scratch& s, const void* in, void* out, uint64
     p.n_slots = cs.n_slots;
     p.n_carry = cs.n_carry;
     p.slot_tag = cs.tag;
+    p.slot_poll_limit = s.slot_poll_limit;
     p.total_out = cs.total_out;
     p.publish = cs.publish;
     p.status = s.status;
@@ -129,7 +131,8 @@ cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, c
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
     const cudaError_t e =
         launch_scan_kernel(csdl_reg_kernel<T, NT, V, INCL, WIN, PROF>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
-    if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
+    // one claim per CTA -- of a launch that actually happened
+    if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;
 }
 
@@ -148,7 +151,8 @@ cudaError_t launch_csdl_smem(Scratch& s, const void* in, void* out, uint64_t n, 
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
     const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
-    if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
+    // one claim per CTA -- of a launch that actually happened
+    if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;
 }
 
@@ -166,7 +170,8 @@ cudaError_t launch_csdl_blocked(Scratch& s, const void* in, void* out, uint64_t 
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
     const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
-    if (!(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;  // one claim per CTA
+    // one claim per CTA -- of a launch that actually happened
+    if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;
 }
 
@@ -194,9 +199,10 @@ cudaError_t launch_csdl_tma(Scratch& s, const void* in, void* out, uint64_t n, c
     ScanParams p = make_scan_params(s, in, out, n, Cfg::TILE_KEYS, cs, st);
     const uint32_t grid = std::min<uint32_t>(p.num_tiles, (uint32_t)(occ * s.sm_count));
     kern<<<grid, NT, Cfg::RING_BYTES, st>>>(p);
+    const cudaError_t e = cudaGetLastError();
     // every CTA claims STAGES-1 tiles up front and one more per tile it processes
-    s.counter_base += grid * (STAGES - 1) + p.num_tiles;
-    return cudaGetLastError();
+    if (e == cudaSuccess) s.counter_base += grid * (STAGES - 1) + p.num_tiles;
+    return e;
 }
 
 // ---- CSDL + Decoupled Fallback ---------------------------------------------------------
@@ -207,7 +213,7 @@ cudaError_t launch_csdl_fallback(Scratch& s, const void* in, void* out, uint64_t
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
     const cudaError_t e = launch_scan_kernel(csdl_fallback_kernel<T, NT, V, INCL>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
-    s.counter_base += p.num_tiles;
+    if (e == cudaSuccess) s.counter_base += p.num_tiles;
     return e;
 }
 
@@ -225,7 +231,7 @@ cudaError_t launch_csdl_smem_fallback(Scratch& s, const void* in, void* out, uin
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
     const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
-    s.counter_base += p.num_tiles;
+    if (e == cudaSuccess) s.counter_base += p.num_tiles;
     return e;
 }
 
@@ -242,7 +248,7 @@ cudaError_t launch_csdl_blocked_fallback(Scratch& s, const void* in, void* out, 
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
     const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
-    s.counter_base += p.num_tiles;
+    if (e == cudaSuccess) s.counter_base += p.num_tiles;
     return e;
 }
 
@@ -273,6 +279,7 @@ cudaError_t launch_rts(Scratch& s, const void* in, void* out, uint64_t n, const 
     p.n_slots = cs.n_slots;
     p.n_carry = cs.n_carry;
     p.slot_tag = cs.tag;
+    p.slot_poll_limit = s.slot_poll_limit;
     p.total_out = cs.total_out;
     p.publish = cs.publish;
     const bool pdl = s.flags & PF_PDL;
@@ -304,6 +311,7 @@ cudaError_t launch_rts_blocked(Scratch& s, const void* in, void* out, uint64_t n
     p.n_slots = cs.n_slots;
     p.n_carry = cs.n_carry;
     p.slot_tag = cs.tag;
+    p.slot_poll_limit = s.slot_poll_limit;
     p.total_out = cs.total_out;
     p.publish = cs.publish;
     // plain launches: this variant serves the large inputs, where programmatic dependent launch

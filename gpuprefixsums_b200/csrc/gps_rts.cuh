@@ -30,6 +30,7 @@ struct RtsParams {
     uint32_t n_slots;
     uint32_t n_carry;
     uint32_t slot_tag;
+    uint32_t slot_poll_limit;
     void* total_out;           // nullable
     PublishList publish;       // tagged total for downstream consumers
     uint32_t* status;
@@ -80,6 +81,7 @@ __device__ __forceinline__ ScanParams carry_view(const RtsParams& p)
     s.n_slots = p.n_slots;
     s.n_carry = p.n_carry;
     s.slot_tag = p.slot_tag;
+    s.slot_poll_limit = p.slot_poll_limit;
     s.status = p.status;
     return s;
 }

@@ -40,6 +40,9 @@ struct SortParams {
     uint32_t* status;          // watchdog word
     uint32_t xform_in;         // key type whose order-preserving map is applied on load (first pass), else 0
     uint32_t xform_out;        // key type whose inverse map is applied on store (last pass), else 0
+    uint32_t digit_mask;       // 0xFF, or (1 << r) - 1 when only r < 8 bits of this digit take part
+                               // (last pass of a sort on end_bit % 8 != 0 bits); honoured by the XFORM
+                               // instantiation only, which the host selects for such a pass
 };
 
 // Order-preserving maps onto uint32 (keys travel transformed between the passes):
@@ -94,7 +97,8 @@ constexpr int kHistThreads = 1024;
 constexpr size_t kHistSmemBytes = (size_t)4 * kRadix * 32 * sizeof(uint32_t);
 
 __global__ void __launch_bounds__(kHistThreads, 1)
-    sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist, int passes, uint32_t key_type)
+    sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist, int passes, uint32_t key_type,
+                     uint32_t last_mask)
 {
     extern __shared__ __align__(16) uint32_t s_hist[];  // [4 * 256][32]
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
@@ -104,7 +108,8 @@ __global__ void __launch_bounds__(kHistThreads, 1)
         k = sort_key_map(k, key_type);
 #pragma unroll
         for (int p = 0; p < 4; ++p)
-            if (p < passes) atomicAdd(&s_hist[((p * kRadix + ((k >> (8 * p)) & 0xFFu)) << 5) + lane], 1u);
+            if (p < passes)  // the last pass may cover fewer than 8 bits (end_bit % 8 != 0)
+                atomicAdd(&s_hist[((p * kRadix + ((k >> (8 * p)) & (p == passes - 1 ? last_mask : 0xFFu))) << 5) + lane], 1u);
     };
     const uint4* k4 = reinterpret_cast<const uint4*>(keys);
     const uint32_t nvec = n / 4u;
@@ -219,6 +224,11 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     __shared__ uint32_t s_tile;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // the digit of a (mapped) key in this pass; only the XFORM instantiation pays for the mask
+    auto digit_of = [&](uint32_t k) -> uint32_t {
+        const uint32_t d = sort_digit(k, p.shift);
+        return XFORM ? (d & p.digit_mask) : d;
+    };
 
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -235,6 +245,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     for (uint32_t i = tid; i < (uint32_t)NW * kRadix; i += NT) (&s_whist[0][0])[i] = 0u;
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed)
+        if (tid == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const uint64_t tile_base = (uint64_t)tile * TILE;
     const bool full = tile_base + TILE <= p.n;
     const uint32_t valid = full ? TILE : (uint32_t)(p.n - tile_base);
@@ -245,8 +259,9 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
             return;
         }
     } else {
-        // last tile: pad with (the preimage of) 0xFFFFFFFF -- digit 255 in every pass, ranked after
-        // every real key of the tile, so the padding occupies exactly the sorted-tile indices >= valid
+        // last tile: pad with (the preimage of) 0xFFFFFFFF -- the largest digit of every pass (255, or
+        // digit_mask), ranked after every real key of the tile, so the padding occupies exactly the
+        // sorted-tile indices >= valid
         const uint32_t pad = XFORM ? sort_key_unmap(0xFFFFFFFFu, p.xform_in) : 0xFFFFFFFFu;
 #pragma unroll 1
         for (uint32_t i = tid; i < TILE; i += NT) {
@@ -275,7 +290,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     };
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
-        const uint32_t d = sort_digit(key[j], p.shift);
+        const uint32_t d = digit_of(key[j]);
         const uint32_t peers = sort_peers(d);
         const uint32_t below = __popc(peers & ((1u << lane) - 1u));
         const uint32_t pre = s_whist[warp][d];
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     // ---- keys into shared memory in digit order
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
-        const uint32_t q = get_pos(j) + s_whist[warp][sort_digit(key[j], p.shift)];
+        const uint32_t q = get_pos(j) + s_whist[warp][digit_of(key[j])];
         set_pos(j, q);
         s_keys[q] = key[j];
     }
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     for (int k = 0; k < KPT; ++k) {
         const uint32_t i = k * NT + tid;
         const uint32_t kk = s_keys[i];
-        const uint32_t g = s_goff[sort_digit(kk, p.shift)] + i;
+        const uint32_t g = s_goff[digit_of(kk)] + i;
         if (full || i < valid) {
             p.keys_out[g] = XFORM ? sort_key_unmap(kk, p.xform_out) : kk;
             if constexpr (PAIRS) p.vals_out[g] = s_vals[i];

@@ -160,6 +160,9 @@ class ShardedScan:
         if h_in.is_cuda or h_out.is_cuda or h_out.numel() != n:
             raise ValueError("scan_host takes two CPU tensors of equal size")
         if getattr(self, "_hp", None) is None or self._hp["x"][0].numel() < n or self._hp["x"][0].dtype != h_in.dtype:
+            # earlier calls may still be copying into / scanning the old staging tensors on the side
+            # streams: drain them before the caching allocator may hand those blocks out again
+            self.synchronize_host()
             mk = lambda: torch.empty(n, dtype=h_in.dtype, device=self.device)  # noqa: E731
             ev = lambda: [torch.cuda.Event(), torch.cuda.Event()]  # noqa: E731
             self._hp = {"x": [mk(), mk()], "out": [mk(), mk()], "k": 0,
@@ -187,7 +190,64 @@ class ShardedScan:
             hp["ev_d2h"][b].record(hp["s_d2h"])
 
     def synchronize_host(self) -> None:
+        """Wait for every queued scan_host call; raises GpsError(GPS_ERR_WATCHDOG) if a look-back or
+        a carry slot of a peer never arrived (the outputs are then invalid)."""
         hp = getattr(self, "_hp", None)
         if hp is not None:
             for key in ("s_h2d", "s_cmp", "s_d2h"):
                 hp[key].synchronize()
+            self.ps.check(hp["s_cmp"])
+
+    def check(self) -> None:
+        """Synchronise the current stream and raise if a scan of this rank gave up waiting."""
+        self.ps.check()
+
+
+class ShardedHostScan:
+    """ONE process, several GPUs, one host array per call (``gps_sharded_scan_host``): the array is
+    cut into chunks dealt round-robin to the GPUs, every GPU pipelines copy-in / scan / copy-out
+    and the chunks' scans chain their running total from GPU to GPU over NVLink.  The multi-GPU
+    form of ``PrefixSum.scan_host``; what a C++ host binds (include/gps_b200.h)."""
+
+    def __init__(self, devices: list[int], chunk_keys: int = 1 << 24):
+        from . import _capi as capi
+
+        self.capi = capi
+        self.devices = list(devices)
+        self._grp = C.c_void_p()
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        capi.check(capi.lib.gps_sharded_create(C.byref(self._grp), len(self.devices), arr, int(chunk_keys)))
+        self.set_option("host_chunk_keys", int(chunk_keys))
+
+    def set_option(self, key: str, value: int) -> None:
+        for i in range(len(self.devices)):
+            ctx = self.capi.lib.gps_sharded_ctx(self._grp, i)
+            self.capi.check(self.capi.lib.gps_set_option(ctx, key.encode(), int(value)))
+
+    def scan_host(self, h_in: torch.Tensor, h_out: torch.Tensor, *, algo="csdl", exclusive: bool = False, carry=0,
+                  total_out: Optional[torch.Tensor] = None, wait: bool = True) -> torch.Tensor:
+        from .scan import _algo, _dtype_code, _kind, carry_bits
+
+        if h_in.is_cuda or h_out.is_cuda or not h_in.is_contiguous() or not h_out.is_contiguous():
+            raise ValueError("scan_host takes contiguous CPU tensors")
+        if h_out.numel() != h_in.numel() or h_out.dtype != h_in.dtype:
+            raise ValueError("h_out must match h_in")
+        fn = self.capi.lib.gps_sharded_scan_host if wait else self.capi.lib.gps_sharded_scan_host_async
+        self.capi.check(fn(self._grp, _algo(algo), _kind(exclusive), _dtype_code(h_in), h_in.data_ptr(), h_out.data_ptr(),
+                           h_in.numel(), carry_bits(carry, h_in.dtype),
+                           total_out.data_ptr() if total_out is not None else None))
+        return h_out
+
+    def sync(self) -> None:
+        self.capi.check(self.capi.lib.gps_sharded_host_sync(self._grp))
+
+    def close(self) -> None:
+        if self._grp.value:
+            self.capi.lib.gps_sharded_destroy(self._grp)
+            self._grp = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -116,6 +116,11 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   their CTAs become resident while the stream's previous kernel drains and
  *                   wait for it to complete before touching memory), 0 = plain launches
  *   "poll_sleep_ns" nanosleep between unsuccessful descriptor polls (default 0)
+ *   "slot_wait_polls" polls a scan may spend waiting for ONE carry slot (gps_scan_carry_slots,
+ *                   the host pipelines) before it gives up: default 0 = 2^26 polls, over a minute
+ *                   -- the writer may be a peer process that is legitimately late.  A slot that
+ *                   never arrives contributes nothing and gps_check / gps_sharded_* report
+ *                   GPS_ERR_WATCHDOG
  *   "host_chunk_keys" chunk size of gps_scan_host (default 2^24; before first use) */
 int gps_set_option(gps_ctx* ctx, const char* key, int64_t value);
 /* Scratch a context of capacity max_n needs on the device, in bytes (descriptors + RTS
@@ -157,7 +162,9 @@ int gps_scan_wide(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in,
 /* ---- radix sort: the scan's consumer (reference README.md:7 names sorting
  * as the downstream use of its scans -- the sort itself is in the sibling repository
  * GPUSorting, outside /root/reference).  Stable LSD radix sort of uint32 keys, ascending, on
- * the low `end_bit` bits (32 = full sort), 8 bits per pass.  One sweep builds the digit
+ * the low `end_bit` bits (32 = full sort): the result is the stable order of key & (2^end_bit-1),
+ * the bits above end_bit do not take part (cub::DeviceRadixSort's end_bit with begin_bit 0).
+ * 8 bits per pass; the last pass covers end_bit % 8 bits when that is not 0.  One sweep builds the digit
  * histograms; each digit pass reads and writes every key once and obtains its 256 per-tile
  * digit offsets from a chained scan with decoupled look-back (csrc/gps_sort.cuh).
  * d_vals_* (all three or none): a 32-bit payload moved with its key.  The result lands in
@@ -286,13 +293,36 @@ int gps_ipc_close(void* d_ptr);
  * downstream GPU's carry slots over NVLink (peer access); pass 2 scans each slice
  * with the carry folded into tile 0's look-back.  carry_mode: 0 = P2P stores,
  * 1 = host-staged exchange (debug).  Synchronous.  h_ms (nullable) receives the
- * max-over-GPUs device time. */
+ * max-over-GPUs device time.  Returns GPS_ERR_WATCHDOG when a look-back or a carry-slot
+ * wait gave up on any GPU (results invalid). */
 int gps_sharded_create(gps_shard_group** grp, int n_gpus, const int* devices,
                        uint64_t max_n_per_gpu);
 void gps_sharded_destroy(gps_shard_group* grp);
 int gps_sharded_scan(gps_shard_group* grp, int algo, int kind, int dtype,
                      const void* const* d_in, void* const* d_out, const uint64_t* n_per_gpu,
                      int carry_mode, float* h_ms);
+/* The ctx of GPU `index` of the group (for gps_set_option, e.g. "host_chunk_keys"); NULL if out
+ * of range.  Owned by the group. */
+gps_ctx* gps_sharded_ctx(gps_shard_group* grp, int index);
+
+/* The reference-facing call with HOST buffers on SEVERAL GPUs: one host array in, one host array
+ * out (pinned for full PCIe bandwidth), all GPUs of the group working on it at once -- the
+ * multi-GPU form of gps_scan_host, and like it the replacement of a dispatcher's
+ * DispatchKernels* over caller memory (ChainedScanDecoupledLookbackDispatcher.cuh:177-195).
+ * The array is cut into chunks of "host_chunk_keys" keys dealt round-robin to the GPUs; every
+ * GPU pipelines copy-in, scan and copy-out of its chunks on three streams, and the scan of a
+ * chunk takes its carry from the tagged running total its predecessor's last tile stored into
+ * this GPU's memory over NVLink (no reduce pre-pass, no host synchronisation, no collective).
+ * gps_sharded_scan_host waits; the _async form returns once everything is queued, consecutive
+ * calls overlap their copies, gps_sharded_host_sync waits for all of them and reports
+ * GPS_ERR_WATCHDOG if a look-back or carry-slot wait gave up.  h_total_out (nullable) receives
+ * carry + sum of all keys. */
+int gps_sharded_scan_host(gps_shard_group* grp, int algo, int kind, int dtype, const void* h_in,
+                          void* h_out, uint64_t n, uint32_t carry_in_bits, void* h_total_out);
+int gps_sharded_scan_host_async(gps_shard_group* grp, int algo, int kind, int dtype,
+                                const void* h_in, void* h_out, uint64_t n, uint32_t carry_in_bits,
+                                void* h_total_out);
+int gps_sharded_host_sync(gps_shard_group* grp);
 
 #ifdef __cplusplus
 }

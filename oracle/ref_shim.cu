@@ -189,6 +189,39 @@ double ref_time_u32(int algo, int exclusive, uint32_t* d_scan, const uint32_t* d
     return total / batch;
 }
 
+/* Self-contained timing of the reference's kernels for bench.py's reference arm, which must not
+ * load the product library: allocates its own buffers, fills the source with hashed keys in
+ * [0,4) (total < 2^30, the reference CSDL's limit), times CSDL / RTS / cub::DeviceScan with the
+ * protocol above.  out_ms[3] = mean ms per dispatch (negative on error).  Returns 0 or -1. */
+__global__ void ref_shim_fill_small(uint32_t* d, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t h = i * 2654435761u;
+        h ^= h >> 15;
+        h *= 2246822519u;
+        h ^= h >> 13;
+        d[i] = h & 3u;
+    }
+}
+
+int ref_bench_all(uint32_t size, uint32_t batch, double out_ms[3])
+{
+    uint32_t *src = nullptr, *buf = nullptr;
+    out_ms[0] = out_ms[1] = out_ms[2] = -1.0;
+    if (cudaMalloc(&src, (size_t)align4(size) * 4) != cudaSuccess) return -1;
+    if (cudaMalloc(&buf, (size_t)align4(size) * 4) != cudaSuccess) {
+        cudaFree(src);
+        return -1;
+    }
+    ref_shim_fill_small<<<1024, 256>>>(src, size);
+    cudaDeviceSynchronize();
+    const int algos[3] = {0, 1, 3};
+    for (int i = 0; i < 3; ++i) out_ms[i] = ref_time_u32(algos[i], 0, buf, src, size, batch);
+    cudaFree(src);
+    cudaFree(buf);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 void ref_shim_release(void)
 {
     if (g_index) cudaFree(g_index);

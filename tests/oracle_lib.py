@@ -186,8 +186,18 @@ class RefShim:
         lib.ref_time_u32.restype = C.c_double
         lib.ref_time_u32.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
 
+        if hasattr(lib, "ref_bench_all"):
+            lib.ref_bench_all.restype = C.c_int
+            lib.ref_bench_all.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+
     def scan_u32(self, algo: int, exclusive: bool, d_ptr: int, size: int) -> int:
         return self.lib.ref_scan_u32(algo, int(exclusive), d_ptr, size)
+
+    def bench_all(self, size: int, batch: int):
+        """(csdl_ms, rts_ms, cub_ms) of the reference's kernels on the shim's own buffers."""
+        out = (C.c_double * 3)()
+        rc = self.lib.ref_bench_all(size, batch, out)
+        return None if rc else tuple(out)
 
     def time_u32(self, algo: int, exclusive: bool, d_ptr: int, d_src: int | None, size: int, batch: int) -> float:
         return self.lib.ref_time_u32(algo, int(exclusive), d_ptr, d_src, size, batch)

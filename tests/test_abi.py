@@ -96,3 +96,18 @@ def test_host_mirror_keeps_the_reference_class_surface():
         for n in needles:
             assert " ".join(n.split()) in text, (fname, n)
     assert os.path.exists(os.path.join(ROOT, "gpuprefixsums_b200", "bin", "gps_main"))
+
+
+def test_reference_main_compiles_against_the_host_mirror():
+    """The literal drop-in, guarded: the reference's main() with only its #include names swapped
+    (.cuh -> .hpp) compiles against gpuprefixsums_b200/host/ (oracle/Makefile ref_main_dropin).
+    Needs the reference sources, i.e. the build container."""
+    ref = "/root/reference/GPUPrefixSumsCUDA/GPUPrefixSumsCUDA.cu"
+    if not os.path.exists(ref):
+        pytest.skip("reference sources not present")
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-B", os.path.join(ROOT, "oracle", "_ref", "ref_main_dropin")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    syms = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(ROOT, "oracle", "_ref", "ref_main_dropin")],
+                          capture_output=True, text=True).stdout
+    assert "gps_scan" in syms and "gps_scan_emulated_deadlock" in syms  # it really binds the C ABI

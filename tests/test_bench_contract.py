@@ -30,6 +30,30 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("uint32 inclusive scan")
+    assert d["warmup"] == 1, "the reference arm honours --warmup exactly"
+    # the same `config` object as the product arm prints for the same flags
+    sys.path.insert(0, ROOT)
+    import bench
+
+    import argparse
+
+    ns = argparse.Namespace(algo="csdl", log2_keys_per_gpu=22, log2_total=0, carry="p2p")
+    assert d["config"] == bench.workload_config(ns, 1)
+    assert set(d["config"]) == {"workload", "keys_total", "keys_per_gpu", "in_place", "l2"}
+
+
+def test_reference_arm_never_loads_the_product_library():
+    """--impl reference must not map libgps_b200.so (nor import the package) at any point."""
+    code = (
+        "import sys, types; sys.argv=['bench.py','--impl','reference','--steps','1','--warmup','0','--log2-keys-per-gpu','20'];"
+        f"sys.path.insert(0, {ROOT!r}); import bench; bench.main();"
+        "maps=open('/proc/self/maps').read();"
+        "assert 'libgps_b200' not in maps, 'product library mapped in the reference arm';"
+        "assert not any(m.startswith('gpuprefixsums_b200') for m in sys.modules), 'product package imported';"
+        "assert 'liboracle_scan' in maps"
+    )
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box without a GPU")

@@ -33,3 +33,20 @@ def test_gps_main_extensions():
     assert out.stdout.count("All tests passed.") == 3, out.stdout[-3000:]
     assert "Test failed" not in out.stdout and "failed (" not in out.stdout
     assert len(re.findall(r"Estimated speed at \d+ [\w -]+: [0-9.E+]+ per sec", out.stdout)) == 3
+
+
+REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "ref_main_dropin")
+
+
+def test_reference_main_unmodified_runs_on_the_new_library():
+    """The reference's OWN main() (GPUPrefixSumsCUDA.cu:14-38; only its #include lines name the
+    .hpp mirrors), built by oracle/Makefile against host/ and the product library: every
+    TestAll* of the reference passes and the four BatchTiming lines appear."""
+    if not os.path.exists(REF_MAIN):
+        pytest.skip("oracle/_ref/ref_main_dropin not built (needs /root/reference at build time)")
+    out = subprocess.run([REF_MAIN], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("4100/4100 All tests passed.") == 5, out.stdout[-3000:]
+    assert "Test failed" not in out.stdout and "failed (" not in out.stdout
+    speeds = re.findall(r"Estimated speed at 268435456 32-bit elements: ([0-9.E+]+) keys/sec", out.stdout)
+    assert len(speeds) == 4

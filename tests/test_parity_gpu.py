@@ -190,11 +190,20 @@ def test_2p28_random_vs_cub_and_properties(gps, ps, oracle):
     gps.cub_scan(x, ref)  # CUB validated against the oracle on a prefix, then used as device oracle
     assert oracle.check_u32(head, to_np_u32(ref[: 1 << 16]))[0] == 0
     out = torch.empty_like(x)
+    # the whole 2^28-key array against the HOST serial oracle, word for word (0.2 s of CPU): the
+    # default kernel directly, and CUB -- which then serves as the device-side oracle below
+    want, want_total = oracle.scan_u32(to_np_u32(x))
+    assert np.array_equal(to_np_u32(ref), want), "cub::DeviceScan vs host serial scan"
+    ps.scan(x, out, algo="csdl")
+    ps.check()
+    assert np.array_equal(to_np_u32(out), want), "default CSDL vs host serial scan, all 2^28 keys"
+    del want
     for algo in ["csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "rts", "csdl_fallback"]:
         total = torch.zeros(1, dtype=torch.int32, device="cuda")
         ps.scan(x, out, algo=algo, total_out=total)
         ps.check()
         assert gps.compare_u32(out, ref) == (0, n), algo
+        assert int(total.item()) & 0xFFFFFFFF == want_total
         # size-independent properties: out[i] - out[i-1] == x[i] (mod 2^32), total == last
         assert torch.equal(out[1:] - out[:-1], x[1:])
         assert int(total.item()) == int(out[-1].item())
@@ -415,7 +424,7 @@ def test_single_thread_lookback(gps, oracle):
     n = (1 << 23) + 5
     x = oracle.random_u32(n, seed=77)
     want, _ = oracle.scan_u32(x)
-    for algo in ("csdl_smem", "csdl_reg", "csdl_tma"):
+    for algo in ("csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "csdl_fallback", "csdl"):
         out = ps.scan(to_dev_u32(x), algo=algo)
         ps.check()
         assert np.array_equal(to_np_u32(out), want), algo
@@ -439,10 +448,17 @@ def test_descriptor_protocols_and_tile_order(gps, oracle, protocol, tile_order):
     n = (1 << 23) + 777
     x = oracle.random_u32(n, seed=9)
     want, _ = oracle.scan_u32(x, exclusive=True)
-    for algo in ("csdl_smem", "csdl_reg", "csdl_tma"):
+    # the default kernel (blocked tile) and the Decoupled Fallback kernels included: the options
+    # apply to every chained variant (the fallback kernels always take tickets)
+    for algo in ("csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "csdl_fallback", "csdl"):
         out = ps.scan(to_dev_u32(x), algo=algo, exclusive=True)
         ps.check()
         assert np.array_equal(to_np_u32(out), want), (algo, protocol, tile_order)
+    for variant in (1, 2, 3):  # every fallback tile, not only the one the size picks
+        ps.set_option("fallback_variant", variant)
+        out = ps.scan(to_dev_u32(x), algo="csdl_fallback", exclusive=True)
+        ps.check()
+        assert np.array_equal(to_np_u32(out), want), (variant, protocol, tile_order)
     ps.close()
 
 

@@ -14,6 +14,13 @@ SIZES = [1, 2, 3, 31, 255, 256, 257, 4095, 4097, 8191, 8192, 8193, 10_239, 10_24
 
 
 @pytest.fixture(scope="module")
+def gps():
+    import gpuprefixsums_b200 as g
+
+    return g
+
+
+@pytest.fixture(scope="module")
 def ps():
     import gpuprefixsums_b200 as gps
 
@@ -54,15 +61,27 @@ def test_sort_pairs_stable(ps, oracle):
         assert np.array_equal(host(ko), wk) and np.array_equal(host(vo), wv), n
 
 
-@pytest.mark.parametrize("end_bit", [1, 8, 13, 16, 24, 32])
-def test_sort_bit_ranges(ps, oracle, end_bit):
+@pytest.mark.parametrize("end_bit", [1, 5, 8, 9, 13, 16, 17, 24, 29, 32])
+def test_sort_bit_ranges(ps, gps, oracle, end_bit):
+    """A sort on the low end_bit bits is the stable order of key & (2^end_bit - 1) on FULL-RANGE
+    keys -- checked against an independent definition (numpy stable argsort of the masked keys),
+    the oracle, and cub::DeviceRadixSort with the same end_bit."""
     n = 300_007
     x = oracle.random_u32(n, seed=7)
     v = np.arange(n, dtype=np.uint32)
     ko, vo = ps.sort(dev(x), dev(v), end_bit=end_bit)
     ps.check()
+    order = np.argsort(x & np.uint32((1 << end_bit) - 1 if end_bit < 32 else 0xFFFFFFFF), kind="stable")
+    assert np.array_equal(host(ko), x[order]) and np.array_equal(host(vo), v[order])
     wk, wv = oracle.sort_u32(x, v, end_bit=end_bit)
     assert np.array_equal(host(ko), wk) and np.array_equal(host(vo), wv)
+    ck, cv = torch.empty_like(ko), torch.empty_like(vo)
+    gps.cub_sort(dev(x), ck, dev(v), cv, end_bit=end_bit)
+    torch.cuda.synchronize()
+    assert torch.equal(ck, ko) and torch.equal(cv, vo)
+    keys_only = ps.sort(dev(x), end_bit=end_bit)
+    ps.check()
+    assert np.array_equal(host(keys_only), x[order])
 
 
 def test_sort_special_inputs(ps, oracle):
