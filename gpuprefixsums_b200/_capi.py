@@ -96,6 +96,9 @@ SIGNATURES = {
     "gps_sharded_scan_host": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
     "gps_sharded_scan_host_async": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
     "gps_sharded_host_sync": (_i32, [_vp]),
+    "gps_sharded_calibrate_host": (_i32, [_vp, _vp, _vp, _u64, C.POINTER(C.c_float)]),
+    "gps_sharded_set_host_io": (_i32, [_vp, C.POINTER(_i32), _i32]),
+    "gps_sharded_get_host_io": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32)]),
 }
 
 

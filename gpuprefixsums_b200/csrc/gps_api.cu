@@ -1301,6 +1301,7 @@ struct gps_shard_group {
     // q % n; its scan publishes the running total into slot [(q / n) & 1] of GPU (q + 1) % n
     uint64_t host_seq = 0;          // chunks issued so far, over all calls
     uint32_t host_tag = 0;
+    std::vector<int> io;               // GPUs (indices into devices) that carry the host traffic, in chain order
     std::vector<cudaEvent_t> ev_call;  // per GPU; [ev_call_idx] = last scan of the previous call
     int ev_call_idx = -1;              // (orders call boundaries), -1 = none yet
 };
@@ -1348,6 +1349,7 @@ int gps_sharded_create(gps_shard_group** out, int n_gpus, const int* devices, ui
     g->ev0.assign(n_gpus, nullptr);
     g->ev1.assign(n_gpus, nullptr);
     g->ev_call.assign(n_gpus, nullptr);
+    for (int i = 0; i < n_gpus; ++i) g->io.push_back(i);  // default: every GPU takes chunks
     int prev = 0;
     cudaGetDevice(&prev);
     int rc = GPS_OK;
@@ -1496,7 +1498,7 @@ int gps_sharded_scan_host_async(gps_shard_group* g, int algo, int kind, int dtyp
     if (n && (!h_in || !h_out)) return fail(GPS_ERR_INVALID, "null host pointer");
     if (kind != GPS_INCLUSIVE && kind != GPS_EXCLUSIVE) return fail(GPS_ERR_INVALID, "bad kind %d", kind);
     if (dtype != GPS_U32 && dtype != GPS_F32) return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
-    const int G = g->n;
+    const int G = (int)g->io.size();  // GPUs that take chunks (all of them unless calibrated / set otherwise)
     int prev = 0;
     cudaGetDevice(&prev);
     struct Restore {
@@ -1504,7 +1506,8 @@ int gps_sharded_scan_host_async(gps_shard_group* g, int algo, int kind, int dtyp
         ~Restore() { cudaSetDevice(dev); }
     } restore{prev};
     uint64_t chunk = ~0ull;
-    for (int i = 0; i < G; ++i) {
+    for (int j = 0; j < G; ++j) {
+        const int i = g->io[j];
         gps_ctx* c = g->ctx[i];
         GPS_CUDA(cudaSetDevice(g->devices[i]));
         if (int rc = host_pipeline_init(c)) return rc;
@@ -1516,7 +1519,7 @@ int gps_sharded_scan_host_async(gps_shard_group* g, int algo, int kind, int dtyp
     uint32_t prev_tag = 0;
     for (uint64_t k = 0; k < n_chunks; ++k) {
         const uint64_t q = g->host_seq++;
-        const int gi = (int)(q % (uint64_t)G);
+        const int gi = g->io[q % (uint64_t)G];
         gps_ctx* c = g->ctx[gi];
         GPS_CUDA(cudaSetDevice(g->devices[gi]));
         const uint64_t seq = c->host_chunk_seq++;
@@ -1543,14 +1546,14 @@ int gps_sharded_scan_host_async(gps_shard_group* g, int algo, int kind, int dtyp
             // two "GPUs" of the group that are one physical device (tests on a single-GPU box): a
             // scan spinning on its slot could keep its predecessor from ever becoming resident,
             // so there the chain is also a stream dependency
-            const int pi = (int)((q - 1) % (uint64_t)G);
+            const int pi = g->io[(q - 1) % (uint64_t)G];
             if (pi != gi && g->devices[pi] == g->devices[gi])
                 GPS_CUDA(cudaStreamWaitEvent(c->s_cmp, g->ctx[pi]->ev_cmp[(g->ctx[pi]->host_chunk_seq - 1) % kHostBufs], 0));
         }
         prev_tag = tag;
         if (k + 1 < n_chunks) {
             cs.publish.n = 1;
-            cs.publish.dst[0] = g->slots[(gi + 1) % G] + kHostChainSlot0 + ((q / (uint64_t)G) & 1u);
+            cs.publish.dst[0] = g->slots[g->io[(q + 1) % (uint64_t)G]] + kHostChainSlot0 + ((q / (uint64_t)G) & 1u);
             cs.publish.tag = tag;
         } else {
             cs.total_out = c->chain_total;
@@ -1572,6 +1575,111 @@ int gps_sharded_scan_host_async(gps_shard_group* g, int algo, int kind, int dtyp
             g->ev_call_idx = gi;
         }
     }
+    return GPS_OK;
+}
+
+namespace {
+// memcpy-only trial: the GPUs of `set` copy `per_gpu` bytes in from h_src and out to h_dst at the
+// same time (pieces of the pipeline's chunk size, both directions concurrently, each GPU on its
+// own section of the host buffers); returns GB/s per direction over the whole set, <= 0 on error
+double host_io_trial(gps_shard_group* g, const std::vector<int>& set, const char* h_src, char* h_dst, uint64_t per_gpu,
+                     uint64_t piece)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t j = 0; j < set.size(); ++j) {
+        gps_ctx* c = g->ctx[set[j]];
+        if (cudaSetDevice(g->devices[set[j]]) != cudaSuccess) return -1.0;
+        for (uint64_t off = 0; off < per_gpu; off += piece) {
+            const uint64_t len = std::min(piece, per_gpu - off);
+            if (cudaMemcpyAsync(c->stage[0], h_src + j * per_gpu + off, len, cudaMemcpyHostToDevice, c->s_h2d) != cudaSuccess ||
+                cudaMemcpyAsync(h_dst + j * per_gpu + off, c->stage[1], len, cudaMemcpyDeviceToHost, c->s_d2h) != cudaSuccess)
+                return -1.0;
+        }
+    }
+    for (size_t j = 0; j < set.size(); ++j) {
+        gps_ctx* c = g->ctx[set[j]];
+        cudaSetDevice(g->devices[set[j]]);
+        if (cudaStreamSynchronize(c->s_h2d) != cudaSuccess || cudaStreamSynchronize(c->s_d2h) != cudaSuccess) return -1.0;
+    }
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return (double)per_gpu * set.size() / s / 1e9;
+}
+}  // namespace
+
+// Which GPUs should carry the host traffic?  On a multi-socket box the host <-> device paths are
+// not equal and they interfere: on the 8 x B200 VM this was developed on, all eight GPUs copying
+// both ways reach 72 GB/s per direction in total, GPUs 4-7 alone 95, GPUs 0-3 alone 53
+// (profiles/r02_pcie_aggregate.json, r02_pcie_combos.jsonl) -- the scan itself needs a fraction of
+// one GPU.  This measures, memcpy only, on the caller's own buffers: the whole group, then its two
+// halves, descending into a half while it beats its parent by more than 3 %, and routes the chunks
+// of gps_sharded_scan_host through the winner.  h_dst is overwritten with junk (pass the output
+// array of the scan that follows).  Synchronous; a few hundred milliseconds.
+int gps_sharded_calibrate_host(gps_shard_group* g, const void* h_src, void* h_dst, uint64_t bytes, float* h_gbs_each_way)
+{
+    if (!g || !h_src || !h_dst) return fail(GPS_ERR_INVALID, "null argument");
+    int prev = 0;
+    cudaGetDevice(&prev);
+    struct Restore {
+        int dev;
+        ~Restore() { cudaSetDevice(dev); }
+    } restore{prev};
+    uint64_t piece = ~0ull;
+    for (int i = 0; i < g->n; ++i) {
+        GPS_CUDA(cudaSetDevice(g->devices[i]));
+        if (int rc = host_pipeline_init(g->ctx[i])) return rc;
+        if (int rc = gps_host_sync(g->ctx[i])) return rc;
+        piece = std::min(piece, 4 * std::min<uint64_t>(g->ctx[i]->host_chunk_keys, std::max<uint64_t>(g->ctx[i]->max_n, 4096)));
+    }
+    std::vector<int> best(g->n);
+    for (int i = 0; i < g->n; ++i) best[i] = i;
+    const uint64_t volume = std::min<uint64_t>(bytes, 4ull << 30);  // per trial and direction
+    if (volume < 8 * piece) {  // too small to tell anything: keep every GPU
+        g->io = best;
+        if (h_gbs_each_way) *h_gbs_each_way = 0.f;
+        return GPS_OK;
+    }
+    auto measure = [&](const std::vector<int>& set) {
+        const uint64_t per_gpu = (volume / set.size()) & ~(uint64_t)255;
+        double r = 0;
+        for (int rep = 0; rep < 2; ++rep)
+            r = std::max(r, host_io_trial(g, set, static_cast<const char*>(h_src), static_cast<char*>(h_dst), per_gpu, piece));
+        return r;
+    };
+    double best_rate = measure(best);
+    if (best_rate <= 0) return fail(GPS_ERR_CUDA, "host I/O calibration: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    while (best.size() >= 2) {
+        const std::vector<int> lo(best.begin(), best.begin() + best.size() / 2), hi(best.begin() + best.size() / 2, best.end());
+        const double r_lo = measure(lo), r_hi = measure(hi);
+        const std::vector<int>& half = r_hi > r_lo ? hi : lo;
+        const double r_half = std::max(r_lo, r_hi);
+        if (r_half <= 1.03 * best_rate) break;
+        best = half;
+        best_rate = r_half;
+    }
+    g->io = best;
+    if (h_gbs_each_way) *h_gbs_each_way = (float)best_rate;
+    return GPS_OK;
+}
+
+int gps_sharded_set_host_io(gps_shard_group* g, const int* gpu_indices, int n)
+{
+    if (!g || !gpu_indices || n < 1 || n > g->n) return fail(GPS_ERR_INVALID, "bad host I/O set");
+    std::vector<int> io(gpu_indices, gpu_indices + n);
+    for (int i = 0; i < n; ++i) {
+        if (io[i] < 0 || io[i] >= g->n) return fail(GPS_ERR_INVALID, "host I/O index %d out of range", io[i]);
+        for (int j = 0; j < i; ++j)
+            if (io[j] == io[i]) return fail(GPS_ERR_INVALID, "host I/O index %d twice", io[i]);
+    }
+    if (int rc = gps_sharded_host_sync(g)) return rc;  // the chain layout changes: nothing may be in flight
+    g->io = io;
+    return GPS_OK;
+}
+
+int gps_sharded_get_host_io(gps_shard_group* g, int* gpu_indices, int* n)
+{
+    if (!g || !gpu_indices || !n) return fail(GPS_ERR_INVALID, "null argument");
+    *n = (int)g->io.size();
+    for (int i = 0; i < *n; ++i) gpu_indices[i] = g->io[i];
     return GPS_OK;
 }
 

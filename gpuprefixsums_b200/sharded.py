@@ -241,6 +241,26 @@ class ShardedHostScan:
     def sync(self) -> None:
         self.capi.check(self.capi.lib.gps_sharded_host_sync(self._grp))
 
+    def calibrate(self, h_src: torch.Tensor, h_dst: torch.Tensor) -> tuple[list[int], float]:
+        """Measure (memcpy only, on these pinned buffers; h_dst is overwritten with junk) which GPUs
+        should carry the host traffic and route the chunks through them.  Returns (GPU indices into
+        the group, GB/s per direction)."""
+        rate = C.c_float(0)
+        nbytes = min(h_src.numel() * h_src.element_size(), h_dst.numel() * h_dst.element_size())
+        self.capi.check(self.capi.lib.gps_sharded_calibrate_host(self._grp, h_src.data_ptr(), h_dst.data_ptr(), nbytes,
+                                                                 C.byref(rate)))
+        return self.host_io(), float(rate.value)
+
+    def host_io(self) -> list[int]:
+        idx = (C.c_int * len(self.devices))()
+        n = C.c_int(0)
+        self.capi.check(self.capi.lib.gps_sharded_get_host_io(self._grp, idx, C.byref(n)))
+        return list(idx[: n.value])
+
+    def set_host_io(self, indices: list[int]) -> None:
+        arr = (C.c_int * len(indices))(*indices)
+        self.capi.check(self.capi.lib.gps_sharded_set_host_io(self._grp, arr, len(indices)))
+
     def close(self) -> None:
         if self._grp.value:
             self.capi.lib.gps_sharded_destroy(self._grp)

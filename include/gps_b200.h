@@ -323,6 +323,20 @@ int gps_sharded_scan_host_async(gps_shard_group* grp, int algo, int kind, int dt
                                 const void* h_in, void* h_out, uint64_t n, uint32_t carry_in_bits,
                                 void* h_total_out);
 int gps_sharded_host_sync(gps_shard_group* grp);
+/* Which GPUs carry the host traffic of gps_sharded_scan_host (default: all of them, round-robin).
+ * Host <-> device paths of a multi-socket box are neither equal nor independent (on the 8 x B200
+ * VM of profiles/r02_pcie_aggregate.json all eight GPUs copying both ways total 72 GB/s per
+ * direction, GPUs 4-7 alone 95), and the scan needs a fraction of one GPU, so fewer GPUs can be
+ * faster.  gps_sharded_calibrate_host measures it, memcpy only, on the caller's buffers (h_src is
+ * read, h_dst -- `bytes` each, pinned -- is overwritten with junk: pass the arrays of the scan
+ * that follows): the whole group, then halves, descending while a half beats its parent by 3 %;
+ * the winner takes the chunks from then on.  *h_gbs_each_way (nullable) = its copy rate per
+ * direction.  Synchronous, a few hundred ms.  set / get: indices into the group's device list,
+ * in chain order. */
+int gps_sharded_calibrate_host(gps_shard_group* grp, const void* h_src, void* h_dst, uint64_t bytes,
+                               float* h_gbs_each_way);
+int gps_sharded_set_host_io(gps_shard_group* grp, const int* gpu_indices, int n);
+int gps_sharded_get_host_io(gps_shard_group* grp, int* gpu_indices, int* n);
 
 #ifdef __cplusplus
 }

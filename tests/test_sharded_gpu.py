@@ -206,6 +206,44 @@ def test_sharded_scan_host_single_process(oracle, G):
         sh.close()
 
 
+def test_sharded_scan_host_io_routing(oracle):
+    """The chunks may be routed through a subset of the group's GPUs, in any chain order (what the
+    host-I/O calibration decides on boxes with unequal host paths); results do not change."""
+    import gpuprefixsums_b200 as gps
+
+    ndev = torch.cuda.device_count()
+    G = 4
+    sh = gps.ShardedHostScan([i % ndev for i in range(G)], chunk_keys=1 << 15)
+    try:
+        n = 3_000_001
+        x = oracle.random_u32(n, seed=61)
+        want, _ = oracle.scan_u32(x)
+        h_in = torch.from_numpy(x.view(np.int32)).pin_memory()
+        h_out = torch.empty(n, dtype=torch.int32).pin_memory()
+        assert sh.host_io() == [0, 1, 2, 3]
+        for io in ([2, 0], [3], [1, 3, 0], [0, 1, 2, 3]):
+            sh.set_host_io(io)
+            assert sh.host_io() == io
+            for _ in range(2):
+                h_out.fill_(-1)
+                sh.scan_host(h_in, h_out)
+                assert np.array_equal(h_out.numpy().view(np.uint32), want), io
+        with pytest.raises(gps.GpsError):
+            sh.set_host_io([1, 1])
+        with pytest.raises(gps.GpsError):
+            sh.set_host_io([4])
+        # calibration: memcpy-only trials on the caller's buffers, then a scan through the winner
+        io, rate = sh.calibrate(h_in, h_out)
+        assert 1 <= len(io) <= G and rate > 0
+        sh.scan_host(h_in, h_out)
+        assert np.array_equal(h_out.numpy().view(np.uint32), want), ("after calibration", io)
+        # too small to measure: every GPU stays in
+        io, rate = sh.calibrate(h_in[:1000], h_out[:1000])
+        assert io == [0, 1, 2, 3] and rate == 0
+    finally:
+        sh.close()
+
+
 def test_carry_slot_timeout_is_reported_and_contributes_nothing(oracle):
     """A slot whose writer never shows up: the scan gives up after its own (here: tiny) budget,
     adds NOTHING for that slot -- never the mismatched word -- and the error is reported."""

@@ -59,24 +59,25 @@ def main():
     for n in (2, 4, 8):
         if n <= n_gpu:
             sets.append(list(range(n)))
-    if n_gpu >= 8 and not args.quick:
-        sets += [[0, 4], [0, 2], [0, 2, 4, 6], [4, 5, 6, 7], [7]]
-    # 1) the headline matrix: every GPU set, both directions concurrently and each alone
+    # 1) the headline matrix: N = 1, 2, 4, 8 GPUs, both directions concurrently and each alone
     for gpus in sets:
         for d in ("both", "h2d", "d2h"):
             doc["points"].append(probe(gpus, dir=d))
             print(json.dumps(doc["points"][-1]), flush=True)
-    # 2) what might move the ceiling, on the largest set: allocation mode, CPU binding, driver
+    # 2) does it matter WHICH GPUs (PCIe switches / sockets)?
+    if n_gpu >= 8 and not args.quick:
+        for gpus in ([0, 4], [0, 2, 4, 6], [4, 5, 6, 7], [7]):
+            doc["points"].append(probe(gpus, dir="both"))
+            print(json.dumps(doc["points"][-1]), flush=True)
+    # 3) what might move the ceiling, on the largest set: allocation mode, CPU binding, driver
     big = list(range(min(n_gpu, 8)))
     variants = [dict(alloc="huge"), dict(alloc="wc"), dict(bind=1), dict(drive="procs"), dict(drive="procs", bind=1),
-                dict(mib=32), dict(mib=1024)]
+                dict(mib=32)]
     if args.quick:
         variants = variants[:4]
     for v in variants:
         doc["points"].append(probe(big, dir="both", **v))
         print(json.dumps(doc["points"][-1]), flush=True)
-    if not args.quick:
-        doc["points"].append(probe([0], dir="both", alloc="pageable", secs=1.0))
     # summary: aggregate under `both`, default mode, per GPU count
     summ = {}
     for p in doc["points"]:

@@ -8,6 +8,7 @@
 //   gps_pcie_probe --gpus 0,1,2,3 [--dir h2d|d2h|both] [--alloc pinned|wc|huge|pageable]
 //                  [--drive threads|procs] [--mib 256] [--secs 0.6] [--bind 0|1]
 //
+//   --dirs h2d,h2d,d2h,d2h   per-GPU direction (ingress through some GPUs, egress through others)
 //   --alloc  pinned   cudaHostAlloc (what torch.pin_memory and gps_malloc_host use)
 //            wc       cudaHostAllocWriteCombined for the H2D source
 //            huge     2 MiB-aligned anonymous memory + MADV_HUGEPAGE + cudaHostRegister
@@ -46,6 +47,7 @@ struct Shared {
 struct Opts {
     std::vector<int> gpus;
     std::string dir = "both", alloc = "pinned", drive = "threads";
+    std::vector<std::string> dirs;  // optional per-GPU direction (h2d | d2h | both), overrides dir
     size_t mib = 256;
     double secs = 0.6;
     int bind = 0;
@@ -122,7 +124,8 @@ bool worker(const Opts& o, int slot, Shared* sh, int* phase)
     if (o.bind) bind_to_gpu_cpus(gpu);
     CK(cudaSetDevice(gpu));
     const size_t bytes = o.mib << 20;
-    const bool up = o.dir != "d2h", down = o.dir != "h2d";
+    const std::string& mydir = slot < (int)o.dirs.size() ? o.dirs[slot] : o.dir;
+    const bool up = mydir != "d2h", down = mydir != "h2d";
     void *h_src = nullptr, *h_dst = nullptr, *f1 = nullptr, *f2 = nullptr, *d_a = nullptr, *d_b = nullptr;
     int k1 = 0, k2 = 0;
     if (up && !alloc_host(o, bytes, true, &h_src, &f1, &k1)) return false;
@@ -216,6 +219,16 @@ int main(int argc, char** argv)
                 o.gpus.push_back(atoi(v.substr(p, q - p).c_str()));
                 p = q + 1;
             }
+        } else if (a == "--dirs") {  // per GPU, e.g. h2d,h2d,d2h,d2h
+            std::string v = val();
+            size_t p = 0;
+            while (p < v.size()) {
+                size_t q = v.find(',', p);
+                if (q == std::string::npos) q = v.size();
+                o.dirs.push_back(v.substr(p, q - p));
+                p = q + 1;
+            }
+            o.dir = "mixed";
         } else if (a == "--dir") o.dir = val();
         else if (a == "--alloc") o.alloc = val();
         else if (a == "--drive") o.drive = val();
