@@ -77,6 +77,8 @@ struct gps_ctx {
     bool rts_blocked_configured[2][2] = {{false, false}, {false, false}};
     int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile, 3 blocked tile
     int rts_variant = 0;            // 0 auto, 1 register-tile propagate, 2 blocked-tile propagate
+    int l2_hints = -1;              // -1 auto, else PF_L2_* bits (bit 0 loads evict_first, bit 1 stores evict_last)
+    uint64_t l2_bytes = 0;          // L2 size of the device
     bool wide_configured[5][2][2] = {};             // [dtype][kind][rts]
     // host pipeline (lazy)
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
@@ -347,6 +349,20 @@ int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, voi
         rc = cap.begin(c, st, CaptureScope::SCAN);
         if (rc) return rc;
     }
+    // L2 policies (gps_common.cuh): auto = evict_first loads while the output is 38..76 % of the L2 (gps_config.h)
+    struct FlagScope {
+        uint32_t& f;
+        const uint32_t saved;
+        ~FlagScope() { f = saved; }
+    } l2scope{c->s.flags, c->s.flags};
+    {
+        uint32_t bits = 0;
+        if (c->l2_hints >= 0) bits = (uint32_t)c->l2_hints;
+        else if (n * 4 <= c->l2_bytes * GPS_L2_HINT_MAX_OUT_PCT / 100 && n * 4 >= c->l2_bytes * GPS_L2_HINT_MIN_OUT_PCT / 100)
+            bits = GPS_L2_HINT_AUTO_BITS;
+        c->s.flags = (c->s.flags & ~(PF_L2_IN_EVICT_FIRST | PF_L2_OUT_EVICT_LAST)) |
+                     ((bits & 1u) ? PF_L2_IN_EVICT_FIRST : 0u) | ((bits & 2u) ? PF_L2_OUT_EVICT_LAST : 0u);
+    }
     if (dtype == GPS_U32)
         return kind == GPS_INCLUSIVE ? dispatch_scan_tk<uint32_t, true>(c, algo, in, out, n, cs, st)
                                      : dispatch_scan_tk<uint32_t, false>(c, algo, in, out, n, cs, st);
@@ -548,6 +564,7 @@ int gps_create_with_scratch(gps_ctx** out, int device, uint64_t max_n, void* d_s
     c->device = device;
     c->max_n = max_n;
     c->s.sm_count = prop.multiProcessorCount;
+    c->l2_bytes = (uint64_t)prop.l2CacheSize;
     c->s.flags |= PF_PDL;  // programmatic dependent launch by default (option "pdl")
     c->owns_scratch = d_scratch == nullptr;
     cudaError_t e = cudaSuccess;
@@ -568,6 +585,7 @@ int gps_create_with_scratch(gps_ctx** out, int device, uint64_t max_n, void* d_s
     c->s.wdesc_words = L.wdesc_words;
     c->s.counter = reinterpret_cast<uint32_t*>(base + L.off_counter);
     c->s.status = c->s.counter + 1;
+    c->s.reduce_acc = c->s.counter + 8;  // 33 words of the same zero-initialised 256-byte block
     c->g_desc = reinterpret_cast<uint64_t*>(base + L.off_gdesc);
     c->g_wdesc = reinterpret_cast<uint64_t*>(base + L.off_gwdesc);
     c->g_counter = reinterpret_cast<uint32_t*>(base + L.off_gcounter);
@@ -671,6 +689,12 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     } else if (!strcmp(key, "poll_sleep_ns")) {
         if (value < 0 || value > 100000) return fail(GPS_ERR_INVALID, "poll_sleep_ns out of range");
         c->s.poll_sleep_ns = (uint32_t)value;
+    } else if (!strcmp(key, "l2_hints")) {
+        // L2 cache policies on the tile loads / stores of the smem-resident kernels: -1 = auto (default:
+        // both for inputs whose output fits the L2, see dispatch), 0 = off, bit 0 = loads evict_first,
+        // bit 1 = stores evict_last
+        if (value < -1 || value > 3) return fail(GPS_ERR_INVALID, "l2_hints must be -1..3");
+        c->l2_hints = (int)value;
     } else if (!strcmp(key, "slot_wait_polls")) {
         // polls tile 0 / the spine may spend on one carry slot before giving up (0 = default 2^26,
         // more than a minute); tests use a small value to exercise the timeout path

@@ -84,6 +84,8 @@ enum : uint32_t {
     PF_LOOKBACK_WAIT_ALL = 512u, // experiment: consume a window only when all 32 are ready
     PF_LOOKBACK_SINGLE = 1024u,  // one-thread look-back (reference LookbackSingle, CSDL.cuh:28-47)
     PF_PDL = 4096u,              // host: launch with programmatic stream serialization (see pdl_entry)
+    PF_L2_IN_EVICT_FIRST = 8192u,   // tile loads carry an L2 evict_first policy (input is read once)
+    PF_L2_OUT_EVICT_LAST = 16384u,  // tile stores carry an L2 evict_last policy (output stays for the consumer)
 };
 
 enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
@@ -91,6 +93,10 @@ enum : uint32_t { STATUS_WATCHDOG = 1u, STATUS_SLOT_TIMEOUT = 2u };
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 // CTAs per SM the scan kernels are compiled for: as many as fit at `regs` registers/thread
 constexpr int min_ctas_per_sm(int nt, int regs = 40) { return 65536 / (nt * regs) > 0 ? 65536 / (nt * regs) : 1; }
+#ifndef GPS_LOOKBACK_MAXWIN
+#define GPS_LOOKBACK_MAXWIN 1  // windows per round trip a far-behind look-back may grow to (1 = never grow);
+                               // measured: growth LOSES at every size (2^24 keys: 27.1 / 27.6 / 30.3 / 34.6 us for 1 / 2 / 4 / 8)
+#endif
 constexpr uint32_t kWatchdogPolls = 1u << 22;  // * ~0.5 us per poll => seconds, then bail out
 
 // ---------------------------------------------------------------------------------
@@ -280,6 +286,62 @@ __device__ __forceinline__ void bulk_wait()
 {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// ---- L2 cache policies (createpolicy) for inputs whose output fits the 126 MB L2 ------------
+// A scan reads its input exactly once and produces an output somebody reads next.  For mid-size
+// inputs (output <= ~L2) the loads are tagged evict_first and the stores evict_last: the input
+// streams through without pushing the freshly written output out of L2, so the output is never
+// written to DRAM while it is still wanted -- by the consumer, or by the next scan that overwrites
+// it.  Measured: DESIGN.md (mid-size regime).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                               uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_addr(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst),
+                 "r"(smem_addr(smem_src)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream_hint(uint4* p, const uint4& v, uint64_t policy)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+                 : "memory");
+}
+// tile load / store that honour the PF_L2_* flags (warp-uniform)
+__device__ __forceinline__ void tile_bulk_load(uint32_t flags, void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                               uint64_t* bar)
+{
+    if (flags & PF_L2_IN_EVICT_FIRST)
+        bulk_load_hint(smem_dst, gmem_src, bytes, bar, l2_policy_evict_first());
+    else
+        bulk_load(smem_dst, gmem_src, bytes, bar);
+}
+__device__ __forceinline__ void tile_bulk_store(uint32_t flags, void* gmem_dst, const void* smem_src, uint32_t bytes)
+{
+    if (flags & PF_L2_OUT_EVICT_LAST)
+        bulk_store_hint(gmem_dst, smem_src, bytes, l2_policy_evict_last());
+    else
+        bulk_store(gmem_dst, smem_src, bytes);
+}
+
 // make generic-proxy shared-memory writes visible to the async proxy (TMA store)
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
@@ -485,7 +547,9 @@ struct LookbackStats {
 
 // WIN = descriptor windows (of 32 tiles) fetched per round trip: the WIN loads of a lane
 // are issued back to back, so one L2 round trip covers 32*WIN predecessors.
-template <typename T, int WIN = 2>
+// MAXWIN = how many windows per round trip a far-behind walk may grow to (see below); the kernels
+// whose tile lives in registers keep MAXWIN = WIN (no spare registers for the extra descriptors)
+template <typename T, int WIN = 2, int MAXWIN_ = 0>
 __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, uint32_t lane,
                                            LookbackStats* stats = nullptr)
 {
@@ -519,15 +583,24 @@ __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, u
         return prefix;
     }
     const bool wait_all = p.flags & PF_LOOKBACK_WAIT_ALL;
+    // Windows fetched per L2 round trip.  One window is the measured optimum (the nearest tiles
+    // decide; more polls only add traffic).  A walk that consumed a whole round of AGGREGATEs without
+    // meeting an INCLUSIVE MAY double its reach every round, up to MAXWIN windows (a round that
+    // stops at a tile that is not ready falls back to WIN) -- an experiment aimed at the burst of
+    // ~1800 tiles that start together at launch.  It lost at every size (profiles/
+    // r02_midsize.txt), so MAXWIN defaults to WIN; the mid-size gap is the tail of the last wave,
+    // not the depth of the walks.
+    constexpr int MAXWIN = MAXWIN_ > WIN ? MAXWIN_ : WIN;
+    int nwin = WIN;
     while (true) {
-        uint64_t d[WIN];
-        bool ready[WIN];
+        uint64_t d[MAXWIN];
+        bool ready[MAXWIN];
 #pragma unroll
-        for (int w = 0; w < WIN; ++w) {
+        for (int w = 0; w < MAXWIN; ++w) {
             const int64_t idx = top - 32 * w - (int64_t)lane;
             d[w] = pack_desc(0u, p.epoch, ST_INCLUSIVE);  // virtual entry below tile 0
             ready[w] = true;
-            if (idx >= 0) {
+            if (w < nwin && idx >= 0) {
                 d[w] = desc_poll(p, p.desc + idx);
                 ready[w] = desc_valid(d[w], p.epoch);
             }
@@ -535,9 +608,10 @@ __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, u
         // consume the run of ready descriptors nearest to this tile; an INCLUSIVE one in
         // that run ends the walk no matter what farther tiles are doing
         uint32_t consumed = 0;
-        bool done = false;
+        bool done = false, stopped = false;
 #pragma unroll
-        for (int w = 0; w < WIN; ++w) {
+        for (int w = 0; w < MAXWIN; ++w) {
+            if (w >= nwin) break;
             const uint32_t not_ready = __ballot_sync(kFullMask, !ready[w]);
             const uint32_t run = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
             const uint32_t in_run = run >= 32u ? kFullMask : ((1u << run) - 1u);
@@ -550,15 +624,22 @@ __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, u
                 done = true;
                 break;
             }
-            if (run < 32u && wait_all) break;  // reference behaviour: all 32 or nothing
+            if (run < 32u && wait_all) {  // reference behaviour: all 32 or nothing
+                stopped = true;
+                break;
+            }
             if (run) {
                 prefix += warp_reduce(lane < run ? v : T(0));
                 consumed += run;
             }
-            if (run < 32u) break;
+            if (run < 32u) {
+                stopped = true;
+                break;
+            }
         }
         windows += (consumed + 31u) / 32u + (done ? 1u : 0u);
         if (done) break;
+        nwin = stopped ? WIN : (2 * nwin < MAXWIN ? 2 * nwin : MAXWIN);
         if (consumed == 0u) {
             const bool bail = watchdog_tick(polls, p.status);
             if (__any_sync(kFullMask, bail)) break;  // warp-uniform exit

@@ -15,8 +15,10 @@
 #endif
 // below this many keys the scan is launch/latency bound and smaller tiles win
 // (2^20 keys: <256,4> 6.4 us vs <128,12> 8.2 us; equal at 2^21..2^23; <128,12> ahead from 2^24)
+// (round 2, with programmatic dependent launch: 2^22 keys <256,4> 8.7 us, smem<128,8> 10.7 us; from
+// 2^23 the smem-resident tile is ahead, 12.9 vs 16.2 us)
 #ifndef GPS_REG_SMALL_MAX_N
-#define GPS_REG_SMALL_MAX_N (1u << 21)
+#define GPS_REG_SMALL_MAX_N (1u << 22)
 #endif
 #ifndef GPS_REG_SMALL_NT
 #define GPS_REG_SMALL_NT 256
@@ -146,4 +148,21 @@
 // window before the CTA recomputes the blocking tile itself
 #ifndef GPS_FALLBACK_DEFAULT_SPIN
 #define GPS_FALLBACK_DEFAULT_SPIN 64
+#endif
+
+// L2 cache policies on the tile loads (evict_first) and stores (evict_last) of the smem-resident
+// CSDL kernels, option "l2_hints" = -1 (auto): applied while the output is at most this many
+// percent of the device's L2 (and at least MIN percent); which bits auto uses
+// Measured (tools/l2_hint_sweep.py, profiles/r02_midsize.txt): evict_first loads help only where
+// input + output are about the size of the L2 -- 2^24 keys: 26.0 -> 24.4 us (the output then stays
+// in L2 and is overwritten there by the next scan); 2^23: 13.3 -> 15.0 us (worse), 2^25 and up:
+// neutral to -3 %; evict_last stores lose everywhere.  Hence a band around 2^24.
+#ifndef GPS_L2_HINT_MIN_OUT_PCT
+#define GPS_L2_HINT_MIN_OUT_PCT 38
+#endif
+#ifndef GPS_L2_HINT_MAX_OUT_PCT
+#define GPS_L2_HINT_MAX_OUT_PCT 76
+#endif
+#ifndef GPS_L2_HINT_AUTO_BITS
+#define GPS_L2_HINT_AUTO_BITS 1
 #endif

@@ -32,11 +32,12 @@ struct BlockedTile {
 
     // called by ONE thread: arm the mbarrier and start the TMA bulk load of a full tile
     __device__ __forceinline__ static void issue_load(uint4* s_data, uint64_t* s_bar, const void* in, uint32_t tile,
-                                                      uint64_t n)
+                                                      uint64_t n, uint32_t flags = 0u)
     {
         if (((uint64_t)tile + 1u) * TILE_KEYS <= n) {
             mbar_arrive_expect_tx(s_bar, TILE_BYTES);
-            bulk_load(s_data, reinterpret_cast<const unsigned char*>(in) + (uint64_t)tile * TILE_BYTES, TILE_BYTES, s_bar);
+            tile_bulk_load(flags, s_data, reinterpret_cast<const unsigned char*>(in) + (uint64_t)tile * TILE_BYTES,
+                           TILE_BYTES, s_bar);
         }
     }
     // all threads: wait for the TMA (full tile) or fill this thread's own uint4 with guarded
@@ -74,7 +75,7 @@ struct BlockedTile {
     // TMA bulk store (full tile) or a guarded coalesced copy (partial tile)
     template <bool INCLUSIVE>
     __device__ __forceinline__ static void finish(uint4* s_data, uint32_t v0, T run, void* out, uint32_t tile,
-                                                  uint64_t n, bool full, uint32_t warp, uint32_t lane)
+                                                  uint64_t n, bool full, uint32_t warp, uint32_t lane, uint32_t flags = 0u)
     {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -101,8 +102,8 @@ struct BlockedTile {
             fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
             __syncwarp();
             if (lane == 0) {
-                bulk_store(reinterpret_cast<unsigned char*>(out) + warp_vec0 * 16u, s_data + warp * WARP_VEC,
-                           WARP_VEC * 16u);
+                tile_bulk_store(flags, reinterpret_cast<unsigned char*>(out) + warp_vec0 * 16u, s_data + warp * WARP_VEC,
+                                WARP_VEC * 16u);
                 bulk_commit();
                 bulk_wait_read<0>();  // shared memory must outlive the engine's read
             }
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
         fence_mbar_init();
         const uint32_t t = (p.flags & PF_STATIC_TILE) ? blockIdx.x : claim_tile(p);
         s_tile = t;
-        Tile::issue_load(s_data, &s_bar, p.in, t, p.n);
+        Tile::issue_load(s_data, &s_bar, p.in, t, p.n, p.flags);
     }
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
         if (tile == 0)
             prefix = acquire_carry<T>(p, lane);
         else
-            prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T, WIN>(p, tile, lane);
+            prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T, WIN, GPS_LOOKBACK_MAXWIN>(p, tile, lane);
         if (lane == 0) {
             const T inclusive = prefix + aggregate;
             desc_publish(p, p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     __syncthreads();
 
     Tile::template finish<INCLUSIVE>(s_data, v0, (s_prefix + warp_prefix) + thread_excl, p.out, tile, p.n, full, warp,
-                                     lane);
+                                     lane, p.flags);
 }
 
 }  // namespace gps

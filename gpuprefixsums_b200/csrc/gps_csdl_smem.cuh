@@ -26,9 +26,11 @@ namespace gps {
 // the prefix, store with coalesced 128-bit stores; `run0` = tile prefix + warp prefix
 template <typename T, int V, bool INCLUSIVE, int G>
 __device__ __forceinline__ void smem_tile_finish(const uint4* s_data, uint32_t row0, uint64_t vbase, bool full,
-                                                 uint64_t n, void* out, uint32_t lane, T run0)
+                                                 uint64_t n, void* out, uint32_t lane, T run0, uint32_t flags = 0u)
 {
     T run = run0;
+    const bool keep = flags & PF_L2_OUT_EVICT_LAST;  // warp-uniform
+    const uint64_t pol = keep ? l2_policy_evict_last() : 0ull;
     uint4* out4 = reinterpret_cast<uint4*>(out);
     uint32_t* out1 = reinterpret_cast<uint32_t*>(out);
 #pragma unroll 1
@@ -75,7 +77,10 @@ __device__ __forceinline__ void smem_tile_finish(const uint4* s_data, uint32_t r
                 const uint4 r = make_uint4(to_bits(o0), to_bits(o1), to_bits(o2), to_bits(o3));
                 const uint64_t v = vbase + 32u * (k0 + g);
                 if (full || (v + 1u) * 4u <= n) {
-                    stg_stream(out4 + v, r);
+                    if (keep)
+                        stg_stream_hint(out4 + v, r, pol);
+                    else
+                        stg_stream(out4 + v, r);
                 } else {
                     const uint64_t e = v * 4u;
                     if (e + 0 < n) out1[e + 0] = r.x;
@@ -114,8 +119,8 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
         s_tile = t;
         if (((uint64_t)t + 1u) * TILE_KEYS <= p.n) {
             mbar_arrive_expect_tx(&s_bar, TILE_BYTES);
-            bulk_load(s_data, reinterpret_cast<const unsigned char*>(p.in) + (uint64_t)t * TILE_BYTES,
-                      TILE_BYTES, &s_bar);
+            tile_bulk_load(p.flags, s_data, reinterpret_cast<const unsigned char*>(p.in) + (uint64_t)t * TILE_BYTES,
+                           TILE_BYTES, &s_bar);
         }
     }
     __syncthreads();
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
         if (tile == 0)
             prefix = acquire_carry<T>(p, lane);
         else
-            prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T, WIN>(p, tile, lane);
+            prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T, WIN, GPS_LOOKBACK_MAXWIN>(p, tile, lane);
         if (lane == 0) {
             const T inclusive = prefix + aggregate;
             desc_publish(p, p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     }
     __syncthreads();
 
-    smem_tile_finish<T, V, INCLUSIVE, G>(s_data, row0, vbase, full, p.n, p.out, lane, s_prefix + warp_prefix);
+    smem_tile_finish<T, V, INCLUSIVE, G>(s_data, row0, vbase, full, p.n, p.out, lane, s_prefix + warp_prefix, p.flags);
 }
 
 // ---------------------------------------------------------------------------------

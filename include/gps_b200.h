@@ -116,6 +116,10 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   their CTAs become resident while the stream's previous kernel drains and
  *                   wait for it to complete before touching memory), 0 = plain launches
  *   "poll_sleep_ns" nanosleep between unsuccessful descriptor polls (default 0)
+ *   "l2_hints"      L2 cache policies on the tile loads / stores of the smem-resident kernels:
+ *                   -1 = auto (default: evict_first loads when input + output are about the size of
+ *                   the L2, measured +6 % at 2^24 keys), 0 = off, bit 0 = loads evict_first, bit 1 =
+ *                   stores evict_last
  *   "slot_wait_polls" polls a scan may spend waiting for ONE carry slot (gps_scan_carry_slots,
  *                   the host pipelines) before it gives up: default 0 = 2^26 polls, over a minute
  *                   -- the writer may be a peer process that is legitimately late.  A slot that

@@ -92,6 +92,8 @@ struct Env {
     bool prof_enabled = false;
     unsigned long long* prof_buf = nullptr;
     double sm_ghz = 1.965;
+    void* flush_buf = nullptr;  // --flush: written before every timed launch (cold L2), launches timed one by one
+    size_t flush_bytes = 0;
 };
 
 struct Result {
@@ -157,13 +159,27 @@ static Result run_variant(Env& env, const char* name, bool verify, const LaunchF
     // timing: out-of-place, back to back (2 GiB of traffic per launch at 2^28 >> L2)
     for (int i = 0; i < 3; ++i) fn(env.in, env.out);
     CK(cudaDeviceSynchronize());
-    CK(cudaEventRecord(env.e0));
-    for (int i = 0; i < env.iters; ++i) fn(env.in, env.out);
-    CK(cudaEventRecord(env.e1));
-    CK(cudaEventSynchronize(env.e1));
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, env.e0, env.e1));
-    r.ms_mean = ms / env.iters;
+    if (env.flush_buf) {  // cold L2: flush, then time ONE launch with its own pair of events
+        double sum = 0;
+        for (int i = 0; i < env.iters; ++i) {
+            CK(cudaMemsetAsync(env.flush_buf, i & 0xFF, env.flush_bytes));
+            CK(cudaEventRecord(env.e0));
+            fn(env.in, env.out);
+            CK(cudaEventRecord(env.e1));
+            CK(cudaEventSynchronize(env.e1));
+            CK(cudaEventElapsedTime(&ms, env.e0, env.e1));
+            sum += ms;
+        }
+        r.ms_mean = sum / env.iters;
+    } else {
+        CK(cudaEventRecord(env.e0));
+        for (int i = 0; i < env.iters; ++i) fn(env.in, env.out);
+        CK(cudaEventRecord(env.e1));
+        CK(cudaEventSynchronize(env.e1));
+        CK(cudaEventElapsedTime(&ms, env.e0, env.e1));
+        r.ms_mean = ms / env.iters;
+    }
     // in place timing
     double ms_inplace = 0;
     if (inplace_too) {
@@ -449,6 +465,36 @@ static int run_all(Env& env, const char* filter)
             CarrySpec cs;
             return launch_csdl_blocked<T, 256, 5, INCL, 1>(env.s, in, out, env.n, cs, cfg_g, 0);
         });
+        // mid-size ladder (round 2): more tile shapes between 8 and 28 KB
+        static bool cfg_h = false, cfg_i = false, cfg_j = false, cfg_k = false, cfg_l = false, cfg_m = false, cfg_n = false;
+        sv.emplace_back("sweep/csdl_smem<128,6>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_smem<T, 128, 6, INCL, 1>(env.s, in, out, env.n, cs, cfg_h, 0);
+        });
+        sv.emplace_back("sweep/csdl_smem<128,12>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_smem<T, 128, 12, INCL, 1>(env.s, in, out, env.n, cs, cfg_i, 0);
+        });
+        sv.emplace_back("sweep/csdl_smem<64,8>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_smem<T, 64, 8, INCL, 1>(env.s, in, out, env.n, cs, cfg_j, 0);
+        });
+        sv.emplace_back("sweep/csdl_blocked<128,7>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 128, 7, INCL, 1>(env.s, in, out, env.n, cs, cfg_k, 0);
+        });
+        sv.emplace_back("sweep/csdl_blocked<256,7>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 256, 7, INCL, 1>(env.s, in, out, env.n, cs, cfg_l, 0);
+        });
+        sv.emplace_back("sweep/csdl_blocked<256,3>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 256, 3, INCL, 1>(env.s, in, out, env.n, cs, cfg_m, 0);
+        });
+        sv.emplace_back("sweep/csdl_blocked<128,11>", [&](const void* in, void* out) {
+            CarrySpec cs;
+            return launch_csdl_blocked<T, 128, 11, INCL, 1>(env.s, in, out, env.n, cs, cfg_n, 0);
+        });
         sv.emplace_back("sweep/csdl_tma<512,S2>", [&](const void* in, void* out) {
             CarrySpec cs;
             return launch_csdl_tma<T, 512, 2, INCL, 1>(env.s, in, out, env.n, cs, occ_t, 0, 0);
@@ -529,6 +575,7 @@ static int run_all(Env& env, const char* filter)
             {"exp/reg<256,4>/fence_all", PF_FENCE_ALL, true},
             {"exp/reg<256,4>/ld_allocate", PF_LD_ALLOCATE, true},
         };
+        const uint32_t pdl_base = env.s.flags & PF_PDL;  // experiments keep the launch mode of the run
         for (auto& ex : exps) {
             env.s.flags = ex.flags;
             run_variant(env, ex.name, ex.verify, [&](const void* in, void* out) {
@@ -545,8 +592,8 @@ static int run_all(Env& env, const char* filter)
                 return launch_csdl_reg<T, 64, 24, INCL, 1>(env.s, in, out, env.n, cs, 0);
             });
         }
-        for (uint32_t fl : {(uint32_t)PF_STATIC_TILE, (uint32_t)PF_SKIP_LOOKBACK, (uint32_t)(PF_SKIP_LOOKBACK | PF_STATIC_TILE), (uint32_t)PF_LOOKBACK_SINGLE, (uint32_t)PF_LOOKBACK_WAIT_ALL}) {
-            env.s.flags = fl;
+        for (uint32_t fl : {0u, (uint32_t)PF_STATIC_TILE, (uint32_t)PF_SKIP_LOOKBACK, (uint32_t)(PF_SKIP_LOOKBACK | PF_STATIC_TILE), (uint32_t)PF_LOOKBACK_SINGLE, (uint32_t)PF_LOOKBACK_WAIT_ALL}) {
+            env.s.flags = fl | pdl_base;
             char name[96];
             static bool cfgx = false;
             snprintf(name, sizeof(name), "exp/smem<128,8>/flags%u", fl);
@@ -574,7 +621,7 @@ static int run_all(Env& env, const char* filter)
                 return launch_csdl_reg<T, 256, 4, INCL>(env.s, in, out, env.n, cs, 0);
             });
         }
-        env.s.flags = 0;
+        env.s.flags = pdl_base;
         env.s.poll_sleep_ns = 0;
     }
     return bad;
@@ -584,8 +631,8 @@ int main(int argc, char** argv)
 {
     Env env;
     const char* filter = nullptr;
-    bool sweep = false, pdl = false;
-    int max_log2n = 30;
+    bool sweep = false, pdl = false, flush = false;
+    int max_log2n = 30, min_log2n = 10;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--log2n") && i + 1 < argc) env.n = 1ull << atoi(argv[++i]);
         else if (!strcmp(argv[i], "--n") && i + 1 < argc) env.n = strtoull(argv[++i], nullptr, 10);
@@ -597,6 +644,8 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--max-log2n") && i + 1 < argc) max_log2n = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--exclusive")) env.exclusive = true;
         else if (!strcmp(argv[i], "--pdl")) pdl = true;
+        else if (!strcmp(argv[i], "--flush")) flush = true;
+        else if (!strcmp(argv[i], "--min-log2n") && i + 1 < argc) min_log2n = atoi(argv[++i]);
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
             return 2;
@@ -625,6 +674,10 @@ int main(int argc, char** argv)
     env.sm_ghz = prop.clockRate / 1e6;
     CK(cudaEventCreate(&env.e0));
     CK(cudaEventCreate(&env.e1));
+    if (flush) {
+        env.flush_bytes = 512ull << 20;  // 4 x the 126 MB L2
+        CK(cudaMalloc(&env.flush_buf, env.flush_bytes));
+    }
     if (env.is_float)
         init_random_f32_kernel<<<2048, 256>>>((float*)env.in, env.n, 1234, 0);
     else
@@ -636,7 +689,8 @@ int main(int argc, char** argv)
         // were allocated for env.n = 2^max.  n <= 2^23: in + out fit the 126 MB L2 ("L2-resident")
         const uint64_t n_max = env.n;
         int bad_total = 0;
-        for (int lg = 10; (1ull << lg) <= n_max; ++lg) {
+        (void)max_log2n;
+        for (int lg = min_log2n; (1ull << lg) <= n_max; ++lg) {
             env.n = 1ull << lg;
             env.iters = lg <= 20 ? 200 : lg <= 24 ? 100 : 30;
             bad_total += env.is_float ? run_all<float, true>(env, filter ? filter : "sweep")
