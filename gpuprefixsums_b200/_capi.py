@@ -53,8 +53,10 @@ SIGNATURES = {
     "gps_scratch_bytes": (_u64, [_u64]),
     "gps_scan": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gps_scan_wide": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "gps_scan_wide_emulated_deadlock": (_i32, [_vp, _i32, _i32, _vp, _vp, _u64, _vp, _u32, _u32, _vp, _vp]),
     "gps_sort_scratch_bytes": (_u64, [_u64]),
     "gps_sort_keys32": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _vp]),
+    "gps_sort_keys32_fallback": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _u32, _u32, _vp, _vp]),
     "gps_sort_u32": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _i32, _vp]),
     "gps_scan_carry_slots": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _u32, _u32, _u32, _vp, _vp]),
     "gps_reduce": (_i32, [_vp, _i32, _vp, _u64, _vp, _vp]),

@@ -79,7 +79,7 @@ struct gps_ctx {
     int rts_variant = 0;            // 0 auto, 1 register-tile propagate, 2 blocked-tile propagate
     int l2_hints = -1;              // -1 auto, else PF_L2_* bits (bit 0 loads evict_first, bit 1 stores evict_last)
     uint64_t l2_bytes = 0;          // L2 size of the device
-    bool wide_configured[5][2][2] = {};             // [dtype][kind][rts]
+    bool wide_configured[5][2][3] = {};             // [dtype][kind][chained | rts | fallback]
     // host pipeline (lazy)
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
     void* stage[kHostBufs] = {nullptr, nullptr, nullptr};
@@ -108,7 +108,7 @@ struct gps_ctx {
     uint64_t sort_desc_tiles = 0;
     uint32_t* sort_hist = nullptr;
     uint32_t sort_epoch = 0;
-    bool sort_configured[4] = {false, false, false, false};  // [pairs + 2 * key-map variant]
+    bool sort_configured[8] = {};   // [pairs + 2 * key-map variant + 4 * Decoupled Fallback]
     bool sort_hist_configured = false;
 };
 
@@ -385,7 +385,7 @@ inline uint64_t wide_desc_words(uint64_t max_n) { return std::max<uint64_t>(1, d
 
 template <typename E, bool INCL>
 int launch_wide(gps_ctx* c, int algo, const void* in, void* out, uint64_t n, const void* h_carry, void* total_out,
-                bool& configured, cudaStream_t st)
+                bool& configured, cudaStream_t st, const WideFallbackParams* fbp = nullptr)
 {
     using S = WideShape<E, GPS_WIDE_NT, GPS_WIDE_V>;
     Scratch& s = c->s;
@@ -419,6 +419,22 @@ int launch_wide(gps_ctx* c, int algo, const void* in, void* out, uint64_t n, con
         GPS_CUDA(launch_scan_kernel(wide_reduce_kernel<E, GPS_WIDE_NT, GPS_WIDE_V>, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p));
         GPS_CUDA(launch_scan_kernel(wide_spine_kernel<E>, 1, 1024, 0, st, pdl, p));
         GPS_CUDA(launch_scan_kernel(kern, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p));
+    } else if (algo == GPS_ALGO_CSDL_FALLBACK) {
+        auto kern = wide_scan_fallback_kernel<E, GPS_WIDE_NT, GPS_WIDE_V, INCL, GPS_WIDE_FB_REGS>;
+        if (!configured) {
+            GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+            configured = true;
+        }
+        if (++s.wepoch == 0) {
+            GPS_CUDA(cudaMemsetAsync(s.wdesc, 0, (size_t)s.wdesc_words * sizeof(uint64_t), st));
+            s.wepoch = 1;
+        }
+        p.epoch = s.wepoch;
+        const WideFallbackParams f = fbp ? *fbp : WideFallbackParams{0xFFFFFFFFu, GPS_FALLBACK_DEFAULT_SPIN, nullptr};
+        const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p, f);
+        if (e == cudaSuccess) s.counter_base += p.num_tiles;  // one claim per CTA
+        GPS_CUDA(e);
     } else {
         auto kern = wide_scan_kernel<E, GPS_WIDE_NT, GPS_WIDE_V, INCL, true, GPS_WIDE_REGS>;
         if (!configured) {
@@ -431,8 +447,9 @@ int launch_wide(gps_ctx* c, int algo, const void* in, void* out, uint64_t n, con
             s.wepoch = 1;
         }
         p.epoch = s.wepoch;
-        GPS_CUDA(launch_scan_kernel(kern, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p));
-        s.counter_base += p.num_tiles;  // one claim per CTA
+        const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, GPS_WIDE_NT, 0, st, pdl, p);
+        if (e == cudaSuccess) s.counter_base += p.num_tiles;  // one claim per CTA
+        GPS_CUDA(e);
     }
     GPS_CUDA(cudaGetLastError());
     return GPS_OK;
@@ -458,12 +475,13 @@ constexpr uint32_t kSortTile = (uint32_t)GPS_SORT_NT * GPS_SORT_KPT;
 constexpr uint32_t kSortPairsTile = (uint32_t)GPS_SORT_PAIRS_NT * GPS_SORT_PAIRS_KPT;
 constexpr uint32_t kSortMinTile = kSortTile < kSortPairsTile ? kSortTile : kSortPairsTile;
 
-template <bool PAIRS, bool XFORM>
-cudaError_t launch_sort_pass(const SortParams& p, bool& configured, bool pdl, cudaStream_t st)
+template <bool PAIRS, bool XFORM, bool FB = false>
+cudaError_t launch_sort_pass(const SortParams& p, bool& configured, bool pdl, cudaStream_t st,
+                             const SortFallbackParams& f = SortFallbackParams{0xFFFFFFFFu, 1u, nullptr})
 {
     constexpr int NT = PAIRS ? GPS_SORT_PAIRS_NT : GPS_SORT_NT, KPT = PAIRS ? GPS_SORT_PAIRS_KPT : GPS_SORT_KPT;
     constexpr size_t smem = ((size_t)(PAIRS ? 2 : 1) * NT * KPT + (size_t)(NT / 32) * kRadix) * sizeof(uint32_t);
-    auto kern = sort_pass_kernel<NT, KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS, GPS_SORT_LB, XFORM>;
+    auto kern = sort_pass_kernel<NT, KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS, GPS_SORT_LB, XFORM, FB>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
@@ -471,7 +489,7 @@ cudaError_t launch_sort_pass(const SortParams& p, bool& configured, bool pdl, cu
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    return launch_scan_kernel(kern, p.num_tiles, NT, smem, st, pdl, p);
+    return launch_scan_kernel(kern, p.num_tiles, NT, smem, st, pdl, p, f);
 }
 }  // namespace
 
@@ -722,13 +740,13 @@ int gps_scan(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* 
     return dispatch_scan(c, algo, kind, dtype, d_in, d_out, n, cs, (cudaStream_t)stream);
 }
 
-int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
-                  const void* h_carry, void* d_total_out, void* stream)
+static int scan_wide_impl(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
+                          const void* h_carry, void* d_total_out, void* stream, const WideFallbackParams* fbp)
 {
     if (!c) return fail(GPS_ERR_INVALID, "null ctx");
     if (kind != GPS_INCLUSIVE && kind != GPS_EXCLUSIVE) return fail(GPS_ERR_INVALID, "bad kind %d", kind);
-    if (algo != GPS_ALGO_CSDL && algo != GPS_ALGO_RTS)
-        return fail(GPS_ERR_INVALID, "gps_scan_wide takes GPS_ALGO_CSDL or GPS_ALGO_RTS");
+    if (algo != GPS_ALGO_CSDL && algo != GPS_ALGO_RTS && algo != GPS_ALGO_CSDL_FALLBACK)
+        return fail(GPS_ERR_INVALID, "gps_scan_wide takes GPS_ALGO_CSDL, GPS_ALGO_CSDL_FALLBACK or GPS_ALGO_RTS");
     const uint64_t es = dtype == GPS_U64 || dtype == GPS_F64 ? 8 : dtype == GPS_U32X4 ? 16
                         : dtype == GPS_U32 || dtype == GPS_F32 ? 4 : 0;
     if (!es) return fail(GPS_ERR_INVALID, "bad dtype %d", dtype);
@@ -743,24 +761,40 @@ int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, v
     if (capturing && algo != GPS_ALGO_RTS)
         if (int rc = cap.begin(c, st, CaptureScope::WIDE)) return rc;
     const bool incl = kind == GPS_INCLUSIVE;
-    bool& cfg = c->wide_configured[dtype][incl ? 0 : 1][algo == GPS_ALGO_RTS ? 1 : 0];
+    bool& cfg = c->wide_configured[dtype][incl ? 0 : 1][algo == GPS_ALGO_RTS ? 1 : algo == GPS_ALGO_CSDL_FALLBACK ? 2 : 0];
     switch (dtype) {
         case GPS_U32:  // the blocked-tile kernel at W = 1, kept to compare it with gps_scan's kernels
-            return incl ? launch_wide<uint32_t, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
-                        : launch_wide<uint32_t, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
+            return incl ? launch_wide<uint32_t, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp)
+                        : launch_wide<uint32_t, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp);
         case GPS_F32:
-            return incl ? launch_wide<float, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
-                        : launch_wide<float, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
+            return incl ? launch_wide<float, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp)
+                        : launch_wide<float, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp);
         case GPS_U64:
-            return incl ? launch_wide<uint64_t, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
-                        : launch_wide<uint64_t, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
+            return incl ? launch_wide<uint64_t, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp)
+                        : launch_wide<uint64_t, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp);
         case GPS_F64:
-            return incl ? launch_wide<double, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
-                        : launch_wide<double, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
+            return incl ? launch_wide<double, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp)
+                        : launch_wide<double, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp);
         default:
-            return incl ? launch_wide<u32x4, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st)
-                        : launch_wide<u32x4, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st);
+            return incl ? launch_wide<u32x4, true>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp)
+                        : launch_wide<u32x4, false>(c, algo, d_in, d_out, n, h_carry, d_total_out, cfg, st, fbp);
     }
+}
+
+int gps_scan_wide(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
+                  const void* h_carry, void* d_total_out, void* stream)
+{
+    return scan_wide_impl(c, algo, kind, dtype, d_in, d_out, n, h_carry, d_total_out, stream, nullptr);
+}
+
+int gps_scan_wide_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
+                                    const void* h_carry, uint32_t stall_mask, uint32_t max_spin, uint32_t* d_stats,
+                                    void* stream)
+{
+    if (stall_mask == 0) return fail(GPS_ERR_INVALID, "stall_mask 0 would stall every tile: nobody left to fall back");
+    if (max_spin == 0) return fail(GPS_ERR_INVALID, "max_spin must be >= 1");
+    const WideFallbackParams f{stall_mask, max_spin, d_stats};
+    return scan_wide_impl(c, GPS_ALGO_CSDL_FALLBACK, kind, dtype, d_in, d_out, n, h_carry, nullptr, stream, &f);
 }
 
 // ---------------------------------------------------------------------------------
@@ -778,8 +812,9 @@ int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_ke
                            end_bit, stream);
 }
 
-int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
-                    const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
+static int sort_keys32_impl(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                            const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit,
+                            void* stream, const SortFallbackParams* fbp)
 {
     if (!c) return fail(GPS_ERR_INVALID, "null ctx");
     const int base_type = key_type & ~GPS_KEY_DESCENDING;
@@ -869,16 +904,42 @@ int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_key
         p.digit_mask = pass == passes - 1 ? last_mask : 0xFFu;
         const bool xf = p.xform_in || p.xform_out || p.digit_mask != 0xFFu;
         const bool pdl = c->s.flags & PF_PDL;
-        GPS_CUDA(pairs ? (xf ? launch_sort_pass<true, true>(p, c->sort_configured[3], pdl, st)
-                             : launch_sort_pass<true, false>(p, c->sort_configured[1], pdl, st))
-                       : (xf ? launch_sort_pass<false, true>(p, c->sort_configured[2], pdl, st)
-                             : launch_sort_pass<false, false>(p, c->sort_configured[0], pdl, st)));
-        c->s.counter_base += tiles;  // one claim per CTA
+        cudaError_t e;
+        if (fbp)
+            e = pairs ? (xf ? launch_sort_pass<true, true, true>(p, c->sort_configured[7], pdl, st, *fbp)
+                            : launch_sort_pass<true, false, true>(p, c->sort_configured[5], pdl, st, *fbp))
+                      : (xf ? launch_sort_pass<false, true, true>(p, c->sort_configured[6], pdl, st, *fbp)
+                            : launch_sort_pass<false, false, true>(p, c->sort_configured[4], pdl, st, *fbp));
+        else
+            e = pairs ? (xf ? launch_sort_pass<true, true>(p, c->sort_configured[3], pdl, st)
+                            : launch_sort_pass<true, false>(p, c->sort_configured[1], pdl, st))
+                      : (xf ? launch_sort_pass<false, true>(p, c->sort_configured[2], pdl, st)
+                            : launch_sort_pass<false, false>(p, c->sort_configured[0], pdl, st));
+        if (e == cudaSuccess) c->s.counter_base += tiles;  // one claim per CTA of a launch that happened
+        GPS_CUDA(e);
         src_k = p.keys_out;
         src_v = p.vals_out;
     }
     GPS_CUDA(cudaGetLastError());
     return GPS_OK;
+}
+
+int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                    const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
+{
+    return sort_keys32_impl(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
+                            stream, nullptr);
+}
+
+int gps_sort_keys32_fallback(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                             const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit,
+                             uint32_t stall_mask, uint32_t max_spin, uint32_t* d_stats, void* stream)
+{
+    if (stall_mask == 0) return fail(GPS_ERR_INVALID, "stall_mask 0 would stall every tile: nobody left to fall back");
+    if (max_spin == 0) return fail(GPS_ERR_INVALID, "max_spin must be >= 1");
+    const SortFallbackParams f{stall_mask, max_spin, d_stats};
+    return sort_keys32_impl(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
+                            stream, &f);
 }
 
 int gps_scan_carry_slots(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out,

@@ -87,6 +87,10 @@
 #ifndef GPS_WIDE_REGS
 #define GPS_WIDE_REGS 40
 #endif
+// register budget of the wide Decoupled Fallback kernel
+#ifndef GPS_WIDE_FB_REGS
+#define GPS_WIDE_FB_REGS 40
+#endif
 
 // radix sort digit pass (gps_sort.cuh): NT threads x KPT keys per thread per tile.
 // Measured at 2^28 random keys on B200 (profiles/r01_sort_sweep.txt), Gkeys/s keys / pairs:

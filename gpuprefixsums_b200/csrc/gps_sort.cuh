@@ -203,12 +203,29 @@ __device__ __forceinline__ uint32_t sort_peers(uint32_t d)
 #endif
 }
 
+// Decoupled Fallback for the digit look-back (template flag FB; the plain kernel carries none of it).
+// The reference's scans guarantee forward progress without fair scheduling by letting a blocked
+// tile recompute its predecessor (EmulatedDeadlocking.cuh:63-151, csdldf_struct.wgsl:161-291); the
+// sort's 256-wide look-back gets the same: when some thread's walk has found the same tile not
+// ready max_spin rounds in a row, the whole CTA re-counts the digits of the NEAREST such tile from
+// the pass's input keys (a pass is out of place, the input is intact) and every thread whose walk
+// is blocked exactly there inserts its digit's count with atomicCAS -- or takes what the owner
+// published meanwhile.  stall_mask emulates stalled tiles for the tests, stats = {spins,
+// fallbacks, insertions, rounds}.
+struct SortFallbackParams {
+    uint32_t stall_mask;  // tiles with (tile & mask) == 0 stall; 0xFFFFFFFF = none
+    uint32_t max_spin;
+    uint32_t* stats;      // nullable
+};
+
 // XFORM: apply the key maps of p.xform_in / p.xform_out (first / last pass of int32 and float32
 // sorts); the uint32 instantiation carries none of that code
-template <int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8, bool XFORM = false>
-__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kernel(const __grid_constant__ SortParams p)
+template <int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8, bool XFORM = false, bool FB = false>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
+    sort_pass_kernel(const __grid_constant__ SortParams p, const SortFallbackParams f)
 {
     pdl_entry();
+    static_assert(!FB || NT == kRadix, "the fallback rounds are block-wide: every thread owns one digit");
     static_assert(NT >= kRadix && NT % 32 == 0, "one thread per digit for the look-back");
     constexpr int NW = NT / 32;
     constexpr uint32_t TILE = NT * KPT;
@@ -310,6 +327,17 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
             s_whist[w][tid] = count;
             count += c;
         }
+        if constexpr (FB) {
+            // stall emulation: refuse to publish until a successor's fallback has inserted this digit's
+            // word (tile 0 is rescued with INCLUSIVE); the last tile never stalls
+            const bool stalled = f.stall_mask != 0xFFFFFFFFu && (tile & f.stall_mask) == 0u && p.num_tiles > 1u &&
+                                 tile != p.num_tiles - 1u;
+            if (stalled) {
+                uint32_t polls = 0;
+                while ((uint32_t)(ld_relaxed_gpu(p.desc + (uint64_t)tile * kRadix + tid) >> 34) != p.epoch)
+                    if (watchdog_tick(polls, p.status)) break;
+            }
+        }
         if (tile != 0) desc_publish_plain(p.desc + (uint64_t)tile * kRadix + tid, pack_desc(count, p.epoch, ST_AGGREGATE));
         const uint32_t inc = warp_inclusive_scan(count, lane);
         if (lane == 31) s_wtot[warp] = inc;
@@ -344,6 +372,112 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) sort_pass_kerne
     }
 
     // ---- chained scan across tiles, one look-back per digit (thread d walks digit d)
+    if constexpr (FB) {
+        __shared__ uint32_t s_fbt[3];  // per round (mod 3): nearest tile some walk is stuck at, + 1
+        uint32_t* const s_fbhist = &s_whist[0][0];  // the per-warp counters are dead by now (after the barrier below)
+        uint32_t prefix = 0, n_spins = 0, n_fallbacks = 0, n_inserts = 0, n_rounds = 0;
+        if (tid < 3u) s_fbt[tid] = 0u;
+        __syncthreads();
+        if (tile != 0) {  // block-uniform
+            uint32_t polls = 0, spins = 0;
+            int64_t t = (int64_t)tile - 1;
+            bool done = false;
+            const uint32_t tag = p.epoch << 2;
+            for (uint32_t round = 0;; ++round) {
+                if (tid == 0) s_fbt[(round + 1u) % 3u] = 0u;  // last read two rounds ago
+                bool want_fb = false;
+                if (!done) {
+                    const uint64_t* dp = p.desc + (uint64_t)t * kRadix + tid;
+                    uint32_t lo[LB], hi[LB];
+#pragma unroll
+                    for (int i = 0; i < LB; ++i) {
+                        lo[i] = 0u;
+                        hi[i] = tag | ST_INCLUSIVE;  // virtual entry below tile 0
+                        if (t - i >= 0) {
+                            const uint64_t d = ld_relaxed_gpu(dp - (int64_t)i * kRadix);
+                            lo[i] = (uint32_t)d;
+                            hi[i] = (uint32_t)(d >> 32);
+                        }
+                    }
+                    uint32_t consumed = 0;
+                    bool open = true;
+#pragma unroll
+                    for (int i = 0; i < LB; ++i) {
+                        const uint32_t st = hi[i] ^ tag;
+                        const bool ok = open && st < 4u && st != 0u;
+                        if (ok) {
+                            prefix += lo[i];
+                            ++consumed;
+                            done = st == ST_INCLUSIVE;
+                        }
+                        open = ok && !done;
+                    }
+                    t -= consumed;
+                    ++n_rounds;
+                    if (consumed == 0u) {
+                        ++n_spins;
+                        if (watchdog_tick(polls, p.status)) done = true;  // give up (reported by gps_check)
+                        want_fb = !done && ++spins >= f.max_spin;
+                    } else {
+                        spins = 0;
+                    }
+                }
+                if (want_fb) atomicMax(&s_fbt[round % 3u], (uint32_t)t + 1u);
+                if (__syncthreads_and(done)) break;
+                const uint32_t fbt = s_fbt[round % 3u];
+                if (fbt == 0u) continue;  // block-uniform: nobody is stuck long enough
+                // ---- Decoupled Fallback on tile fb (never the last tile => full): re-count its digits
+                const uint32_t fb = fbt - 1u;
+                s_fbhist[tid] = 0u;
+                __syncthreads();
+#pragma unroll 4
+                for (int k = 0; k < KPT; ++k) {
+                    uint32_t kk = p.keys_in[(uint64_t)fb * TILE + (uint32_t)k * NT + tid];
+                    if constexpr (XFORM) kk = sort_key_map(kk, p.xform_in);
+                    atomicAdd(&s_fbhist[digit_of(kk)], 1u);
+                }
+                __syncthreads();
+                if (tid == 0) ++n_fallbacks;
+                if (!done && t == (int64_t)fb) {  // my walk is stuck exactly there
+                    const uint32_t cnt = s_fbhist[tid];
+                    const uint32_t st_mine = fb ? ST_AGGREGATE : ST_INCLUSIVE;
+                    const uint64_t mine = pack_desc(cnt, p.epoch, st_mine);
+                    uint64_t* ptr = p.desc + (uint64_t)fb * kRadix + tid;
+                    uint64_t seen = ld_relaxed_gpu(ptr);
+                    uint32_t use = cnt, use_st = st_mine;
+                    bool inserted = false;
+                    while ((uint32_t)(seen >> 34) != p.epoch) {
+                        const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(ptr), (unsigned long long)seen,
+                                                       (unsigned long long)mine);
+                        if (old == seen) {
+                            inserted = true;
+                            break;
+                        }
+                        seen = old;
+                    }
+                    if (inserted) {
+                        ++n_inserts;
+                    } else {  // the owner (or another rescuer) got there first
+                        use = (uint32_t)seen;
+                        use_st = (uint32_t)(seen >> 32) & ST_MASK;
+                    }
+                    prefix += use;
+                    done = use_st == ST_INCLUSIVE;
+                    t -= 1;
+                    spins = 0;
+                }
+                __syncthreads();  // s_fbhist is zeroed again by the next fallback
+            }
+        }
+        desc_publish_plain(p.desc + (uint64_t)tile * kRadix + tid, pack_desc(prefix + count, p.epoch, ST_INCLUSIVE));
+        s_goff[tid] = p.digit_base[tid] + prefix - cta_excl;
+        if (f.stats) {
+            if (n_spins) atomicAdd(f.stats + 0, n_spins);
+            if (n_fallbacks) atomicAdd(f.stats + 1, n_fallbacks);
+            if (n_inserts) atomicAdd(f.stats + 2, n_inserts);
+            if (tid == 0 && n_rounds) atomicAdd(f.stats + 3, n_rounds);
+        }
+    } else
     if (tid < (uint32_t)kRadix) {
         // Thread d walks digit d's descriptors backwards, LB descriptors per L2 round trip: the
         // loads of one round are independent, the walk consumes them nearest first and stops

@@ -31,6 +31,7 @@
 // deterministic for float64.
 #pragma once
 #include "gps_common.cuh"
+#include "gps_csdl_reg.cuh"  // LB_DONE / LB_FALLBACK
 
 namespace gps {
 
@@ -294,6 +295,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     }
     __syncthreads();
     const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed)
+        if (tid == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
     const bool full = ((uint64_t)tile + 1u) * S::TILE_ELEMS <= p.n;
     const uint32_t v0 = tid * V;  // this thread's first vector within the tile
 
@@ -386,6 +391,313 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
                        S::WARP_VEC * 16u);
             bulk_commit();
             bulk_wait_read<0>();  // shared memory must outlive the engine's read
+        }
+    } else {
+        __syncwarp();
+        const E* s_e = reinterpret_cast<const E*>(s_data + warp * S::WARP_VEC);
+        E* out1 = reinterpret_cast<E*>(p.out);
+        const uint64_t e0 = warp_vec0 * KPV;
+#pragma unroll 1
+        for (uint32_t i = lane; i < S::WARP_VEC * KPV; i += 32u)
+            if (e0 + i < p.n) out1[e0 + i] = s_e[i];
+    }
+}
+
+// ---- the chained tile kernel with Decoupled Fallback (and optional emulated stalls) ----------
+// The struct scan of the reference IS a fallback kernel (GPUPrefixSumsWebGPUapis/SharedShaders/
+// csdldf_struct.wgsl:61-316: per-member flag words, a spin budget, the whole workgroup re-reducing
+// the blocking tile from the input, insertion with an atomic that never overwrites a finished
+// word).  Here: warp 0 walks the two-set descriptors with a spin budget; when a window stays
+// blocked, the whole CTA re-reduces the nearest not-ready tile from the INPUT -- in exactly the
+// association order its owner uses (thread t sums its V consecutive vectors serially, one warp
+// scan, warp totals added in order), so the recomputed aggregate is BIT-IDENTICAL to the owner's
+// for every element type, float64 included, and words written by the owner and by rescuers can
+// mix freely -- and inserts the W aggregate words with atomicCAS from the stale word it observes.
+// In place: the owner's descriptor words are performed (fence) before the barrier that precedes
+// its first output store, and a rescuer fences between its re-read and its CAS; a rescuer that
+// read half-overwritten input therefore finds every word already valid and takes the owner's.
+struct WideFallbackParams {
+    uint32_t stall_mask;  // tiles with (tile & mask) == 0 stall; 0xFFFFFFFF = none
+    uint32_t max_spin;    // unsuccessful polls of a window before falling back
+    uint32_t* stats;      // nullable: {spins, fallbacks, insertions, lookback windows}
+};
+
+template <typename E>
+__device__ __forceinline__ bool wide_word_cas_insert(uint64_t* ptr, uint32_t value, uint32_t epoch, uint32_t& result)
+{
+    // stale word -> {value | epoch}; a word that already carries this launch's epoch is kept
+    const uint64_t mine = ((uint64_t)epoch << 32) | value;
+    uint64_t seen = ld_relaxed_gpu(ptr);
+    while ((uint32_t)(seen >> 32) != epoch) {
+        const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(ptr), (unsigned long long)seen,
+                                       (unsigned long long)mine);
+        if (old == seen) {
+            result = value;
+            return true;
+        }
+        seen = old;
+    }
+    result = (uint32_t)seen;
+    return false;
+}
+
+template <typename E, int NT, int V, bool INCLUSIVE, int REGS = 48>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
+    wide_scan_fallback_kernel(const __grid_constant__ WideParams<E> p, const WideFallbackParams f)
+{
+    pdl_entry();
+    using S = WideShape<E, NT, V>;
+    using Vec = typename S::Vec;
+    constexpr int W = S::W, KPV = S::KPV, NW = S::NW;
+    __shared__ __align__(128) uint4 s_data[S::TILE_VEC];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(16) E s_warp[NW];
+    __shared__ __align__(16) E s_fb[NW];
+    __shared__ __align__(16) E s_prefix;
+    __shared__ uint32_t s_tile, s_state, s_fb_tile;
+    __shared__ uint32_t s_stats[4];  // {spins, fallbacks, insertions, windows}: only touched when f.stats is set
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool in_place = p.in == p.out;  // only then may a rescuer's re-read race with the owner's stores
+    const bool stats = f.stats != nullptr;
+    if (tid < 4u) s_stats[tid] = 0u;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        const uint32_t t = atomicAdd(p.counter, 1u) - p.counter_base;
+        s_tile = t;
+        if (((uint64_t)t + 1u) * S::TILE_ELEMS <= p.n && t < p.num_tiles) {
+            mbar_arrive_expect_tx(&s_bar, S::TILE_BYTES);
+            bulk_load(s_data, reinterpret_cast<const unsigned char*>(p.in) + (uint64_t)t * S::TILE_BYTES,
+                      S::TILE_BYTES, &s_bar);
+        }
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed)
+        if (tid == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
+    const bool full = ((uint64_t)tile + 1u) * S::TILE_ELEMS <= p.n;
+    const uint32_t v0 = tid * V;
+    if (full) {
+        if (!mbar_wait_bounded(&s_bar, 0u)) {
+            atomicOr(p.status, STATUS_WATCHDOG);
+            return;
+        }
+    } else {
+        const E* in1 = reinterpret_cast<const E*>(p.in);
+#pragma unroll 1
+        for (int k = 0; k < V; ++k) {
+            const uint64_t e0 = ((uint64_t)tile * S::TILE_VEC + v0 + k) * KPV;
+            Vec t;
+#pragma unroll
+            for (int c = 0; c < KPV; ++c) t.e[c] = e0 + c < p.n ? in1[e0 + c] : wide_zero<E>();
+            s_data[v0 + k] = t.u;
+        }
+    }
+
+    // ---- pass 1 (the association order the fallback below reproduces)
+    E acc = wide_zero<E>();
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        Vec t;
+        t.u = s_data[v0 + k];
+#pragma unroll
+        for (int c = 0; c < KPV; ++c) acc = acc + t.e[c];
+    }
+    const E inc = wide_warp_inclusive_scan(acc);
+    E local_prefix = wide_exclusive_of(inc, acc, lane);  // within the warp ...
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    E aggregate = wide_zero<E>();
+    {
+        E warp_prefix = wide_zero<E>();
+#pragma unroll
+        for (int j = 0; j < NW; ++j) {
+            const E w = s_warp[j];
+            if ((uint32_t)j < warp) warp_prefix = warp_prefix + w;
+            aggregate = aggregate + w;
+        }
+        local_prefix = warp_prefix + local_prefix;  // ... and within the tile: one value kept across the look-back
+    }
+
+    // stall emulation (EmulatedDeadlocking.cuh:63-72 / the WebGPU test variants): the tile refuses
+    // to publish until a successor's fallback has published for it; the last tile never stalls
+    const bool stalled = f.stall_mask != 0xFFFFFFFFu && (tile & f.stall_mask) == 0u && p.num_tiles > 1u &&
+                         tile != p.num_tiles - 1u;
+    uint64_t* const my_desc = p.desc + (uint64_t)tile * (2 * W);
+    if (warp == 0) {
+        if (stalled && lane < (uint32_t)W) {
+            uint32_t polls = 0;
+            uint64_t* word = my_desc + (tile ? 0 : W) + lane;  // tile 0 is rescued with INCLUSIVE words
+            while ((uint32_t)(ld_relaxed_gpu(word) >> 32) != p.epoch)
+                if (watchdog_tick(polls, p.status)) break;
+        }
+        __syncwarp();
+        if (tile != 0 && lane < (uint32_t)W) {
+            wide_desc_publish(my_desc + lane, wide_word(aggregate, lane), p.epoch);
+            if (in_place) __threadfence();  // performed before any thread of this CTA overwrites the input
+        }
+    }
+
+    // One barrier per round: warp 0 walks (with a spin budget); when the walk is complete it publishes
+    // INCLUSIVE at once -- that word is what every successor waits for -- and only then meets the
+    // other warps at the barrier; a round that ends in LB_FALLBACK sends the whole CTA to re-reduce.
+    E prefix = tile ? wide_zero<E>() : p.carry;
+    bool finished = tile == 0;  // tile 0: nothing to look back at
+    int64_t top = (int64_t)tile - 1;
+    while (true) {
+        if (warp == 0) {
+            uint32_t state = LB_DONE, spins = 0, polls = 0, fb = 0;
+            while (!finished) {
+                const int64_t idx = top - (int64_t)lane;
+                uint32_t st = ST_INCLUSIVE;  // virtual entry below tile 0
+                E v = wide_zero<E>();
+                if (idx >= 0) {
+                    const uint64_t* d = p.desc + (uint64_t)idx * (2 * W);
+                    uint64_t w[2 * W];  // relaxed: every word carries its own epoch tag next to its payload
+                    if constexpr (W == 1) {
+                        w[0] = ld_relaxed_gpu(d);
+                        w[1] = ld_relaxed_gpu(d + 1);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 2 * W; i += 2)
+                            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];"
+                                         : "=l"(w[i]), "=l"(w[i + 1])
+                                         : "l"(d + i)
+                                         : "memory");
+                    }
+                    bool agg_ok = true, inc_ok = true;
+#pragma unroll
+                    for (int i = 0; i < W; ++i) {
+                        agg_ok = agg_ok && (uint32_t)(w[i] >> 32) == p.epoch;
+                        inc_ok = inc_ok && (uint32_t)(w[W + i] >> 32) == p.epoch;
+                    }
+                    st = inc_ok ? ST_INCLUSIVE : agg_ok ? ST_AGGREGATE : ST_NOT_READY;
+                    uint32_t words[W];
+#pragma unroll
+                    for (int i = 0; i < W; ++i) words[i] = (uint32_t)(inc_ok ? w[W + i] : w[i]);
+                    v = wide_from_words<E>(words);
+                }
+                if (stats && lane == 0) ++s_stats[3];
+                const uint32_t not_ready = __ballot_sync(kFullMask, st == ST_NOT_READY);
+                const uint32_t first_nr = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
+                const uint32_t below = first_nr >= 32u ? kFullMask : ((1u << first_nr) - 1u);
+                const uint32_t incl = __ballot_sync(kFullMask, st == ST_INCLUSIVE) & below;
+                if (incl) {
+                    const uint32_t nearest = (uint32_t)__ffs((int)incl) - 1u;
+                    prefix = prefix + wide_warp_reduce(lane <= nearest ? v : wide_zero<E>());
+                    break;
+                }
+                if (first_nr == 32u) {  // whole window ready, none inclusive
+                    prefix = prefix + wide_warp_reduce(v);
+                    top -= 32;
+                    spins = 0;
+                    continue;
+                }
+                if (stats && lane == 0) ++s_stats[0];
+                const bool bail = watchdog_tick(polls, p.status);
+                if (__any_sync(kFullMask, bail)) break;
+                if (++spins < f.max_spin) continue;
+                // budget exhausted: consume the ready tiles nearer than the blocker, fall back on it
+                prefix = prefix + wide_warp_reduce(lane < first_nr ? v : wide_zero<E>());
+                fb = (uint32_t)(top - (int64_t)first_nr);
+                top = (int64_t)fb - 1;
+                state = LB_FALLBACK;
+                break;
+            }
+            if (state == LB_DONE) {  // warp-uniform
+                const E inclusive = prefix + aggregate;
+                if (lane < (uint32_t)W) {
+                    wide_desc_publish(my_desc + W + lane, wide_word(inclusive, lane), p.epoch);
+                    if (in_place) __threadfence();
+                }
+                if (lane == 0) {
+                    s_prefix = prefix;
+                    if (tile == p.num_tiles - 1 && p.total_out) *reinterpret_cast<E*>(p.total_out) = inclusive;
+                }
+            }
+            if (lane == 0) {
+                s_state = state;
+                s_fb_tile = fb;
+            }
+        }
+        __syncthreads();
+        if (s_state == LB_DONE) break;
+
+        // ---- Decoupled Fallback: every thread re-reads ITS blocked run of tile fb (a fallback
+        // target is never the last tile => always full) and the CTA repeats pass 1 on it
+        const uint32_t fb = s_fb_tile;
+        if (stats && tid == 0) ++s_stats[1];
+        {
+            const uint4* in4 = reinterpret_cast<const uint4*>(p.in) + (uint64_t)fb * S::TILE_VEC + v0;
+            E facc = wide_zero<E>();
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                Vec t;
+                t.u = in4[k];  // L1-allocating: the 32-byte sectors of this strided pattern are reused by the next k
+#pragma unroll
+                for (int c = 0; c < KPV; ++c) facc = facc + t.e[c];
+            }
+            const E finc = wide_warp_inclusive_scan(facc);
+            if (lane == 31) s_fb[warp] = finc;
+        }
+        __syncthreads();  // also: every warp has read s_state / s_fb_tile before warp 0 rewrites them
+        if (warp == 0) {
+            E red = wide_zero<E>();
+#pragma unroll
+            for (int j = 0; j < NW; ++j) red = red + s_fb[j];
+            if (fb == 0) red = p.carry + red;  // tile 0 is INCLUSIVE incl. the carry (owner: prefix + aggregate)
+            if (in_place) __threadfence();  // my re-read is ordered before my CAS (see the header comment)
+            uint32_t got = 0;
+            bool inserted = false;
+            if (lane < (uint32_t)W)
+                inserted = wide_word_cas_insert<E>(p.desc + (uint64_t)fb * (2 * W) + (fb ? 0 : W) + lane,
+                                                   wide_word(red, lane), p.epoch, got);
+            if (stats && __any_sync(kFullMask, inserted) && lane == 0) ++s_stats[2];
+            // the value in the descriptor (mine or the owner's: identical unless my read raced
+            // with an in-place overwrite, in which case every word is the owner's)
+            uint32_t words[W];
+#pragma unroll
+            for (int i = 0; i < W; ++i) words[i] = __shfl_sync(kFullMask, got, i);
+            prefix = prefix + wide_from_words<E>(words);
+            finished = fb == 0;  // the walk goes on below fb, or ends here
+        }
+    }
+    if (stats) {
+        __syncthreads();
+        if (tid < 4u && s_stats[tid]) atomicAdd(f.stats + tid, s_stats[tid]);
+    }
+
+    // ---- pass 2 + store: as wide_scan_kernel
+    E run = s_prefix + local_prefix;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        Vec t;
+        t.u = s_data[v0 + k];
+#pragma unroll
+        for (int c = 0; c < KPV; ++c) {
+            const E x = t.e[c];
+            if (INCLUSIVE) {
+                run = run + x;
+                t.e[c] = run;
+            } else {
+                t.e[c] = run;
+                run = run + x;
+            }
+        }
+        s_data[v0 + k] = t.u;
+    }
+    const uint64_t warp_vec0 = (uint64_t)tile * S::TILE_VEC + (uint64_t)warp * S::WARP_VEC;
+    if (full) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_store(reinterpret_cast<unsigned char*>(p.out) + warp_vec0 * 16u, s_data + warp * S::WARP_VEC,
+                       S::WARP_VEC * 16u);
+            bulk_commit();
+            bulk_wait_read<0>();
         }
     } else {
         __syncwarp();

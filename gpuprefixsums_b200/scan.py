@@ -114,15 +114,7 @@ class PrefixSum:
                            _stream_ptr(stream, self.device)))
         return out
 
-    def scan_wide(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, algo="csdl",
-                  exclusive: bool = False, struct4: bool = False, carry=None, total_out: Optional[torch.Tensor] = None,
-                  stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
-        """uint64 (torch.int64 bit pattern), float64, or -- with struct4=True on an int32 tensor
-        whose last dimension is 4 -- the four-lane struct scan.  algo: "csdl" (chained scan,
-        default) or "rts" (Reduce-then-Scan, deterministic for float64)."""
-        if algo not in ("csdl", "rts"):
-            raise ValueError("scan_wide: algo must be 'csdl' or 'rts'")
-        inp, out = self._prep(inp, out)
+    def _wide_args(self, inp: torch.Tensor, struct4: bool, carry):
         if struct4:
             if inp.dtype not in (torch.int32, torch.uint32) or inp.numel() % 4:
                 raise TypeError("struct4 needs an int32 tensor with a multiple of 4 values")
@@ -142,16 +134,44 @@ class PrefixSum:
             cval = C.c_float(float(carry)) if carry is not None else None
         else:
             raise TypeError(f"scan_wide: unsupported dtype {inp.dtype}")
-        check(lib.gps_scan_wide(self._ctx, capi.ALGO_RTS if algo == "rts" else capi.ALGO_CSDL, _kind(exclusive), dtype, inp.data_ptr(), out.data_ptr(), n,
+        return dtype, n, cval
+
+    def scan_wide(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, algo="csdl",
+                  exclusive: bool = False, struct4: bool = False, carry=None, total_out: Optional[torch.Tensor] = None,
+                  stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """uint64 (torch.int64 bit pattern), float64, or -- with struct4=True on an int32 tensor
+        whose last dimension is 4 -- the four-lane struct scan.  algo: "csdl" (chained scan,
+        default), "csdl_fallback" (chained scan with Decoupled Fallback) or "rts" (Reduce-then-Scan,
+        deterministic for float64)."""
+        if algo not in ("csdl", "rts", "csdl_fallback"):
+            raise ValueError("scan_wide: algo must be 'csdl', 'csdl_fallback' or 'rts'")
+        inp, out = self._prep(inp, out)
+        dtype, n, cval = self._wide_args(inp, struct4, carry)
+        check(lib.gps_scan_wide(self._ctx, capi.ALGO_NAMES[algo], _kind(exclusive), dtype, inp.data_ptr(), out.data_ptr(), n,
                                 C.cast(C.byref(cval), C.c_void_p) if cval is not None else None,
                                 total_out.data_ptr() if total_out is not None else None,
                                 _stream_ptr(stream, self.device)))
         return out
 
+    def scan_wide_emulated_deadlock(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, exclusive: bool = False,
+                                    struct4: bool = False, carry=None, stall_mask: int = 7, max_spin: int = 4,
+                                    stats: Optional[torch.Tensor] = None,
+                                    stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """The wide scans' Decoupled Fallback kernel with emulated stalls (see gps_b200.h)."""
+        inp, out = self._prep(inp, out)
+        dtype, n, cval = self._wide_args(inp, struct4, carry)
+        check(lib.gps_scan_wide_emulated_deadlock(self._ctx, _kind(exclusive), dtype, inp.data_ptr(), out.data_ptr(), n,
+                                                  C.cast(C.byref(cval), C.c_void_p) if cval is not None else None,
+                                                  stall_mask & 0xFFFFFFFF, max_spin,
+                                                  stats.data_ptr() if stats is not None else None,
+                                                  _stream_ptr(stream, self.device)))
+        return out
+
     def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None, *, end_bit: int = 32, key_type: str = "u32",
              descending: bool = False,
              keys_out: Optional[torch.Tensor] = None, values_out: Optional[torch.Tensor] = None,
-             stream: Optional[torch.cuda.Stream] = None):
+             stream: Optional[torch.cuda.Stream] = None, fallback: bool = False, stall_mask: int = 0xFFFFFFFF,
+             max_spin: int = 4, stats: Optional[torch.Tensor] = None):
         """Stable ascending LSD radix sort of 32-bit keys, optionally moving a 32-bit payload;
         returns keys or (keys, values).  key_type: "u32" (default: the bit pattern as unsigned,
         on the low `end_bit` bits), "i32" (signed order) or "f32" (numeric order, float32 keys)."""
@@ -171,8 +191,14 @@ class PrefixSum:
             vptrs = (values.data_ptr(), vo.data_ptr(), vt.data_ptr())
         else:
             vo, vptrs = None, (None, None, None)
-        check(lib.gps_sort_keys32(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs, keys.numel(),
-                               int(end_bit), _stream_ptr(stream, self.device)))
+        if fallback:  # Decoupled Fallback in the digit look-back (+ emulated stalls for the tests)
+            check(lib.gps_sort_keys32_fallback(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs,
+                                               keys.numel(), int(end_bit), stall_mask & 0xFFFFFFFF, max_spin,
+                                               stats.data_ptr() if stats is not None else None,
+                                               _stream_ptr(stream, self.device)))
+        else:
+            check(lib.gps_sort_keys32(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs, keys.numel(),
+                                      int(end_bit), _stream_ptr(stream, self.device)))
         return ko if values is None else (ko, vo)
 
     def scan_carry_slots(self, inp: torch.Tensor, out: Optional[torch.Tensor], slots_ptr: int, n_slots: int,

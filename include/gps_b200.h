@@ -156,12 +156,24 @@ int gps_scan(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void
  * exceed 4 * max_n bytes of the ctx.  h_carry (nullable) points to one element on the HOST
  * that seeds the scan; d_total_out (nullable) receives carry + sum on the device.
  * algo: GPS_ALGO_CSDL = chained scan with decoupled look-back over two-set epoch-tagged
- * descriptors (single pass, 2 x element size of HBM traffic per element), GPS_ALGO_RTS =
+ * descriptors (single pass, 2 x element size of HBM traffic per element), GPS_ALGO_CSDL_FALLBACK =
+ * the same with Decoupled Fallback (what csdldf_struct.wgsl is: spin budget, whole-CTA
+ * re-reduction of the blocking tile from the input, per-word atomicCAS insertion), GPS_ALGO_RTS =
  * Reduce-then-Scan (3 x, deterministic for float64).  Both use the blocked shared-memory
  * tile of csrc/gps_wide.cuh (TMA bulk load and store).  GPS_U32 / GPS_F32 are accepted too:
  * the same kernel at 32 bits, kept to compare it with gps_scan's kernels.  Asynchronous. */
 int gps_scan_wide(gps_ctx* ctx, int algo, int kind, int dtype, const void* d_in, void* d_out,
                   uint64_t n, const void* h_carry, void* d_total_out, void* stream);
+
+/* The wide scan's emulated-deadlock harness (the struct scan's counterpart of
+ * gps_scan_emulated_deadlock; GPUPrefixSumsWebGPUapis/SharedShaders/csdldf_struct.wgsl:161-291 with
+ * the stall injection of TestVariants/): tiles with (tile & stall_mask) == 0 refuse to publish until
+ * a successor's fallback has inserted their aggregate; the last tile never stalls.  d_stats
+ * (nullable) accumulates {spins, fallbacks, insertions, look-back windows}.  Bit-exact for every
+ * element type, float64 included: a rescuer reproduces the owner's association order. */
+int gps_scan_wide_emulated_deadlock(gps_ctx* ctx, int kind, int dtype, const void* d_in, void* d_out,
+                                    uint64_t n, const void* h_carry, uint32_t stall_mask,
+                                    uint32_t max_spin, uint32_t* d_stats, void* stream);
 
 /* ---- radix sort: the scan's consumer (reference README.md:7 names sorting
  * as the downstream use of its scans -- the sort itself is in the sibling repository
@@ -190,6 +202,16 @@ enum gps_key_type {
 int gps_sort_keys32(gps_ctx* ctx, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
                     const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,
                     int end_bit, void* stream);
+/* The same sort with Decoupled Fallback in the per-digit look-back (forward progress without fair
+ * scheduling, as the reference's scans have it: EmulatedDeadlocking.cuh:63-151): a tile whose walk
+ * finds the same predecessor not ready max_spin rounds in a row re-counts that predecessor's digits
+ * from the pass's input and inserts them with atomicCAS.  stall_mask emulates stalled tiles
+ * ((tile & mask) == 0, never the last; 0xFFFFFFFF = none: the production variant); d_stats
+ * (nullable) accumulates {spins, fallbacks, insertions, look-back rounds} over all passes. */
+int gps_sort_keys32_fallback(gps_ctx* ctx, int key_type, const void* d_keys_in, void* d_keys_out,
+                             void* d_keys_tmp, const void* d_vals_in, void* d_vals_out,
+                             void* d_vals_tmp, uint64_t n, int end_bit, uint32_t stall_mask,
+                             uint32_t max_spin, uint32_t* d_stats, void* stream);
 /* = gps_sort_keys32(GPS_KEY_U32, ...) */
 int gps_sort_u32(gps_ctx* ctx, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
                  const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,

@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SIZES = [0, 1, 2, 3, 5, 1023, 1025, 2303, 2304, 2305, 4607, 4608, 4609, 9217, 100_003, (1 << 22) + 7]
-ALGOS = ["csdl", "rts"]
+ALGOS = ["csdl", "rts", "csdl_fallback"]
 F64_RTOL = 1e-13
 
 
@@ -144,3 +144,53 @@ def test_blocked_kernel_at_32_bits(ps, oracle, exclusive, algo):
     ps.check()
     errs, max_rel = oracle.check_f32(xf, outf.cpu().numpy(), exclusive=exclusive, rtol=2e-5, atol=1e-6)
     assert errs == 0, max_rel
+
+
+# ---------------------------------------------------------------------------------------
+# Decoupled Fallback for the wide scans (the reference's struct scan IS a fallback kernel:
+# GPUPrefixSumsWebGPUapis/SharedShaders/csdldf_struct.wgsl:61-316)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mask,spin", [(7, 4), (1, 1), (63, 2), (0xFFFFFFFF, 1)])
+def test_wide_emulated_deadlock_bit_exact(ps, oracle, mask, spin):
+    """Stalled tiles are rescued by their successors (whole-CTA re-reduction from the input, per-word
+    CAS insertion); results stay bit-exact for uint64 and the struct scan, both kinds, in place too,
+    and the counters show that fallbacks really happened."""
+    rng = np.random.default_rng(11)
+    for n in [1, 2303, 2304, 2305, 4608, 9 * 2304 + 1, 100_003, (1 << 21) + 7]:
+        x = rng.integers(0, 2**63, size=n, dtype=np.uint64)
+        for exclusive in (False, True):
+            want, _ = oracle.scan_u64(x, exclusive=exclusive, carry=5)
+            stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+            buf = torch.from_numpy(x.view(np.int64)).cuda()
+            ps.scan_wide_emulated_deadlock(buf, buf, exclusive=exclusive, carry=5, stall_mask=mask, max_spin=spin, stats=stats)
+            ps.check()
+            assert np.array_equal(buf.cpu().numpy().view(np.uint64), want), (n, exclusive, mask)
+            if mask != 0xFFFFFFFF and n > 4 * 4608:
+                st = stats.cpu().numpy()
+                assert st[1] > 0 and st[2] > 0, f"no fallbacks recorded: {st}"
+        xs = oracle.random_u32(4 * (n // 2 + 1), seed=n)
+        want, _ = oracle.scan_u32x4(xs, carry=(1, 2, 3, 4))
+        out = ps.scan_wide_emulated_deadlock(torch.from_numpy(xs.view(np.int32)).cuda().view(-1, 4), struct4=True,
+                                             carry=(1, 2, 3, 4), stall_mask=mask, max_spin=spin)
+        ps.check()
+        assert np.array_equal(out.cpu().numpy().view(np.uint32).reshape(-1), want), (n, mask)
+
+
+def test_wide_fallback_float64_and_large_closed_form(ps, oracle):
+    """float64 under emulated stalls: a rescuer reproduces the owner's association order (its aggregate
+    is bit-identical to the owner's, so descriptor words written by either can mix); results are within
+    the float64 tolerance of the serial oracle.  Plus the all-ones closed form over 7282 tiles."""
+    rng = np.random.default_rng(3)
+    n = (1 << 21) + 123
+    x = rng.random(n) * 2.0 - 0.5
+    d_in = torch.from_numpy(x).cuda()
+    for mask, spin in [(7, 4), (1, 1)]:
+        out = ps.scan_wide_emulated_deadlock(d_in, stall_mask=mask, max_spin=spin)
+        ps.check()
+        errs, max_rel = oracle.check_f64(x, out.cpu().numpy(), rtol=F64_RTOL)
+        assert errs == 0, (mask, max_rel)
+    # all-ones closed form through the fallback kernel at 1 GiB-scale tile counts
+    ones = torch.ones(1 << 24, dtype=torch.int64, device="cuda")
+    out = ps.scan_wide_emulated_deadlock(ones, stall_mask=7, max_spin=4)
+    ps.check()
+    assert torch.equal(out, torch.arange(1, (1 << 24) + 1, dtype=torch.int64, device="cuda"))

@@ -49,5 +49,17 @@ res["cub_pairs"] = timed(lambda: gps.cub_sort(keys, ref, vals, refv))
 kf = keys.view(torch.float32)
 res["gps_keys_f32"] = timed(lambda: ps.sort(kf, key_type="f32"))
 res["gps_keys_16bit"] = timed(lambda: ps.sort(keys, keys_out=ko, end_bit=16))
+# Decoupled Fallback in the digit look-back: production variant (no stalls) and emulated stalls
+res["gps_keys_fallback"] = timed(lambda: ps.sort(keys, keys_out=ko, fallback=True, max_spin=64))
+ps.check()
+gps.cub_sort(keys, ref)
+res["keys_fallback_equal_cub"] = bool(torch.equal(ko, ref))
+res["gps_pairs_fallback"] = timed(lambda: ps.sort(keys, vals, keys_out=ko, values_out=vo, fallback=True, max_spin=64))
+stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+res["gps_keys_emulated_deadlock_mask7_spin4"] = timed(
+    lambda: ps.sort(keys, keys_out=ko, fallback=True, stall_mask=7, max_spin=4, stats=stats))
+ps.check()
+res["keys_emulated_equal_cub"] = bool(torch.equal(ko, ref))
+res["emulated_stats_per_sort"] = [int(v) // (iters + 2) for v in stats.tolist()]
 ps.close()
 print(json.dumps(res))
