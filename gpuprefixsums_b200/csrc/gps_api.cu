@@ -603,7 +603,6 @@ int gps_create_with_scratch(gps_ctx** out, int device, uint64_t max_n, void* d_s
     c->s.wdesc_words = L.wdesc_words;
     c->s.counter = reinterpret_cast<uint32_t*>(base + L.off_counter);
     c->s.status = c->s.counter + 1;
-    c->s.reduce_acc = c->s.counter + 8;  // 33 words of the same zero-initialised 256-byte block
     c->g_desc = reinterpret_cast<uint64_t*>(base + L.off_gdesc);
     c->g_wdesc = reinterpret_cast<uint64_t*>(base + L.off_gwdesc);
     c->g_counter = reinterpret_cast<uint32_t*>(base + L.off_gcounter);

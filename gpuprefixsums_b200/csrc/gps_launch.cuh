@@ -46,7 +46,6 @@ struct Scratch {
     uint32_t desc_tiles = 0;
     uint32_t* counter = nullptr;  // tile-claim counter, never reset
     uint32_t* status = nullptr;   // watchdog word
-    uint32_t* reduce_acc = nullptr;  // 32 accumulator words + done counter of rts_reduce_total_kernel (zero when idle)
     void* partials = nullptr;     // one key-sized value per RTS tile
     uint32_t partials_capacity = 0;
     uint32_t counter_base = 0;
@@ -336,12 +335,6 @@ cudaError_t launch_reduce(Scratch& s, const void* in, uint64_t n, void* total_ou
     p.total_out = total_out;
     p.publish = pl;
     const bool pdl = s.flags & PF_PDL;
-    if constexpr (std::is_same<T, uint32_t>::value) {
-        if (p.num_tiles && s.reduce_acc) {  // one launch: the last CTA to finish folds and publishes
-            const ReduceAcc a{s.reduce_acc, s.reduce_acc + 32};
-            return launch_scan_kernel(rts_reduce_total_kernel<NT, V>, p.num_tiles, NT, 0, st, pdl, p, a);
-        }
-    }
     if (p.num_tiles) e = launch_scan_kernel(rts_reduce_kernel<T, NT, V>, p.num_tiles, NT, 0, st, pdl, p);
     if (e == cudaSuccess) e = launch_scan_kernel(rts_fold_kernel<T>, 1, kSpineThreads, 0, st, pdl, p);
     return e;

@@ -69,52 +69,11 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 16 + 4 * V))
     if (threadIdx.x == 0) reinterpret_cast<T*>(p.partials)[tile] = sum;
 }
 
-// ---- reduce + total in ONE launch (uint32): every CTA adds its tile sum into one of 32
-// accumulator words (integer adds commute exactly, so the order does not matter), fences, and
-// takes a number at the done-counter; the CTA that draws the last number collects the 32 words
-// (exchanging them back to 0 for the next launch -- the counter wraps to 0 by itself), writes the
-// total and publishes it to the (peer) carry slots.  Saves the separate fold launch of
-// gps_reduce / gps_reduce_publish on the sharded step's critical path.  float32 keeps the
-// partials + fold pair (fixed association order: deterministic).
-struct ReduceAcc {
-    uint32_t* acc;   // 32 words, zero between launches
-    uint32_t* done;  // CTAs finished, wraps to 0 at num_tiles
-};
-
-template <int NT, int V>
-__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 16 + 4 * V))
-    rts_reduce_total_kernel(const __grid_constant__ RtsParams p, const ReduceAcc a)
-{
-    pdl_entry();
-    using Tile = RegTile<uint32_t, NT, V>;
-    __shared__ uint32_t s_red[NT / 32];
-    __shared__ uint32_t s_last;
-    const uint32_t lane = lane_id();
-    const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t tile = p.num_tiles - 1u - blockIdx.x;  // back to front, see rts_reduce_kernel
-    const uint64_t vbase = Tile::vec_base(tile, warp, lane);
-    Tile t;
-    if (((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n)
-        t.load_full(p.in, vbase);
-    else
-        t.load_partial(p.in, vbase, p.n);
-    const uint32_t sum = block_reduce<uint32_t, NT>(t.thread_sum(), s_red, warp, lane);
-    if (threadIdx.x == 0) {
-        atomicAdd(a.acc + (tile & 31u), sum);
-        __threadfence();  // the add is performed before this CTA counts as done
-        s_last = atomicInc(a.done, p.num_tiles - 1u) == p.num_tiles - 1u;
-    }
-    __syncthreads();
-    if (s_last && warp == 0) {
-        __threadfence();
-        const uint32_t total = warp_reduce(atomicExch(a.acc + lane, 0u));
-        if (lane == 0) {
-            if (p.total_out) *reinterpret_cast<uint32_t*>(p.total_out) = total;
-            publish_total<uint32_t>(p.publish, total);
-        }
-    }
-}
-
+// (Round 2 tried to fold the total inside the reduce kernel -- every CTA adds its tile sum to an
+// accumulator, fences and takes a number; the last one publishes -- to save the fold launch of
+// gps_reduce_publish: the fence + returning atomic lengthen every CTA's lifetime and the reduce
+// pass dropped from 7.2 to 5.5 TB/s (sharded step 0.475 -> 0.522 ms on 2 GPUs).  Reverted: the
+// partials + one-block fold below stay.)
 // ---- kernel 2: spine -- exclusive scan of the tile sums (+ carry) -------------------
 constexpr int kSpineThreads = 1024;
 

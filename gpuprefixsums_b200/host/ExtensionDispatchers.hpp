@@ -81,6 +81,7 @@ class WideScanDispatcher : public ExtensionBase {
     const uint32_t k_elemBytes;
 
    protected:
+    int m_timingAlgo = GPS_ALGO_CSDL;
     WideScanDispatcher(uint64_t maxElems, int dtype, uint32_t elemBytes, const char* name)
         : ExtensionBase(maxElems * elemBytes, 1, name), k_dtype(dtype), k_elemBytes(elemBytes)
     {
@@ -121,7 +122,8 @@ class WideScanDispatcher : public ExtensionBase {
         printf("Beginning %s validation test: \n", k_name);
         uint32_t passed = 0, total = 0;
         const uint64_t tile = 36864 / k_elemBytes;  // elements per tile of the compiled kernel
-        for (int algo : {GPS_ALGO_CSDL, GPS_ALGO_RTS})
+        // chained scan, chained scan with Decoupled Fallback (what csdldf_struct.wgsl is), Reduce-then-Scan
+        for (int algo : {GPS_ALGO_CSDL, GPS_ALGO_CSDL_FALLBACK, GPS_ALGO_RTS})
             for (int kind : {GPS_INCLUSIVE, GPS_EXCLUSIVE}) {
                 for (uint64_t n = tile - 3; n <= 2 * tile + 3; n += (n < tile + 3 || n > 2 * tile - 4) ? 1 : tile / 7) {
                     ++total;
@@ -133,6 +135,20 @@ class WideScanDispatcher : public ExtensionBase {
                 else printf("\n Test failed at size %llu \n", (unsigned long long)(k_maxBytes / k_elemBytes));
                 printf(".");
             }
+        // the emulated-deadlock harness of the wide scans: reference settings (mask 7, spin 4)
+        for (uint64_t n : {tile * 9 + 1, tile * 64, k_maxBytes / k_elemBytes}) {
+            ++total;
+            check(gps_init_ones_strided(m_a, n), "init");
+            if (k_dtype == GPS_U32X4) check(gps_init_ones(m_a, n * 4, GPS_U32, nullptr), "gps_init_ones");
+            check(gps_scan_wide_emulated_deadlock(m_ctx, GPS_INCLUSIVE, k_dtype, m_a, m_a, n, nullptr, 7, 4, nullptr, nullptr),
+                  "gps_scan_wide_emulated_deadlock");
+            uint64_t errs = ~0ull;
+            if (check(gps_check(m_ctx, nullptr), "gps_check") &&
+                check(gps_validate_ones_wide(m_a, n, GPS_INCLUSIVE, k_dtype, &errs), "validate") && errs == 0)
+                ++passed;
+            else
+                printf("\n Emulated-deadlock test failed at size %llu \n", (unsigned long long)n);
+        }
         if (passed == total) printf("\n%u/%u All tests passed.\n\n", passed, total);
         else printf("\n%u/%u Test failed.\n\n", passed, total);
         if (passed != total) m_ok = false;
@@ -142,7 +158,7 @@ class WideScanDispatcher : public ExtensionBase {
         printf("Beginning %s inclusive batch timing test at:\nSize: %llu\nTest size: %u\n", k_name,
                (unsigned long long)elems, batchCount);
         return timeLoop(elems, batchCount, "elements", [&] {
-            check(gps_scan_wide(m_ctx, GPS_ALGO_CSDL, GPS_INCLUSIVE, k_dtype, m_a, m_a, elems, nullptr, nullptr, nullptr),
+            check(gps_scan_wide(m_ctx, m_timingAlgo, GPS_INCLUSIVE, k_dtype, m_a, m_a, elems, nullptr, nullptr, nullptr),
                   "gps_scan_wide");
         });
     }
@@ -150,7 +166,12 @@ class WideScanDispatcher : public ExtensionBase {
 
 class StructScanDispatcher : public WideScanDispatcher {
    public:
-    explicit StructScanDispatcher(uint64_t maxElems) : WideScanDispatcher(maxElems, GPS_U32X4, 16, "GPS vec4<u32> struct scan") {}
+    // timed with the Decoupled Fallback variant: that is what the reference's struct scan is
+    // (csdldf_struct.wgsl), and it runs within 1 % of the plain chained kernel
+    explicit StructScanDispatcher(uint64_t maxElems) : WideScanDispatcher(maxElems, GPS_U32X4, 16, "GPS vec4<u32> struct scan")
+    {
+        m_timingAlgo = GPS_ALGO_CSDL_FALLBACK;
+    }
 };
 class Uint64ScanDispatcher : public WideScanDispatcher {
    public:
