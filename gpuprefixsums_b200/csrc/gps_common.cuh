@@ -163,6 +163,22 @@ __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// system-scope relaxed: the carry slots.  A slot word {value | tag} is self-contained -- nothing
+// else has to become visible with it -- so neither side needs release / acquire ordering; what
+// matters is that the access is STRONG at system scope (performed at the point of coherence, never
+// served from a stale line).  st.release.sys costs a system-wide fence per store, and a rank
+// publishes to every peer one after the other: with relaxed stores the G stores are in flight
+// together.
+__device__ __forceinline__ uint64_t ld_relaxed_sys(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p)
 {
     uint32_t v;
@@ -493,7 +509,7 @@ __device__ __forceinline__ T acquire_carry(const ScanParams& p, uint32_t lane)
         T v = T(0);
         if (i < p.n_slots) {
             uint32_t polls = 0;
-            uint64_t s = ld_acquire_sys(p.slots + i);
+            uint64_t s = ld_relaxed_sys(p.slots + i);
             bool ok = true;
             while ((uint32_t)(s >> 32) != p.slot_tag) {
                 if (++polls >= budget) {
@@ -502,7 +518,7 @@ __device__ __forceinline__ T acquire_carry(const ScanParams& p, uint32_t lane)
                     break;
                 }
                 __nanosleep(polls < 1024u ? 64u : 1000u);
-                s = ld_acquire_sys(p.slots + i);
+                s = ld_relaxed_sys(p.slots + i);
             }
             if (ok && i < p.n_carry) v = from_bits<T>((uint32_t)s);
         }
@@ -517,7 +533,7 @@ __device__ __forceinline__ void publish_total(const PublishList& pl, T total)
 {
     const uint64_t word = ((uint64_t)pl.tag << 32) | (uint64_t)to_bits(total);
 #pragma unroll 1
-    for (uint32_t i = 0; i < pl.n; ++i) st_release_sys(pl.dst[i], word);
+    for (uint32_t i = 0; i < pl.n; ++i) st_relaxed_sys(pl.dst[i], word);  // all in flight together
 }
 
 // grand total of a launch: plain value + tagged copies for downstream consumers
