@@ -61,6 +61,9 @@ def parse_args():
                     help="N>1 end-to-end leg: every rank through ShardedScan.scan_host, rank 0 alone through "
                          "gps_sharded_scan_host on all GPUs, or both (auto: report the faster, list both)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true",
+                    help="development: only the device-resident measurement (no end-to-end legs, no 2^33 point); "
+                         "prints a reduced line")
     ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
                     help="gps_set_option passthrough (tuning), e.g. poll_sleep_ns=100, tile_order=1")
     return ap.parse_args()
@@ -404,6 +407,17 @@ def run_ours(args) -> None:
     ms_per_step = timed_steps(step, args.steps, warm)
     value = n_total / (ms_per_step * 1e-3) / 1e9
     validate_slice(torch, dist, x, out, world, rank, dev)
+    if args.device_only:
+        if sampler:
+            sampler.stop()
+        if rank == 0:
+            print(json.dumps({"device_only": True, "n_gpus": world, "value": value, "unit": UNIT, "ms_per_step": ms_per_step,
+                              "steps": args.steps, "options": args.option}), flush=True)
+        if world > 1:
+            dist.barrier()
+            sh.close()
+            dist.destroy_process_group()
+        return
 
     # ---- end to end through the host-buffer call ----------------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 20)

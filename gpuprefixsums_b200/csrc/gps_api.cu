@@ -77,6 +77,9 @@ struct gps_ctx {
     bool rts_blocked_configured[2][2] = {{false, false}, {false, false}};
     int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile, 3 blocked tile
     int rts_variant = 0;            // 0 auto, 1 register-tile propagate, 2 blocked-tile propagate
+    int sharded_pdl = GPS_SHARDED_PDL_DEFAULT;  // see NoPdlScope
+    int sharded_l2 = GPS_SHARDED_L2_DEFAULT;    // option "sharded_l2"
+    int sharded_l2_keep_mb = GPS_SHARDED_L2_KEEP_MB;
     int l2_hints = -1;              // -1 auto, else PF_L2_* bits (bit 0 loads evict_first, bit 1 stores evict_last)
     uint64_t l2_bytes = 0;          // L2 size of the device
     bool wide_configured[5][2][3] = {};             // [dtype][kind][chained | rts | fallback]
@@ -141,7 +144,13 @@ int enter_stream(gps_ctx* c, cudaStream_t st, bool* capturing = nullptr);
 struct NoPdlScope {
     uint32_t& flags;
     const uint32_t saved;
-    explicit NoPdlScope(uint32_t& f) : flags(f), saved(f) { flags &= ~PF_PDL; }
+    // mode ("sharded_pdl"): 0 = every launch of the pair plain, 1 = only the one-block fold
+    // programmatic, 2 = fold and scan programmatic
+    explicit NoPdlScope(uint32_t& f, int mode = 0) : flags(f), saved(f)
+    {
+        if (mode < 2) flags &= ~PF_PDL;
+        if (mode >= 1 && (saved & PF_PDL)) flags |= PF_PDL_FOLD;
+    }
     ~NoPdlScope() { flags = saved; }
 };
 
@@ -357,11 +366,12 @@ int dispatch_scan(gps_ctx* c, int algo, int kind, int dtype, const void* in, voi
     } l2scope{c->s.flags, c->s.flags};
     {
         uint32_t bits = 0;
-        if (c->l2_hints >= 0) bits = (uint32_t)c->l2_hints;
+        if (c->l2_hints >= 0) bits = (uint32_t)c->l2_hints & 0xFFu;  // (bit 2: stores evict_first, internal)
         else if (n * 4 <= c->l2_bytes * GPS_L2_HINT_MAX_OUT_PCT / 100 && n * 4 >= c->l2_bytes * GPS_L2_HINT_MIN_OUT_PCT / 100)
             bits = GPS_L2_HINT_AUTO_BITS;
-        c->s.flags = (c->s.flags & ~(PF_L2_IN_EVICT_FIRST | PF_L2_OUT_EVICT_LAST)) |
-                     ((bits & 1u) ? PF_L2_IN_EVICT_FIRST : 0u) | ((bits & 2u) ? PF_L2_OUT_EVICT_LAST : 0u);
+        c->s.flags = (c->s.flags & ~(PF_L2_IN_EVICT_FIRST | PF_L2_OUT_EVICT_LAST | PF_L2_OUT_EVICT_FIRST)) |
+                     ((bits & 1u) ? PF_L2_IN_EVICT_FIRST : 0u) | ((bits & 2u) ? PF_L2_OUT_EVICT_LAST : 0u) |
+                     ((bits & 4u) ? PF_L2_OUT_EVICT_FIRST : 0u);
     }
     if (dtype == GPS_U32)
         return kind == GPS_INCLUSIVE ? dispatch_scan_tk<uint32_t, true>(c, algo, in, out, n, cs, st)
@@ -706,6 +716,18 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     } else if (!strcmp(key, "poll_sleep_ns")) {
         if (value < 0 || value > 100000) return fail(GPS_ERR_INVALID, "poll_sleep_ns out of range");
         c->s.poll_sleep_ns = (uint32_t)value;
+    } else if (!strcmp(key, "sharded_l2")) {
+        // L2 policies of the sharded step: 0 = none, bit 0 = the reduce pass keeps the front of the slice
+        // (evict_last) and streams the rest (evict_first), bit 1 = the scan's stores are evict_first,
+        // bit 2 = the scan's loads are evict_first
+        if (value < 0 || value > 7) return fail(GPS_ERR_INVALID, "sharded_l2 must be 0..7");
+        c->sharded_l2 = (int)value;
+    } else if (!strcmp(key, "sharded_l2_keep_mb")) {
+        if (value < 1 || value > 4096) return fail(GPS_ERR_INVALID, "sharded_l2_keep_mb out of range");
+        c->sharded_l2_keep_mb = (int)value;
+    } else if (!strcmp(key, "sharded_pdl")) {
+        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "sharded_pdl must be 0..2");
+        c->sharded_pdl = (int)value;
     } else if (!strcmp(key, "l2_hints")) {
         // L2 cache policies on the tile loads / stores of the smem-resident kernels: -1 = auto (default:
         // both for inputs whose output fits the L2, see dispatch), 0 = off, bit 0 = loads evict_first,
@@ -954,8 +976,13 @@ int gps_scan_carry_slots(gps_ctx* c, int algo, int kind, int dtype, const void* 
     cs.tag = tag;
     cs.total_out = d_total_out;
     if (!c) return fail(GPS_ERR_INVALID, "null ctx");
-    NoPdlScope plain(c->s.flags);
-    return dispatch_scan(c, algo, kind, dtype, d_in, d_out, n, cs, (cudaStream_t)stream);
+    NoPdlScope plain(c->s.flags, c->sharded_pdl);
+    // (dispatch_scan re-derives the PF_L2_* bits from l2_hints: pass the sharded step's through it)
+    const int saved_hints = c->l2_hints;
+    if (c->sharded_l2 & 6) c->l2_hints = 0x100 | ((c->sharded_l2 & 2) ? 4 : 0) | ((c->sharded_l2 & 4) ? 1 : 0);
+    const int rc = dispatch_scan(c, algo, kind, dtype, d_in, d_out, n, cs, (cudaStream_t)stream);
+    c->l2_hints = saved_hints;
+    return rc;
 }
 
 int gps_reduce_publish(gps_ctx* c, int dtype, const void* d_in, uint64_t n,
@@ -975,7 +1002,8 @@ int gps_reduce_publish(gps_ctx* c, int dtype, const void* d_in, uint64_t n,
     cudaStream_t st = (cudaStream_t)stream;
     rc = enter_stream(c, st);  // no epoch / ticket state: replay-safe as it is
     if (rc) return rc;
-    NoPdlScope plain(c->s.flags);
+    NoPdlScope plain(c->s.flags, c->sharded_pdl);
+    c->s.reduce_keep_bytes = (n_dst && (c->sharded_l2 & 1)) ? (uint64_t)c->sharded_l2_keep_mb << 20 : 0;
     const cudaError_t e =
         dtype == GPS_U32
             ? launch_reduce<uint32_t, GPS_RTS_NT, GPS_RTS_V>(c->s, d_in, n, d_total_out, pl, st)

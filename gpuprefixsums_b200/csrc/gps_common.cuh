@@ -84,6 +84,9 @@ enum : uint32_t {
     PF_LOOKBACK_WAIT_ALL = 512u, // experiment: consume a window only when all 32 are ready
     PF_LOOKBACK_SINGLE = 1024u,  // one-thread look-back (reference LookbackSingle, CSDL.cuh:28-47)
     PF_PDL = 4096u,              // host: launch with programmatic stream serialization (see pdl_entry)
+    PF_PDL_FOLD = 32768u,        // host: the one-block fold of gps_reduce_publish is launched programmatically
+    PF_L2_OUT_EVICT_FIRST = 65536u, // tile stores carry an L2 evict_first policy (the sharded scan: keep the input the
+                                    // reduce pass left in L2 instead of the output nobody re-reads)
     PF_L2_IN_EVICT_FIRST = 8192u,   // tile loads carry an L2 evict_first policy (input is read once)
     PF_L2_OUT_EVICT_LAST = 16384u,  // tile stores carry an L2 evict_last policy (output stays for the consumer)
 };
@@ -354,6 +357,8 @@ __device__ __forceinline__ void tile_bulk_store(uint32_t flags, void* gmem_dst, 
 {
     if (flags & PF_L2_OUT_EVICT_LAST)
         bulk_store_hint(gmem_dst, smem_src, bytes, l2_policy_evict_last());
+    else if (flags & PF_L2_OUT_EVICT_FIRST)
+        bulk_store_hint(gmem_dst, smem_src, bytes, l2_policy_evict_first());
     else
         bulk_store(gmem_dst, smem_src, bytes);
 }

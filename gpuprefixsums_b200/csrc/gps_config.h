@@ -170,3 +170,18 @@
 #ifndef GPS_L2_HINT_AUTO_BITS
 #define GPS_L2_HINT_AUTO_BITS 1
 #endif
+
+// programmatic dependent launch inside the sharded step (gps_reduce_publish + gps_scan_carry_slots):
+// 0 = plain launches, 1 = only the one-block fold, 2 = fold and scan (option "sharded_pdl")
+#ifndef GPS_SHARDED_PDL_DEFAULT
+#define GPS_SHARDED_PDL_DEFAULT 1  // measured on 2 GPUs: 0.4740 / 0.4727 / 0.4804 ms per step for 0 / 1 / 2
+#endif
+
+// L2 policies of the sharded step (option "sharded_l2", bits: 1 = reduce keeps the front of the slice,
+// 2 = scan stores evict_first, 4 = scan loads evict_first) and how much of the front is kept
+#ifndef GPS_SHARDED_L2_DEFAULT
+#define GPS_SHARDED_L2_DEFAULT 0
+#endif
+#ifndef GPS_SHARDED_L2_KEEP_MB
+#define GPS_SHARDED_L2_KEEP_MB 96
+#endif

@@ -52,6 +52,7 @@ struct Scratch {
     uint32_t epoch = 0;
     int sm_count = 148;
     uint32_t poll_sleep_ns = 0;
+    uint64_t reduce_keep_bytes = 0;  // gps_reduce_publish: front of the slice loaded evict_last (0 = no L2 policies)
     uint32_t slot_poll_limit = 0;  // 0 = kSlotPollsDefault (option "slot_wait_polls")
     uint32_t flags = 0;
     unsigned long long* prof = nullptr;  // optional profiling counters (tuning harness)
@@ -334,9 +335,13 @@ cudaError_t launch_reduce(Scratch& s, const void* in, uint64_t n, void* total_ou
     p.in = in;
     p.total_out = total_out;
     p.publish = pl;
+    p.keep_tiles = s.reduce_keep_bytes ? (uint32_t)std::min<uint64_t>(p.num_tiles, s.reduce_keep_bytes / (RegTile<T, NT, V>::TILE_KEYS * 4)) : 0u;
     const bool pdl = s.flags & PF_PDL;
     if (p.num_tiles) e = launch_scan_kernel(rts_reduce_kernel<T, NT, V>, p.num_tiles, NT, 0, st, pdl, p);
-    if (e == cudaSuccess) e = launch_scan_kernel(rts_fold_kernel<T>, 1, kSpineThreads, 0, st, pdl, p);
+    // the one-block fold may be launched programmatically even where the big kernels are not
+    // (PF_PDL_FOLD, the sharded step): its launch latency then hides behind the reduce's last wave
+    if (e == cudaSuccess)
+        e = launch_scan_kernel(rts_fold_kernel<T>, 1, kSpineThreads, 0, st, pdl || (s.flags & PF_PDL_FOLD), p);
     return e;
 }
 

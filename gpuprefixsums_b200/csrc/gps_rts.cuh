@@ -34,6 +34,8 @@ struct RtsParams {
     void* total_out;           // nullable
     PublishList publish;       // tagged total for downstream consumers
     uint32_t* status;
+    uint32_t keep_tiles;       // reduce: the first keep_tiles tiles are loaded with an L2 evict_last policy (the
+                               // scan that follows reads them first), the others evict_first; 0 = no policies
 };
 
 template <typename T, int NT>
@@ -61,10 +63,14 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 16 + 4 * V))
     const uint32_t tile = p.num_tiles - 1u - blockIdx.x;
     const uint64_t vbase = Tile::vec_base(tile, warp, lane);
     Tile t;
-    if (((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n)
-        t.load_full(p.in, vbase);
-    else
+    if (((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n) {
+        if (p.keep_tiles)  // block-uniform
+            t.load_full_policy(p.in, vbase, tile < p.keep_tiles ? l2_policy_evict_last() : l2_policy_evict_first());
+        else
+            t.load_full(p.in, vbase);
+    } else {
         t.load_partial(p.in, vbase, p.n);
+    }
     const T sum = block_reduce<T, NT>(t.thread_sum(), s_red, warp, lane);
     if (threadIdx.x == 0) reinterpret_cast<T*>(p.partials)[tile] = sum;
 }

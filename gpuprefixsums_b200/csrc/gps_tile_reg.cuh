@@ -59,6 +59,23 @@ struct RegTile {
         for (int k = 0; k < V; ++k) set_row(k, r[k]);
     }
 
+    // full tile, every load tagged with an L2 eviction policy (createpolicy descriptor)
+    __device__ __forceinline__ void load_full_policy(const void* in, uint64_t vbase, uint64_t policy)
+    {
+        const uint4* in4 = reinterpret_cast<const uint4*>(in);
+        uint4 r[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const uint4* a = in4 + vbase + 32u * k;
+            asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                         : "=r"(r[k].x), "=r"(r[k].y), "=r"(r[k].z), "=r"(r[k].w)
+                         : "l"(a), "l"(policy)
+                         : "memory");
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) set_row(k, r[k]);
+    }
+
     // partial (last) tile: keys at index >= n read as 0
     __device__ __forceinline__ void load_partial(const void* in, uint64_t vbase, uint64_t n)
     {
