@@ -1596,7 +1596,7 @@ gps_ctx* gps_sharded_ctx(gps_shard_group* g, int index)
 // "host_chunk_keys"; chunk q of the running sequence goes to GPU q % G: copy-in, scan, copy-out on
 // that GPU's three streams over its rotating staging buffers, exactly as gps_scan_host does on one
 // GPU.  The scan of chunk q seeds itself from the tagged running total its predecessor's last tile
-// stored into THIS GPU's slot over NVLink (st.release.sys -> ld.acquire.sys in tile 0's carry
+// stored into THIS GPU's slot over NVLink (st.relaxed.sys -> ld.relaxed.sys in tile 0's carry
 // acquisition) and publishes its own inclusive total to the next GPU's slot: the chunks' scans
 // form one chain across the GPUs (~20 us per 64 MiB link) while G copy-ins and G copy-outs run
 // concurrently -- 8 B/key of HBM traffic per key, no reduce pre-pass, no host synchronisation and

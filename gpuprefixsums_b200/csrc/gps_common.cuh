@@ -156,16 +156,6 @@ __device__ __forceinline__ void st_relaxed_gpu(uint64_t* p, uint64_t v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p)
-{
-    uint64_t v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 // system-scope relaxed: the carry slots.  A slot word {value | tag} is self-contained -- nothing
 // else has to become visible with it -- so neither side needs release / acquire ordering; what
 // matters is that the access is STRONG at system scope (performed at the point of coherence, never
@@ -495,7 +485,7 @@ __device__ __forceinline__ bool watchdog_tick(uint32_t& polls, uint32_t* status)
 // ---------------------------------------------------------------------------------
 // carry acquisition (tile 0 / spine): immediate carry + sum of the tagged carry slots.
 // Called by a full warp.  Slots may live in this GPU's memory and be written by peer
-// GPUs over NVLink (st.release.sys), hence system scope.
+// GPUs over NVLink (st.relaxed.sys), hence system scope.
 // ---------------------------------------------------------------------------------
 // The wait for a slot has its OWN poll budget, far larger than the look-back watchdog: the writer
 // is another GPU / process / pipeline stage that may legitimately be seconds late (lazy module

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kSpineThreads) rts_spine_kernel(const __grid_c
 }
 
 // Fold of the tile sums into one total, optionally published to (peer) carry slots with
-// st.release.sys -- the second half of gps_reduce / gps_reduce_publish.
+// st.relaxed.sys -- the second half of gps_reduce / gps_reduce_publish.
 template <typename T>
 __global__ void __launch_bounds__(kSpineThreads) rts_fold_kernel(const __grid_constant__ RtsParams p)
 {

@@ -219,7 +219,7 @@ int gps_sort_u32(gps_ctx* ctx, const void* d_keys_in, void* d_keys_out, void* d_
 
 /* Same, with the carry read ON THE DEVICE by tile 0 from 64-bit carry slots
  * {value bits : 32 | tag : 32} (low word = value).  Tile 0 polls all `n_slots` slots
- * with ld.acquire.sys until their tag equals `tag`, sums the values of the first
+ * with ld.relaxed.sys (strong, system scope; the word is self-contained) until their tag equals `tag`, sums the values of the first
  * `n_carry` (<= n_slots) of them and seeds the look-back chain -- the multi-GPU carry
  * "folded into the look-back" (slots may be written by peer GPUs over NVLink, see
  * gps_reduce_publish).  Polling more slots than are summed (all G ranks, not only the
@@ -234,7 +234,7 @@ int gps_scan_carry_slots(gps_ctx* ctx, int algo, int kind, int dtype, const void
 int gps_reduce(gps_ctx* ctx, int dtype, const void* d_in, uint64_t n, void* d_total_out,
                void* stream);
 
-/* Reduce + publish: writes {total bits | tag<<32} with st.release.sys to each of the
+/* Reduce + publish: writes {total bits | tag<<32} with st.relaxed.sys (system scope) to each of the
  * `n_dst` device addresses in h_dst_slots (host array of device pointers; may point
  * into peer-GPU memory mapped with gps_ipc_open / peer access). */
 int gps_reduce_publish(gps_ctx* ctx, int dtype, const void* d_in, uint64_t n,
