@@ -62,6 +62,7 @@ SIGNATURES = {
     "gps_reduce": (_i32, [_vp, _i32, _vp, _u64, _vp, _vp]),
     "gps_reduce_publish": (_i32, [_vp, _i32, _vp, _u64, C.POINTER(_vp), _u32, _u32, _vp, _vp]),
     "gps_scan_emulated_deadlock": (_i32, [_vp, _i32, _i32, _vp, _vp, _u64, _u32, _u32, _vp, _vp]),
+    "gps_scan_estimate_occupancy": (_i32, [_vp, _i32, _i32, _vp, _vp, _u64, C.POINTER(_u32), _vp]),
     "gps_scan_host": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
     "gps_scan_host_async": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp]),
     "gps_host_sync": (_i32, [_vp]),

@@ -1053,6 +1053,42 @@ int gps_scan_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void* d_in
     return GPS_OK;
 }
 
+int gps_scan_estimate_occupancy(gps_ctx* c, int kind, int dtype, const void* d_in, void* d_out, uint64_t n,
+                                uint32_t* h_occupancy, void* stream)
+{
+    int rc = check_scan_args(c, kind, dtype, d_in, d_out, n);
+    if (rc) return rc;
+    if (!h_occupancy) return fail(GPS_ERR_INVALID, "null occupancy out");
+    *h_occupancy = 0;
+    if (n == 0) return GPS_OK;
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool capturing = false;
+    rc = enter_stream(c, st, &capturing);
+    if (rc) return rc;
+    if (capturing) return fail(GPS_ERR_UNSUPPORTED, "gps_scan_estimate_occupancy is synchronous: not capturable");
+    uint32_t* d_occ = nullptr;
+    GPS_CUDA(cudaMalloc(&d_occ, sizeof(uint32_t)));
+    cudaError_t e = cudaMemsetAsync(d_occ, 0, sizeof(uint32_t), st);
+    CarrySpec cs;
+    const FallbackParams f{kNoStall, GPS_FALLBACK_DEFAULT_SPIN, nullptr};
+    if (e == cudaSuccess) {
+        if (dtype == GPS_U32)
+            e = kind == GPS_INCLUSIVE
+                    ? launch_csdl_fallback_occ<uint32_t, GPS_REG_NT, GPS_REG_V, true>(c->s, d_in, d_out, n, cs, f, d_occ, st)
+                    : launch_csdl_fallback_occ<uint32_t, GPS_REG_NT, GPS_REG_V, false>(c->s, d_in, d_out, n, cs, f, d_occ, st);
+        else
+            e = kind == GPS_INCLUSIVE
+                    ? launch_csdl_fallback_occ<float, GPS_REG_NT, GPS_REG_V, true>(c->s, d_in, d_out, n, cs, f, d_occ, st)
+                    : launch_csdl_fallback_occ<float, GPS_REG_NT, GPS_REG_V, false>(c->s, d_in, d_out, n, cs, f, d_occ, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_occupancy, d_occ, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_occ);
+    if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "occupancy scan failed: %s", cudaGetErrorString(e));
+    return GPS_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // host-buffer pipeline: H2D(c+1) || scan(c) || D2H(c-1), chunk totals chained on device
 // ---------------------------------------------------------------------------------

@@ -112,30 +112,20 @@ constexpr uint32_t kNoStall = 0xFFFFFFFFu;
 
 enum : uint32_t { LB_DONE = 0, LB_FALLBACK = 1 };
 
+// one tile of the chained scan with Decoupled Fallback (the whole pipeline after the claim)
 template <typename T, int NT, int V, bool INCLUSIVE>
-__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
-    csdl_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
+__device__ __forceinline__ void csdl_fallback_tile(const ScanParams& p, const FallbackParams& f, const uint32_t tile)
 {
-    pdl_entry();
     using Tile = RegTile<T, NT, V>;
     constexpr int NW = Tile::NW;
     __shared__ T s_warp[NW];
     __shared__ T s_red[NW];
     __shared__ T s_prefix;
-    __shared__ uint32_t s_tile;
     __shared__ uint32_t s_state;     // LB_DONE / LB_FALLBACK
     __shared__ uint32_t s_fb_tile;   // tile to recompute
 
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
-
-    if (threadIdx.x == 0) s_tile = claim_tile(p);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
-        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
-        return;
-    }
     const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
     const uint64_t vbase = Tile::vec_base(tile, warp, lane);
 
@@ -322,6 +312,45 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
         t.template store_full<INCLUSIVE>(p.out, vbase, out_prefix);
     else
         t.template store_partial<INCLUSIVE>(p.out, vbase, p.n, out_prefix);
+}
+
+template <typename T, int NT, int V, bool INCLUSIVE>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
+    csdl_fallback_kernel(const __grid_constant__ ScanParams p, const FallbackParams f)
+{
+    pdl_entry();
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = claim_tile(p);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
+        if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
+        return;
+    }
+    csdl_fallback_tile<T, NT, V, INCLUSIVE>(p, f, tile);
+}
+
+// Occupancy-estimation variant (GPUPrefixSumsWebGPUapis/SharedShaders/TestVariants/csdldf_occ.wgsl:
+// 72-82): the same scan, but every CTA keeps claiming tiles until none are left, and a CTA counts
+// itself once if its FIRST claim was a real tile.  With one CTA launched per tile, only the CTAs
+// resident at the start ever get a tile (those launched later find the counter exhausted), so the
+// count estimates how many CTAs of this kernel the device holds at once.  The result of the scan
+// stays correct.  Claims made: num_tiles + gridDim.x.
+template <typename T, int NT, int V, bool INCLUSIVE>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
+    csdl_fallback_occ_kernel(const __grid_constant__ ScanParams p, const FallbackParams f, uint32_t* occupancy)
+{
+    pdl_entry();
+    __shared__ uint32_t s_tile;
+    for (bool first = true;; first = false) {
+        if (threadIdx.x == 0) s_tile = claim_tile(p);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= p.num_tiles) break;
+        if (first && threadIdx.x == 0) atomicAdd(occupancy, 1u);
+        csdl_fallback_tile<T, NT, V, INCLUSIVE>(p, f, tile);
+        __syncthreads();  // shared state of the tile pipeline is reused by the next tile
+    }
 }
 
 }  // namespace gps

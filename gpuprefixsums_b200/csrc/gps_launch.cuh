@@ -218,6 +218,19 @@ cudaError_t launch_csdl_fallback(Scratch& s, const void* in, void* out, uint64_t
     return e;
 }
 
+// occupancy-estimation variant: one CTA per tile is launched, the resident ones drain the tickets
+template <typename T, int NT, int V, bool INCL>
+cudaError_t launch_csdl_fallback_occ(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                                     const FallbackParams& f, uint32_t* d_occupancy, cudaStream_t st)
+{
+    using Tile = RegTile<T, NT, V>;
+    ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
+    const cudaError_t e = launch_scan_kernel(csdl_fallback_occ_kernel<T, NT, V, INCL>, p.num_tiles, NT, 0, st, false, p, f,
+                                             d_occupancy);
+    if (e == cudaSuccess) s.counter_base += 2u * p.num_tiles;  // every CTA claims until it draws a ticket past the end
+    return e;
+}
+
 // the same on the shared-memory-resident tile (gps_csdl_smem.cuh)
 template <typename T, int NT, int V, bool INCL>
 cudaError_t launch_csdl_smem_fallback(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,

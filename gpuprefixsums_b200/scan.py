@@ -241,6 +241,14 @@ class PrefixSum:
                                              _stream_ptr(stream, self.device)))
         return out
 
+    def estimate_occupancy(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *, exclusive: bool = False):
+        """(scan result, estimated number of concurrently resident CTAs) -- the reference's csdldf_occ variant."""
+        inp, out = self._prep(inp, out)
+        occ = C.c_uint32(0)
+        check(lib.gps_scan_estimate_occupancy(self._ctx, _kind(exclusive), _dtype_code(inp), inp.data_ptr(), out.data_ptr(),
+                                              inp.numel(), C.byref(occ), _stream_ptr(None, self.device)))
+        return out, int(occ.value)
+
     def scan_host(self, h_in: torch.Tensor, h_out: Optional[torch.Tensor] = None, *, algo="csdl",
                   exclusive: bool = False, carry=0, wait: bool = True) -> torch.Tensor:
         """Host buffers in, host buffers out (pinned recommended).  wait=False returns once the

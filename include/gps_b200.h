@@ -254,6 +254,15 @@ int gps_scan_emulated_deadlock(gps_ctx* ctx, int kind, int dtype, const void* d_
                                void* d_out, uint64_t n, uint32_t stall_mask,
                                uint32_t max_spin, uint32_t* d_stats, void* stream);
 
+/* Occupancy-estimation variant of the Decoupled Fallback scan (GPUPrefixSumsWebGPUapis/SharedShaders/
+ * TestVariants/csdldf_occ.wgsl:72-82, read back by Dawn/main.cpp:663-667,833-836): one CTA per tile is
+ * launched, every CTA keeps claiming tiles until none are left and counts itself once if its first
+ * claim was a real tile; *h_occupancy = that count = an estimate of how many CTAs of the kernel the
+ * device holds at once (for inputs with more tiles than that).  d_out receives the correct scan.
+ * Synchronous. */
+int gps_scan_estimate_occupancy(gps_ctx* ctx, int kind, int dtype, const void* d_in, void* d_out,
+                                uint64_t n, uint32_t* h_occupancy, void* stream);
+
 /* The reference-facing call with HOST buffers: pipelined H2D -> scan -> D2H in
  * chunks on internal streams, chunk totals chained on the device.  Synchronous.
  * h_in / h_out should be pinned for full PCIe bandwidth (pageable works). */

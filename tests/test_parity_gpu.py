@@ -616,3 +616,26 @@ def test_cuda_graph_capture(gps, oracle):
         assert np.array_equal(to_np_u32(plain), want), seed
     ps.check()
     ps.close()
+
+
+def test_occupancy_estimation_variant(gps, oracle):
+    """The reference's csdldf_occ test variant: persistent CTAs drain the tickets, the ones whose first
+    claim was a real tile count themselves; the scan stays bit-exact and later scans on the ctx are
+    unaffected (ticket accounting: 2 x tiles claims)."""
+    ps = gps.PrefixSum(1 << 24)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for n in [1, 6143, 6145, 100_003, (1 << 24) - 5]:
+        x = oracle.random_u32(n, seed=n % 1000)
+        for exclusive in (False, True):
+            out, occ = ps.estimate_occupancy(to_dev_u32(x), exclusive=exclusive)
+            ps.check()
+            want, _ = oracle.scan_u32(x, exclusive=exclusive)
+            assert np.array_equal(to_np_u32(out), want), (n, exclusive)
+            tiles = -(-n // 6144)
+            assert 1 <= occ <= tiles
+            if tiles > 64 * sms:  # many more tiles than the device can hold: the count is the residency
+                assert sms <= occ <= 16 * sms, occ
+        got = ps.scan(to_dev_u32(x))  # the never-reset ticket counter is still in step
+        ps.check()
+        assert np.array_equal(to_np_u32(got), oracle.scan_u32(x)[0])
+    ps.close()

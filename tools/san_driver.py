@@ -47,7 +47,42 @@ for dtype, es in ((capi.U64, 8), (capi.F64, 8), (capi.U32X4, 16), (capi.U32, 4))
         for kind in (capi.INCLUSIVE, capi.EXCLUSIVE):
             check(lib.gps_scan_wide(ctx, algo, kind, dtype, a, b, (N * 4) // es - 1, None, None, None))
             check(lib.gps_scan_wide(ctx, algo, kind, dtype, a, a, 37, None, None, None))  # in place, one partial tile
+# round 2: Decoupled Fallback for the wide scans (production variant, emulated stalls, in place)
+for dtype, es in ((capi.U64, 8), (capi.F64, 8), (capi.U32X4, 16), (capi.U32, 4)):
+    for kind in (capi.INCLUSIVE, capi.EXCLUSIVE):
+        nel = (N * 4) // es - 1
+        check(lib.gps_scan_wide(ctx, capi.ALGO_CSDL_FALLBACK, kind, dtype, a, b, nel, None, None, None))
+        check(lib.gps_scan_wide_emulated_deadlock(ctx, kind, dtype, a, b, nel, None, 7, 2, stats, None))
+        check(lib.gps_memcpy_d2d(f, a, N * 4, None))
+        check(lib.gps_scan_wide_emulated_deadlock(ctx, kind, dtype, f, f, nel, None, 1, 1, stats, None))  # in place
+# round 2: occupancy-estimation variant (persistent CTAs)
+occ = C.c_uint32(0)
+check(lib.gps_scan_estimate_occupancy(ctx, capi.INCLUSIVE, capi.U32, a, b, N, C.byref(occ), None))
+check(lib.gps_scan_estimate_occupancy(ctx, capi.EXCLUSIVE, capi.F32, a, b, 1 << 20, C.byref(occ), None))
+# round 2: L2 cache policies on the tile loads / stores, sharded-step options
+for hints in (1, 2, 3):
+    check(lib.gps_set_option(ctx, b"l2_hints", hints))
+    for algo in (capi.ALGO_CSDL_SMEM, capi.ALGO_CSDL_BLOCKED):
+        check(lib.gps_scan(ctx, algo, capi.INCLUSIVE, capi.U32, a, b, 1 << 20, 0, None, None))
+check(lib.gps_set_option(ctx, b"l2_hints", -1))
+slots = C.c_void_p()
+check(lib.gps_malloc(C.byref(slots), 64 * 8))
+check(lib.gps_memset(slots, 0, 64 * 8, None))
+for l2 in (0, 7):
+    check(lib.gps_set_option(ctx, b"sharded_l2", l2))
+    for tag in (1, 2):
+        dst = (C.c_void_p * 1)(slots.value + (tag & 1) * 16 * 8)
+        check(lib.gps_reduce_publish(ctx, capi.U32, a, 1 << 20, dst, 1, tag, None, None))
+        check(lib.gps_scan_carry_slots(ctx, capi.ALGO_CSDL_BLOCKED, capi.INCLUSIVE, capi.U32, a, b, 1 << 20,
+                                       slots.value + (tag & 1) * 16 * 8, 1, 0, tag, None, None))
+check(lib.gps_set_option(ctx, b"sharded_l2", 0))
 check(lib.gps_init_random(a, 1 << 20, capi.U32, 9, 0xFFFFFFFF, 0, None))
+# round 2: the sort with Decoupled Fallback in the digit look-back (no stalls / emulated stalls), partial digit
+for n in (N, 10_240):
+    check(lib.gps_sort_keys32_fallback(ctx, 0, a, b, c, None, None, None, n, 32, 0xFFFFFFFF, 4, None, None))
+    check(lib.gps_sort_keys32_fallback(ctx, 0, a, b, c, a, d, e, n, 32, 7, 2, stats, None))
+    check(lib.gps_sort_keys32_fallback(ctx, 1, a, b, c, None, None, None, n, 32, 1, 1, stats, None))
+    check(lib.gps_sort_u32(ctx, a, b, c, None, None, None, n, 13, None))
 for n in (N, 10_240, 3):
     check(lib.gps_sort_u32(ctx, a, b, c, None, None, None, n, 32, None))
     check(lib.gps_sort_u32(ctx, a, b, c, a, d, e, n, 32, None))
@@ -65,6 +100,23 @@ for k in range(3):
     check(lib.gps_scan_host_async(ctx, capi.ALGO_CSDL, k & 1, capi.U32, hin, hout, N - k, k, None))
 check(lib.gps_host_sync(ctx))
 check(lib.gps_check(ctx, None))
+# round 2: the multi-GPU host entry with three "GPUs" on device 0, I/O routing, calibration
+grp = C.c_void_p()
+devs = (C.c_int * 3)(0, 0, 0)
+check(lib.gps_sharded_create(C.byref(grp), 3, devs, 1 << 15))
+for i in range(3):
+    check(lib.gps_set_option(lib.gps_sharded_ctx(grp, i), b"host_chunk_keys", 1 << 13))
+tot = C.c_uint32(0)
+for k in range(3):
+    check(lib.gps_sharded_scan_host_async(grp, capi.ALGO_CSDL, k & 1, capi.U32, hin, hout, N - k, k, None))
+check(lib.gps_sharded_host_sync(grp))
+io = (C.c_int * 2)(2, 0)
+check(lib.gps_sharded_set_host_io(grp, io, 2))
+check(lib.gps_sharded_scan_host(grp, capi.ALGO_RTS, capi.INCLUSIVE, capi.F32, hin, hout, N, 0, None))
+rate = C.c_float(0)
+check(lib.gps_sharded_calibrate_host(grp, hin, hout, N * 4, C.byref(rate)))
+check(lib.gps_sharded_scan_host(grp, capi.ALGO_CSDL_FALLBACK, capi.INCLUSIVE, capi.U32, hin, hout, N, 0, None))
+lib.gps_sharded_destroy(grp)
 inv, sums = C.c_uint64(0), (C.c_uint64 * 2)()
 check(lib.gps_sort_fingerprint(b, 3, C.byref(inv), sums))
 lib.gps_destroy(ctx)
