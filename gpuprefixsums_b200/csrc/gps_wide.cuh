@@ -580,7 +580,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
                     for (int i = 0; i < W; ++i) words[i] = (uint32_t)(inc_ok ? w[W + i] : w[i]);
                     v = wide_from_words<E>(words);
                 }
-                if (stats && lane == 0) ++s_stats[3];
+                if (stats && lane == 0) atomicAdd(&s_stats[3], 1u);
                 const uint32_t not_ready = __ballot_sync(kFullMask, st == ST_NOT_READY);
                 const uint32_t first_nr = not_ready ? (uint32_t)__ffs((int)not_ready) - 1u : 32u;
                 const uint32_t below = first_nr >= 32u ? kFullMask : ((1u << first_nr) - 1u);
@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
                     spins = 0;
                     continue;
                 }
-                if (stats && lane == 0) ++s_stats[0];
+                if (stats && lane == 0) atomicAdd(&s_stats[0], 1u);
                 const bool bail = watchdog_tick(polls, p.status);
                 if (__any_sync(kFullMask, bail)) break;
                 if (++spins < f.max_spin) continue;
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
         // ---- Decoupled Fallback: every thread re-reads ITS blocked run of tile fb (a fallback
         // target is never the last tile => always full) and the CTA repeats pass 1 on it
         const uint32_t fb = s_fb_tile;
-        if (stats && tid == 0) ++s_stats[1];
+        if (stats && tid == 0) atomicAdd(&s_stats[1], 1u);  // (atomic: a plain ++ lets the compiler hoist the load above the predicate, which racecheck flags)
         {
             const uint4* in4 = reinterpret_cast<const uint4*>(p.in) + (uint64_t)fb * S::TILE_VEC + v0;
             E facc = wide_zero<E>();
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
             if (lane < (uint32_t)W)
                 inserted = wide_word_cas_insert<E>(p.desc + (uint64_t)fb * (2 * W) + (fb ? 0 : W) + lane,
                                                    wide_word(red, lane), p.epoch, got);
-            if (stats && __any_sync(kFullMask, inserted) && lane == 0) ++s_stats[2];
+            if (stats && __any_sync(kFullMask, inserted) && lane == 0) atomicAdd(&s_stats[2], 1u);
             // the value in the descriptor (mine or the owner's: identical unless my read raced
             // with an in-place overwrite, in which case every word is the owner's)
             uint32_t words[W];
