@@ -111,8 +111,8 @@ struct gps_ctx {
     uint64_t sort_desc_tiles = 0;
     uint32_t* sort_hist = nullptr;
     uint32_t sort_epoch = 0;
-    bool sort_configured[8] = {};   // [pairs + 2 * key-map variant + 4 * Decoupled Fallback]
-    bool sort_hist_configured = false;
+    bool sort_configured[16] = {};  // [pairs + 2 * key-map variant + 4 * Decoupled Fallback + 8 * 64-bit keys]
+    bool sort_hist_configured[2] = {false, false};  // [64-bit keys]
 };
 
 namespace {
@@ -481,26 +481,156 @@ int fill_publish(PublishList& pl, uint64_t* const* dst, uint32_t n_dst, uint32_t
 // library / device
 // ---------------------------------------------------------------------------------
 namespace {
-constexpr uint32_t kSortTile = (uint32_t)GPS_SORT_NT * GPS_SORT_KPT;
-constexpr uint32_t kSortPairsTile = (uint32_t)GPS_SORT_PAIRS_NT * GPS_SORT_PAIRS_KPT;
-constexpr uint32_t kSortMinTile = kSortTile < kSortPairsTile ? kSortTile : kSortPairsTile;
+// tile shapes of the digit pass per key width: 32-bit keys <NT, KPT> / pairs, 64-bit keys / pairs
+template <typename K, bool PAIRS>
+struct SortShape {
+    static constexpr bool W64 = sizeof(K) == 8;
+    static constexpr int NT = W64 ? GPS_SORT64_NT : (PAIRS ? GPS_SORT_PAIRS_NT : GPS_SORT_NT);
+    static constexpr int KPT = W64 ? (PAIRS ? GPS_SORT64_PAIRS_KPT : GPS_SORT64_KPT) : (PAIRS ? GPS_SORT_PAIRS_KPT : GPS_SORT_KPT);
+    static constexpr int REGS = W64 ? GPS_SORT64_REGS : (PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS);
+    static constexpr uint32_t TILE = (uint32_t)NT * KPT;
+    static constexpr size_t SMEM = ((size_t)(sizeof(K) / 4 + (PAIRS ? 1 : 0)) * TILE + (size_t)(NT / 32) * kRadix) * sizeof(uint32_t);
+};
+constexpr uint32_t cmin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+constexpr uint32_t kSortMinTile = cmin(cmin(SortShape<uint32_t, false>::TILE, SortShape<uint32_t, true>::TILE),
+                                       cmin(SortShape<uint64_t, false>::TILE, SortShape<uint64_t, true>::TILE));
 
-template <bool PAIRS, bool XFORM, bool FB = false>
+template <typename K, bool PAIRS, bool XFORM, bool FB = false>
 cudaError_t launch_sort_pass(const SortParams& p, bool& configured, bool pdl, cudaStream_t st,
                              const SortFallbackParams& f = SortFallbackParams{0xFFFFFFFFu, 1u, nullptr})
 {
-    constexpr int NT = PAIRS ? GPS_SORT_PAIRS_NT : GPS_SORT_NT, KPT = PAIRS ? GPS_SORT_PAIRS_KPT : GPS_SORT_KPT;
-    constexpr size_t smem = ((size_t)(PAIRS ? 2 : 1) * NT * KPT + (size_t)(NT / 32) * kRadix) * sizeof(uint32_t);
-    auto kern = sort_pass_kernel<NT, KPT, PAIRS, PAIRS ? GPS_SORT_PAIRS_REGS : GPS_SORT_REGS, GPS_SORT_LB, XFORM, FB>;
+    using S = SortShape<K, PAIRS>;
+    auto kern = sort_pass_kernel<K, S::NT, S::KPT, PAIRS, S::REGS, GPS_SORT_LB, XFORM, FB>;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    return launch_scan_kernel(kern, p.num_tiles, NT, smem, st, pdl, p, f);
+    return launch_scan_kernel(kern, p.num_tiles, S::NT, S::SMEM, st, pdl, p, f);
 }
+template <typename K>
+int sort_impl(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                     const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit,
+                     void* stream, const SortFallbackParams* fbp)
+{
+    constexpr int kBits = (int)sizeof(K) * 8;
+    constexpr bool W64 = sizeof(K) == 8;
+    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
+    const int base_type = key_type & ~GPS_KEY_DESCENDING;
+    if (base_type != GPS_KEY_U32 && base_type != GPS_KEY_I32 && base_type != GPS_KEY_F32)
+        return fail(GPS_ERR_INVALID, "bad key type %d", key_type);
+    if (key_type != GPS_KEY_U32 && end_bit != kBits)
+        return fail(GPS_ERR_INVALID, "signed / floating-point / descending sorts use all %d bits (end_bit %d)", kBits, kBits);
+    if (end_bit < 1 || end_bit > kBits) return fail(GPS_ERR_INVALID, "end_bit %d outside 1..%d", end_bit, kBits);
+    if (n >= (1ull << 32)) return fail(GPS_ERR_INVALID, "the sort takes fewer than 2^32 keys");
+    const bool pairs = d_vals_in || d_vals_out || d_vals_tmp;
+    if (n == 0) return GPS_OK;
+    if (!d_keys_in || !d_keys_out || !d_keys_tmp) return fail(GPS_ERR_INVALID, "null key pointer");
+    if (pairs && (!d_vals_in || !d_vals_out || !d_vals_tmp)) return fail(GPS_ERR_INVALID, "null value pointer");
+    if (!aligned16(d_keys_in) || !aligned16(d_keys_out) || !aligned16(d_keys_tmp))
+        return fail(GPS_ERR_ALIGNMENT, "key pointers must be 16-byte aligned");
+    if (pairs && (!aligned16(d_vals_in) || !aligned16(d_vals_out) || !aligned16(d_vals_tmp)))
+        return fail(GPS_ERR_ALIGNMENT, "value pointers must be 16-byte aligned");
+    if (d_keys_tmp == d_keys_in || d_keys_tmp == d_keys_out || (pairs && (d_vals_tmp == d_vals_in || d_vals_tmp == d_vals_out)))
+        return fail(GPS_ERR_INVALID, "the tmp buffer must be distinct from in and out");
+    const int passes = (end_bit + 7) / 8;
+    // bits of the last digit that take part: a sort on end_bit bits orders by key & (2^end_bit - 1)
+    // and nothing else (cub's end_bit), so the last pass masks its digit when end_bit % 8 != 0
+    const uint32_t last_mask = (end_bit & 7) ? ((1u << (end_bit & 7)) - 1u) : 0xFFu;
+    if ((passes & 1) && (d_keys_in == d_keys_out || (pairs && d_vals_in == d_vals_out)))
+        return fail(GPS_ERR_INVALID, "in == out needs an even number of digit passes (ceil(end_bit / 8) even)");
+    DeviceGuard g(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    bool capturing = false;
+    if (int rc = enter_stream(c, st, &capturing)) return rc;
+    const uint32_t tile = pairs ? SortShape<K, true>::TILE : SortShape<K, false>::TILE;
+    const uint32_t tiles = (uint32_t)div_up(n, tile);
+    if (capturing && tiles > c->sort_desc_tiles)
+        return fail(GPS_ERR_UNSUPPORTED, "capture needs one gps_sort call of at least this size outside the capture first");
+    CaptureScope cap;
+    if (capturing)
+        if (int rc = cap.begin(c, st, CaptureScope::SORT)) return rc;
+    if (tiles > c->sort_desc_tiles) {  // grow (synchronous, rare)
+        GPS_CUDA(cudaDeviceSynchronize());
+        if (c->sort_desc) cudaFree(c->sort_desc);
+        c->sort_desc = nullptr;
+        c->sort_desc_tiles = 0;
+        GPS_CUDA(cudaMalloc(&c->sort_desc, (size_t)tiles * kRadix * sizeof(uint64_t)));
+        GPS_CUDA(cudaMemset(c->sort_desc, 0, (size_t)tiles * kRadix * sizeof(uint64_t)));
+        if (c->g_sort_desc) cudaFree(c->g_sort_desc);  // shadow for captured sorts (CaptureScope)
+        c->g_sort_desc = nullptr;
+        GPS_CUDA(cudaMalloc(&c->g_sort_desc, (size_t)tiles * kRadix * sizeof(uint64_t)));
+        c->sort_desc_tiles = tiles;
+        c->sort_epoch = 0;
+    }
+    if (!c->sort_hist) GPS_CUDA(cudaMalloc(&c->sort_hist, 2 * kMaxSortPasses * kRadix * sizeof(uint32_t)));
+    uint32_t* hist = c->sort_hist;
+    uint32_t* digit_base = c->sort_hist + kMaxSortPasses * kRadix;
+    GPS_CUDA(cudaMemsetAsync(hist, 0, kMaxSortPasses * kRadix * sizeof(uint32_t), st));
+    {
+        bool& cfg = c->sort_hist_configured[W64 ? 1 : 0];
+        if (!cfg) {
+            GPS_CUDA(cudaFuncSetAttribute(sort_hist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes));
+            cfg = true;
+        }
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->s.sm_count, div_up(n, (16 / sizeof(K)) * kHistThreads));
+        for (int pass0 = 0; pass0 < passes; pass0 += 4)  // the shared-memory table holds 4 passes: 64-bit keys take two sweeps
+            sort_hist_kernel<K><<<grid, kHistThreads, kHistSmemBytes, st>>>((const K*)d_keys_in, (uint32_t)n, hist, pass0,
+                                                                        std::min(4, passes - pass0), passes,
+                                                                        (uint32_t)key_type, last_mask);
+        sort_digit_base_kernel<<<passes, kRadix, 0, st>>>(hist, digit_base);
+    }
+    // ping-pong so that the last pass lands in `out`
+    const void* src_k = d_keys_in;
+    const uint32_t* src_v = (const uint32_t*)d_vals_in;
+    const int cfg0 = W64 ? 8 : 0;
+    for (int pass = 0; pass < passes; ++pass) {
+        const bool to_out = ((passes - 1 - pass) & 1) == 0;
+        SortParams p{};
+        p.keys_in = src_k;
+        p.keys_out = to_out ? d_keys_out : d_keys_tmp;
+        p.vals_in = src_v;
+        p.vals_out = (uint32_t*)(to_out ? d_vals_out : d_vals_tmp);
+        p.n = (uint32_t)n;
+        p.shift = 8u * pass;
+        p.desc = c->sort_desc;
+        p.digit_base = digit_base + pass * kRadix;
+        p.counter = c->s.counter;
+        p.counter_base = c->s.counter_base;
+        if (++c->sort_epoch >= (1u << 30)) {  // wrap: epoch values would alias -> clear once
+            GPS_CUDA(cudaMemsetAsync(c->sort_desc, 0, (size_t)c->sort_desc_tiles * kRadix * sizeof(uint64_t), st));
+            c->sort_epoch = 1;
+        }
+        p.epoch = c->sort_epoch;
+        p.num_tiles = tiles;
+        p.status = c->s.status;
+        p.xform_in = pass == 0 ? (uint32_t)key_type : 0u;
+        p.xform_out = pass == passes - 1 ? (uint32_t)key_type : 0u;
+        p.digit_mask = pass == passes - 1 ? last_mask : 0xFFu;
+        const bool xf = p.xform_in || p.xform_out || p.digit_mask != 0xFFu;
+        const bool pdl = c->s.flags & PF_PDL;
+        cudaError_t e;
+        if (fbp)
+            e = pairs ? (xf ? launch_sort_pass<K, true, true, true>(p, c->sort_configured[cfg0 + 7], pdl, st, *fbp)
+                            : launch_sort_pass<K, true, false, true>(p, c->sort_configured[cfg0 + 5], pdl, st, *fbp))
+                      : (xf ? launch_sort_pass<K, false, true, true>(p, c->sort_configured[cfg0 + 6], pdl, st, *fbp)
+                            : launch_sort_pass<K, false, false, true>(p, c->sort_configured[cfg0 + 4], pdl, st, *fbp));
+        else
+            e = pairs ? (xf ? launch_sort_pass<K, true, true>(p, c->sort_configured[cfg0 + 3], pdl, st)
+                            : launch_sort_pass<K, true, false>(p, c->sort_configured[cfg0 + 1], pdl, st))
+                      : (xf ? launch_sort_pass<K, false, true>(p, c->sort_configured[cfg0 + 2], pdl, st)
+                            : launch_sort_pass<K, false, false>(p, c->sort_configured[cfg0 + 0], pdl, st));
+        if (e == cudaSuccess) c->s.counter_base += tiles;  // one claim per CTA of a launch that happened
+        GPS_CUDA(e);
+        src_k = p.keys_out;
+        src_v = p.vals_out;
+    }
+    GPS_CUDA(cudaGetLastError());
+    return GPS_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -823,7 +953,8 @@ int gps_scan_wide_emulated_deadlock(gps_ctx* c, int kind, int dtype, const void*
 // ---------------------------------------------------------------------------------
 uint64_t gps_sort_scratch_bytes(uint64_t n)
 {
-    return std::max<uint64_t>(1, div_up(n, kSortMinTile)) * kRadix * sizeof(uint64_t) + 2 * 4 * kRadix * sizeof(uint32_t);
+    return std::max<uint64_t>(1, div_up(n, kSortMinTile)) * kRadix * sizeof(uint64_t) +
+           2 * kMaxSortPasses * kRadix * sizeof(uint32_t);
 }
 
 int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp, const void* d_vals_in,
@@ -833,123 +964,11 @@ int gps_sort_u32(gps_ctx* c, const void* d_keys_in, void* d_keys_out, void* d_ke
                            end_bit, stream);
 }
 
-static int sort_keys32_impl(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
-                            const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit,
-                            void* stream, const SortFallbackParams* fbp)
-{
-    if (!c) return fail(GPS_ERR_INVALID, "null ctx");
-    const int base_type = key_type & ~GPS_KEY_DESCENDING;
-    if (base_type != GPS_KEY_U32 && base_type != GPS_KEY_I32 && base_type != GPS_KEY_F32)
-        return fail(GPS_ERR_INVALID, "bad key type %d", key_type);
-    if (key_type != GPS_KEY_U32 && end_bit != 32)
-        return fail(GPS_ERR_INVALID, "int32 / float32 / descending sorts use all 32 bits (end_bit 32)");
-    if (end_bit < 1 || end_bit > 32) return fail(GPS_ERR_INVALID, "end_bit %d outside 1..32", end_bit);
-    if (n >= (1ull << 32)) return fail(GPS_ERR_INVALID, "gps_sort_u32 takes fewer than 2^32 keys");
-    const bool pairs = d_vals_in || d_vals_out || d_vals_tmp;
-    if (n == 0) return GPS_OK;
-    if (!d_keys_in || !d_keys_out || !d_keys_tmp) return fail(GPS_ERR_INVALID, "null key pointer");
-    if (pairs && (!d_vals_in || !d_vals_out || !d_vals_tmp)) return fail(GPS_ERR_INVALID, "null value pointer");
-    if (!aligned16(d_keys_in) || !aligned16(d_keys_out) || !aligned16(d_keys_tmp))
-        return fail(GPS_ERR_ALIGNMENT, "key pointers must be 16-byte aligned");
-    if (d_keys_tmp == d_keys_in || d_keys_tmp == d_keys_out || (pairs && (d_vals_tmp == d_vals_in || d_vals_tmp == d_vals_out)))
-        return fail(GPS_ERR_INVALID, "the tmp buffer must be distinct from in and out");
-    const int passes = (end_bit + 7) / 8;
-    // bits of the last digit that take part: a sort on end_bit bits orders by key & (2^end_bit - 1)
-    // and nothing else (cub's end_bit), so the last pass masks its digit when end_bit % 8 != 0
-    const uint32_t last_mask = (end_bit & 7) ? ((1u << (end_bit & 7)) - 1u) : 0xFFu;
-    if ((passes & 1) && (d_keys_in == d_keys_out || (pairs && d_vals_in == d_vals_out)))
-        return fail(GPS_ERR_INVALID, "in == out needs an even number of digit passes (end_bit 9..16 or 25..32)");
-    DeviceGuard g(c->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    bool capturing = false;
-    if (int rc = enter_stream(c, st, &capturing)) return rc;
-    const uint32_t tiles = (uint32_t)div_up(n, pairs ? kSortPairsTile : kSortTile);
-    if (capturing && tiles > c->sort_desc_tiles)
-        return fail(GPS_ERR_UNSUPPORTED, "capture needs one gps_sort call of at least this size outside the capture first");
-    CaptureScope cap;
-    if (capturing)
-        if (int rc = cap.begin(c, st, CaptureScope::SORT)) return rc;
-    if (tiles > c->sort_desc_tiles) {  // grow (synchronous, rare)
-        GPS_CUDA(cudaDeviceSynchronize());
-        if (c->sort_desc) cudaFree(c->sort_desc);
-        c->sort_desc = nullptr;
-        c->sort_desc_tiles = 0;
-        GPS_CUDA(cudaMalloc(&c->sort_desc, (size_t)tiles * kRadix * sizeof(uint64_t)));
-        GPS_CUDA(cudaMemset(c->sort_desc, 0, (size_t)tiles * kRadix * sizeof(uint64_t)));
-        if (c->g_sort_desc) cudaFree(c->g_sort_desc);  // shadow for captured sorts (CaptureScope)
-        c->g_sort_desc = nullptr;
-        GPS_CUDA(cudaMalloc(&c->g_sort_desc, (size_t)tiles * kRadix * sizeof(uint64_t)));
-        c->sort_desc_tiles = tiles;
-        c->sort_epoch = 0;
-    }
-    if (!c->sort_hist) GPS_CUDA(cudaMalloc(&c->sort_hist, 2 * 4 * kRadix * sizeof(uint32_t)));
-    uint32_t* hist = c->sort_hist;
-    uint32_t* digit_base = c->sort_hist + 4 * kRadix;
-    GPS_CUDA(cudaMemsetAsync(hist, 0, 4 * kRadix * sizeof(uint32_t), st));
-    {
-        if (!c->sort_hist_configured) {
-            GPS_CUDA(cudaFuncSetAttribute(sort_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)kHistSmemBytes));
-            c->sort_hist_configured = true;
-        }
-        const uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)c->s.sm_count, div_up(n, 4 * kHistThreads));
-        sort_hist_kernel<<<grid, kHistThreads, kHistSmemBytes, st>>>((const uint32_t*)d_keys_in, (uint32_t)n, hist, passes,
-                                                                     (uint32_t)key_type, last_mask);
-        sort_digit_base_kernel<<<passes, kRadix, 0, st>>>(hist, digit_base);
-    }
-    // ping-pong so that the last pass lands in `out`
-    const uint32_t* src_k = (const uint32_t*)d_keys_in;
-    const uint32_t* src_v = (const uint32_t*)d_vals_in;
-    for (int pass = 0; pass < passes; ++pass) {
-        const bool to_out = ((passes - 1 - pass) & 1) == 0;
-        SortParams p{};
-        p.keys_in = src_k;
-        p.keys_out = (uint32_t*)(to_out ? d_keys_out : d_keys_tmp);
-        p.vals_in = src_v;
-        p.vals_out = (uint32_t*)(to_out ? d_vals_out : d_vals_tmp);
-        p.n = (uint32_t)n;
-        p.shift = 8u * pass;
-        p.desc = c->sort_desc;
-        p.digit_base = digit_base + pass * kRadix;
-        p.counter = c->s.counter;
-        p.counter_base = c->s.counter_base;
-        if (++c->sort_epoch >= (1u << 30)) {  // wrap: epoch values would alias -> clear once
-            GPS_CUDA(cudaMemsetAsync(c->sort_desc, 0, (size_t)c->sort_desc_tiles * kRadix * sizeof(uint64_t), st));
-            c->sort_epoch = 1;
-        }
-        p.epoch = c->sort_epoch;
-        p.num_tiles = tiles;
-        p.status = c->s.status;
-        p.xform_in = pass == 0 ? (uint32_t)key_type : 0u;
-        p.xform_out = pass == passes - 1 ? (uint32_t)key_type : 0u;
-        p.digit_mask = pass == passes - 1 ? last_mask : 0xFFu;
-        const bool xf = p.xform_in || p.xform_out || p.digit_mask != 0xFFu;
-        const bool pdl = c->s.flags & PF_PDL;
-        cudaError_t e;
-        if (fbp)
-            e = pairs ? (xf ? launch_sort_pass<true, true, true>(p, c->sort_configured[7], pdl, st, *fbp)
-                            : launch_sort_pass<true, false, true>(p, c->sort_configured[5], pdl, st, *fbp))
-                      : (xf ? launch_sort_pass<false, true, true>(p, c->sort_configured[6], pdl, st, *fbp)
-                            : launch_sort_pass<false, false, true>(p, c->sort_configured[4], pdl, st, *fbp));
-        else
-            e = pairs ? (xf ? launch_sort_pass<true, true>(p, c->sort_configured[3], pdl, st)
-                            : launch_sort_pass<true, false>(p, c->sort_configured[1], pdl, st))
-                      : (xf ? launch_sort_pass<false, true>(p, c->sort_configured[2], pdl, st)
-                            : launch_sort_pass<false, false>(p, c->sort_configured[0], pdl, st));
-        if (e == cudaSuccess) c->s.counter_base += tiles;  // one claim per CTA of a launch that happened
-        GPS_CUDA(e);
-        src_k = p.keys_out;
-        src_v = p.vals_out;
-    }
-    GPS_CUDA(cudaGetLastError());
-    return GPS_OK;
-}
-
 int gps_sort_keys32(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
                     const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
 {
-    return sort_keys32_impl(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
-                            stream, nullptr);
+    return sort_impl<uint32_t>(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
+                               stream, nullptr);
 }
 
 int gps_sort_keys32_fallback(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
@@ -959,8 +978,26 @@ int gps_sort_keys32_fallback(gps_ctx* c, int key_type, const void* d_keys_in, vo
     if (stall_mask == 0) return fail(GPS_ERR_INVALID, "stall_mask 0 would stall every tile: nobody left to fall back");
     if (max_spin == 0) return fail(GPS_ERR_INVALID, "max_spin must be >= 1");
     const SortFallbackParams f{stall_mask, max_spin, d_stats};
-    return sort_keys32_impl(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
-                            stream, &f);
+    return sort_impl<uint32_t>(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
+                               stream, &f);
+}
+
+int gps_sort_keys64(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                    const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit, void* stream)
+{
+    return sort_impl<uint64_t>(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
+                               stream, nullptr);
+}
+
+int gps_sort_keys64_fallback(gps_ctx* c, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                             const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n, int end_bit,
+                             uint32_t stall_mask, uint32_t max_spin, uint32_t* d_stats, void* stream)
+{
+    if (stall_mask == 0) return fail(GPS_ERR_INVALID, "stall_mask 0 would stall every tile: nobody left to fall back");
+    if (max_spin == 0) return fail(GPS_ERR_INVALID, "max_spin must be >= 1");
+    const SortFallbackParams f{stall_mask, max_spin, d_stats};
+    return sort_impl<uint64_t>(c, key_type, d_keys_in, d_keys_out, d_keys_tmp, d_vals_in, d_vals_out, d_vals_tmp, n, end_bit,
+                               stream, &f);
 }
 
 int gps_scan_carry_slots(gps_ctx* c, int algo, int kind, int dtype, const void* d_in, void* d_out,

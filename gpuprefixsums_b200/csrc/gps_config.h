@@ -124,6 +124,25 @@
 #define GPS_SORT_PAIRS_REGS 84
 #endif
 
+// 64-bit keys (gps_sort_keys64): about half as many keys per thread, so that the keys take about the same
+// registers and the tile about the same shared memory as for 32-bit keys.  Measured at 2^27 random uint64
+// keys on B200 (tools/gpu_r2_p.sh, profiles/r02_sort64_bench.txt), Gkeys/s keys / pairs:
+// <256,24> / <256,20> r84: 24.9 / 20.3 (default); <256,20> / <256,16> r84: 23.6 / 19.0;
+// <256,16> / <256,12> r64: 23.2 / 18.2; <256,28> / <256,24> r96: 22.7 / 18.8;
+// cub::DeviceRadixSort on the same keys: 12.3 / 15.1
+#ifndef GPS_SORT64_NT
+#define GPS_SORT64_NT 256
+#endif
+#ifndef GPS_SORT64_KPT
+#define GPS_SORT64_KPT 24
+#endif
+#ifndef GPS_SORT64_PAIRS_KPT
+#define GPS_SORT64_PAIRS_KPT 20
+#endif
+#ifndef GPS_SORT64_REGS
+#define GPS_SORT64_REGS 84
+#endif
+
 // CSDL on the blocked shared-memory tile (gps_csdl_blocked.cuh): NT threads x V (odd) uint4
 // per thread, TMA bulk load + per-warp TMA bulk store
 #ifndef GPS_BLOCKED_NT

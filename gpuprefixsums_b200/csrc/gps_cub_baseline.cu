@@ -68,6 +68,30 @@ int gps_cub_sort_u32(const void* d_keys_in, void* d_keys_out, const void* d_vals
     return e == cudaSuccess ? 0 : -1;
 }
 
+// the same for uint64 keys (32-bit payload)
+int gps_cub_sort_u64(const void* d_keys_in, void* d_keys_out, const void* d_vals_in, void* d_vals_out, uint64_t n,
+                     int end_bit, void* stream)
+{
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t* ki = (const uint64_t*)d_keys_in;
+    uint64_t* ko = (uint64_t*)d_keys_out;
+    const uint32_t* vi = (const uint32_t*)d_vals_in;
+    uint32_t* vo = (uint32_t*)d_vals_out;
+    size_t need = 0;
+    cudaError_t e = vi ? cub::DeviceRadixSort::SortPairs(nullptr, need, ki, ko, vi, vo, (int64_t)n, 0, end_bit, st)
+                       : cub::DeviceRadixSort::SortKeys(nullptr, need, ki, ko, (int64_t)n, 0, end_bit, st);
+    if (e != cudaSuccess) return -1;
+    if (need > g_temp_bytes) {
+        if (g_temp) cudaFree(g_temp);
+        if (cudaMalloc(&g_temp, need) != cudaSuccess) return -1;
+        g_temp_bytes = need;
+    }
+    e = vi ? cub::DeviceRadixSort::SortPairs(g_temp, need, ki, ko, vi, vo, (int64_t)n, 0, end_bit, st)
+           : cub::DeviceRadixSort::SortKeys(g_temp, need, ki, ko, (int64_t)n, 0, end_bit, st);
+    return e == cudaSuccess ? 0 : -1;
+}
+
 void gps_cub_release(void)
 {
     if (g_temp) cudaFree(g_temp);

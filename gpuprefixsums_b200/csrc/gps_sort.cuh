@@ -25,12 +25,12 @@ namespace gps {
 constexpr int kRadix = 256;
 
 struct SortParams {
-    const uint32_t* keys_in;
-    uint32_t* keys_out;
+    const void* keys_in;       // uint32_t or uint64_t keys (template parameter K of the kernels)
+    void* keys_out;
     const uint32_t* vals_in;   // pairs only
     uint32_t* vals_out;
     uint32_t n;
-    uint32_t shift;            // 0, 8, 16, 24
+    uint32_t shift;            // 0, 8, 16, 24 (64-bit keys: ... 56)
     uint64_t* desc;            // num_tiles * 256 descriptors, shared by all passes
     const uint32_t* digit_base;  // 256 exclusive digit offsets of THIS pass
     uint32_t* counter;         // tile-claim counter (never reset)
@@ -66,11 +66,32 @@ __host__ __device__ __forceinline__ uint32_t sort_key_unmap(uint32_t k, uint32_t
     return k;
 }
 
+// 64-bit keys: the same maps on 64 bits (1 = int64, 2 = float64)
+__host__ __device__ __forceinline__ uint64_t sort_key_map(uint64_t k, uint32_t type)
+{
+    const uint32_t t = type & KEY_TYPE_MASK;
+    if (t == KEY_I32) k ^= 0x8000000000000000ull;
+    if (t == KEY_F32) k ^= ((k >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+    return (type & KEY_DESC) ? ~k : k;
+}
+__host__ __device__ __forceinline__ uint64_t sort_key_unmap(uint64_t k, uint32_t type)
+{
+    if (type & KEY_DESC) k = ~k;
+    const uint32_t t = type & KEY_TYPE_MASK;
+    if (t == KEY_I32) k ^= 0x8000000000000000ull;
+    if (t == KEY_F32) k ^= ((k >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+    return k;
+}
+
 // digit = byte (shift / 8) of the key: one PRMT (selector 0x4440 + byte index: byte 0 <- that
 // byte of the key, bytes 1..3 <- byte 0 of the zero operand)
 __device__ __forceinline__ uint32_t sort_digit(uint32_t key, uint32_t shift)
 {
     return __byte_perm(key, 0u, 0x4440u + (shift >> 3));
+}
+__device__ __forceinline__ uint32_t sort_digit(uint64_t key, uint32_t shift)  // shift is warp-uniform
+{
+    return sort_digit(shift >= 32u ? (uint32_t)(key >> 32) : (uint32_t)key, shift & 31u);
 }
 
 // 256 descriptors per tile are published by 8 full warps: plain coalesced stores by default
@@ -95,45 +116,56 @@ __device__ __forceinline__ void desc_publish_plain(uint64_t* ptr, uint64_t v)
 // construction.  128 KB of shared memory, one persistent CTA per SM.
 constexpr int kHistThreads = 1024;
 constexpr size_t kHistSmemBytes = (size_t)4 * kRadix * 32 * sizeof(uint32_t);
+constexpr int kMaxSortPasses = 8;  // 64-bit keys
 
+// K = key type; one launch covers up to 4 digit passes [pass0, pass0 + passes) (the table holds 4 x 256
+// counters per lane): 32-bit keys need one launch, 64-bit keys two
+template <typename K>
 __global__ void __launch_bounds__(kHistThreads, 1)
-    sort_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* hist, int passes, uint32_t key_type,
-                     uint32_t last_mask)
+    sort_hist_kernel(const K* __restrict__ keys, uint32_t n, uint32_t* hist, int pass0, int passes, int total_passes,
+                     uint32_t key_type, uint32_t last_mask)
 {
     extern __shared__ __align__(16) uint32_t s_hist[];  // [4 * 256][32]
+    constexpr uint32_t KPV = 16 / sizeof(K);             // keys per 16-byte vector
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     for (uint32_t i = tid; i < 4u * kRadix * 32u; i += kHistThreads) s_hist[i] = 0u;
     __syncthreads();
-    auto add = [&](uint32_t k) {
+    auto add = [&](K k) {
         k = sort_key_map(k, key_type);
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
-            if (p < passes)  // the last pass may cover fewer than 8 bits (end_bit % 8 != 0)
-                atomicAdd(&s_hist[((p * kRadix + ((k >> (8 * p)) & (p == passes - 1 ? last_mask : 0xFFu))) << 5) + lane], 1u);
+        for (int q = 0; q < 4; ++q)
+            if (q < passes) {  // the last pass of the sort may cover fewer than 8 bits (end_bit % 8 != 0)
+                const uint32_t d = (uint32_t)(k >> (8 * (pass0 + q))) & (pass0 + q == total_passes - 1 ? last_mask : 0xFFu);
+                atomicAdd(&s_hist[((q * kRadix + d) << 5) + lane], 1u);
+            }
+    };
+    auto add_vec = [&](const uint4& a) {
+        if constexpr (sizeof(K) == 4) {
+            add((K)a.x); add((K)a.y); add((K)a.z); add((K)a.w);
+        } else {
+            add((K)(((uint64_t)a.y << 32) | a.x)); add((K)(((uint64_t)a.w << 32) | a.z));
+        }
     };
     const uint4* k4 = reinterpret_cast<const uint4*>(keys);
-    const uint32_t nvec = n / 4u;
+    const uint32_t nvec = n / KPV;
     const uint32_t stride = gridDim.x * kHistThreads;
     uint32_t v = blockIdx.x * kHistThreads + tid;
     // two independent loads in flight per thread
     for (; v + stride < nvec; v += 2u * stride) {
         const uint4 a = ldg_stream(k4 + v);
         const uint4 b = ldg_stream(k4 + v + stride);
-        add(a.x); add(a.y); add(a.z); add(a.w);
-        add(b.x); add(b.y); add(b.z); add(b.w);
+        add_vec(a);
+        add_vec(b);
     }
-    if (v < nvec) {
-        const uint4 a = ldg_stream(k4 + v);
-        add(a.x); add(a.y); add(a.z); add(a.w);
-    }
-    if (blockIdx.x == 0 && tid < (n & 3u)) add(keys[(uint64_t)nvec * 4u + tid]);
+    if (v < nvec) add_vec(ldg_stream(k4 + v));
+    if (blockIdx.x == 0 && tid < (n % KPV)) add(keys[(uint64_t)nvec * KPV + tid]);
     __syncthreads();
     // thread t folds the 32 columns of counter t (rotated start: conflict free)
     if (tid < (uint32_t)passes * kRadix) {
         uint32_t c = 0;
 #pragma unroll
         for (uint32_t i = 0; i < 32u; ++i) c += s_hist[(tid << 5) + ((i + tid) & 31u)];
-        if (c) atomicAdd(hist + tid, c);
+        if (c) atomicAdd(hist + pass0 * kRadix + tid, c);
     }
 }
 
@@ -220,10 +252,13 @@ struct SortFallbackParams {
 
 // XFORM: apply the key maps of p.xform_in / p.xform_out (first / last pass of int32 and float32
 // sorts); the uint32 instantiation carries none of that code
-template <int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8, bool XFORM = false, bool FB = false>
+template <typename K, int NT, int KPT, bool PAIRS, int REGS = 64, int LB = 8, bool XFORM = false, bool FB = false>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     sort_pass_kernel(const __grid_constant__ SortParams p, const SortFallbackParams f)
 {
+    constexpr uint32_t KW = sizeof(K) / 4;  // 32-bit words per key
+    const K* const keys_in = static_cast<const K*>(p.keys_in);
+    K* const keys_out = static_cast<K*>(p.keys_out);
     pdl_entry();
     static_assert(!FB || NT == kRadix, "the fallback rounds are block-wide: every thread owns one digit");
     static_assert(NT >= kRadix && NT % 32 == 0, "one thread per digit for the look-back");
@@ -232,9 +267,9 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     constexpr uint32_t WARP_KEYS = 32 * KPT;
     // dynamic shared memory: keys | payload (pairs) | per-warp digit counters -> placement offsets
     extern __shared__ __align__(128) uint32_t s_dyn[];
-    uint32_t* const s_keys = s_dyn;
-    uint32_t* const s_vals = s_dyn + TILE;  // payload: fetched by TMA, permuted in place
-    uint32_t(*const s_whist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(s_dyn + (PAIRS ? 2 : 1) * TILE);
+    K* const s_keys = reinterpret_cast<K*>(s_dyn);
+    uint32_t* const s_vals = s_dyn + KW * TILE;  // payload (always 32 bits): fetched by TMA, permuted in place
+    uint32_t(*const s_whist)[kRadix] = reinterpret_cast<uint32_t(*)[kRadix]>(s_dyn + (KW + (PAIRS ? 1 : 0)) * TILE);
     __shared__ uint32_t s_goff[kRadix];       // global position of sorted-tile index 0 of each digit run
     __shared__ uint32_t s_wtot[kRadix / 32];
     __shared__ __align__(8) uint64_t s_bar;
@@ -242,7 +277,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // the digit of a (mapped) key in this pass; only the XFORM instantiation pays for the mask
-    auto digit_of = [&](uint32_t k) -> uint32_t {
+    auto digit_of = [&](K k) -> uint32_t {
         const uint32_t d = sort_digit(k, p.shift);
         return XFORM ? (d & p.digit_mask) : d;
     };
@@ -253,8 +288,8 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
         const uint32_t t = atomicAdd(p.counter, 1u) - p.counter_base;
         s_tile = t;
         if (((uint64_t)t + 1u) * TILE <= p.n) {
-            mbar_arrive_expect_tx(&s_bar, TILE * 4u * (PAIRS ? 2u : 1u));
-            bulk_load(s_keys, p.keys_in + (uint64_t)t * TILE, TILE * 4u, &s_bar);
+            mbar_arrive_expect_tx(&s_bar, TILE * 4u * (KW + (PAIRS ? 1u : 0u)));
+            bulk_load(s_keys, keys_in + (uint64_t)t * TILE, TILE * 4u * KW, &s_bar);
             if constexpr (PAIRS) bulk_load(s_vals, p.vals_in + (uint64_t)t * TILE, TILE * 4u, &s_bar);
         }
     }
@@ -279,17 +314,17 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
         // last tile: pad with (the preimage of) 0xFFFFFFFF -- the largest digit of every pass (255, or
         // digit_mask), ranked after every real key of the tile, so the padding occupies exactly the
         // sorted-tile indices >= valid
-        const uint32_t pad = XFORM ? sort_key_unmap(0xFFFFFFFFu, p.xform_in) : 0xFFFFFFFFu;
+        const K pad = XFORM ? sort_key_unmap((K)~(K)0, p.xform_in) : (K)~(K)0;
 #pragma unroll 1
         for (uint32_t i = tid; i < TILE; i += NT) {
-            s_keys[i] = i < valid ? p.keys_in[tile_base + i] : pad;
+            s_keys[i] = i < valid ? keys_in[tile_base + i] : pad;
             if constexpr (PAIRS) s_vals[i] = i < valid ? p.vals_in[tile_base + i] : 0u;
         }
         __syncthreads();
     }
 
     // ---- keys to registers, warp-striped: key j of lane l is element warp*32*KPT + j*32 + l
-    uint32_t key[KPT];
+    K key[KPT];
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
         key[j] = s_keys[warp * WARP_KEYS + j * 32 + lane];
@@ -432,7 +467,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
                 __syncthreads();
 #pragma unroll 4
                 for (int k = 0; k < KPT; ++k) {
-                    uint32_t kk = p.keys_in[(uint64_t)fb * TILE + (uint32_t)k * NT + tid];
+                    K kk = keys_in[(uint64_t)fb * TILE + (uint32_t)k * NT + tid];
                     if constexpr (XFORM) kk = sort_key_map(kk, p.xform_in);
                     atomicAdd(&s_fbhist[digit_of(kk)], 1u);
                 }
@@ -532,10 +567,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
         const uint32_t i = k * NT + tid;
-        const uint32_t kk = s_keys[i];
+        const K kk = s_keys[i];
         const uint32_t g = s_goff[digit_of(kk)] + i;
         if (full || i < valid) {
-            p.keys_out[g] = XFORM ? sort_key_unmap(kk, p.xform_out) : kk;
+            keys_out[g] = XFORM ? sort_key_unmap(kk, p.xform_out) : kk;
             if constexpr (PAIRS) p.vals_out[g] = s_vals[i];
         }
     }

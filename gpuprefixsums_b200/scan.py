@@ -167,16 +167,26 @@ class PrefixSum:
                                                   _stream_ptr(stream, self.device)))
         return out
 
-    def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None, *, end_bit: int = 32, key_type: str = "u32",
+    def sort(self, keys: torch.Tensor, values: Optional[torch.Tensor] = None, *, end_bit: Optional[int] = None,
+             key_type: str = "u32",
              descending: bool = False,
              keys_out: Optional[torch.Tensor] = None, values_out: Optional[torch.Tensor] = None,
              stream: Optional[torch.cuda.Stream] = None, fallback: bool = False, stall_mask: int = 0xFFFFFFFF,
              max_spin: int = 4, stats: Optional[torch.Tensor] = None):
-        """Stable ascending LSD radix sort of 32-bit keys, optionally moving a 32-bit payload;
+        """Stable ascending LSD radix sort of 32- or 64-bit keys, optionally moving a 32-bit payload;
         returns keys or (keys, values).  key_type: "u32" (default: the bit pattern as unsigned,
-        on the low `end_bit` bits), "i32" (signed order) or "f32" (numeric order, float32 keys)."""
-        kt = {"u32": 0, "i32": 1, "f32": 2}[key_type]
-        want = (torch.float32,) if kt == 2 else (torch.int32, torch.uint32)
+        on the low `end_bit` bits), "i32" (signed order), "f32" (numeric order, float32 keys), or
+        "u64" / "i64" / "f64" for 64-bit keys (int64 / float64 tensors).  end_bit defaults to the key width."""
+        wide = key_type in ("u64", "i64", "f64")  # 64-bit keys: same call, 8 digit passes
+        kt = {"u32": 0, "i32": 1, "f32": 2, "u64": 0, "i64": 1, "f64": 2}[key_type]
+        if wide:
+            want = (torch.float64,) if kt == 2 else (torch.int64,)
+            if end_bit is None:
+                end_bit = 64
+        else:
+            want = (torch.float32,) if kt == 2 else (torch.int32, torch.uint32)
+            if end_bit is None:
+                end_bit = 32
         if descending:
             kt |= 0x100
         if keys.dtype not in want or not keys.is_cuda or not keys.is_contiguous():
@@ -191,14 +201,16 @@ class PrefixSum:
             vptrs = (values.data_ptr(), vo.data_ptr(), vt.data_ptr())
         else:
             vo, vptrs = None, (None, None, None)
+        fn_plain, fn_fb = (lib.gps_sort_keys64, lib.gps_sort_keys64_fallback) if wide else (lib.gps_sort_keys32,
+                                                                                          lib.gps_sort_keys32_fallback)
         if fallback:  # Decoupled Fallback in the digit look-back (+ emulated stalls for the tests)
-            check(lib.gps_sort_keys32_fallback(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs,
+            check(fn_fb(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs,
                                                keys.numel(), int(end_bit), stall_mask & 0xFFFFFFFF, max_spin,
                                                stats.data_ptr() if stats is not None else None,
                                                _stream_ptr(stream, self.device)))
         else:
-            check(lib.gps_sort_keys32(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs, keys.numel(),
-                                      int(end_bit), _stream_ptr(stream, self.device)))
+            check(fn_plain(self._ctx, kt, keys.data_ptr(), ko.data_ptr(), ktmp.data_ptr(), *vptrs, keys.numel(),
+                           int(end_bit), _stream_ptr(stream, self.device)))
         return ko if values is None else (ko, vo)
 
     def scan_carry_slots(self, inp: torch.Tensor, out: Optional[torch.Tensor], slots_ptr: int, n_slots: int,
@@ -300,9 +312,13 @@ def cub_scan(inp: torch.Tensor, out: torch.Tensor, exclusive: bool = False) -> t
 
 
 def cub_sort(keys: torch.Tensor, keys_out: torch.Tensor, values: Optional[torch.Tensor] = None,
-             values_out: Optional[torch.Tensor] = None, end_bit: int = 32) -> None:
-    """cub::DeviceRadixSort baseline (libgps_cub.so) on the current stream."""
-    rc = capi.cub_lib().gps_cub_sort_u32(keys.data_ptr(), keys_out.data_ptr(),
+             values_out: Optional[torch.Tensor] = None, end_bit: Optional[int] = None) -> None:
+    """cub::DeviceRadixSort baseline (libgps_cub.so) on the current stream; int64 tensors = uint64 keys."""
+    wide = keys.dtype == torch.int64
+    if end_bit is None:
+        end_bit = 64 if wide else 32
+    fn = capi.cub_lib().gps_cub_sort_u64 if wide else capi.cub_lib().gps_cub_sort_u32
+    rc = fn(keys.data_ptr(), keys_out.data_ptr(),
                                          values.data_ptr() if values is not None else None,
                                          values_out.data_ptr() if values_out is not None else None,
                                          keys.numel(), end_bit, _stream_ptr(None, keys.device))

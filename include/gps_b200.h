@@ -212,6 +212,17 @@ int gps_sort_keys32_fallback(gps_ctx* ctx, int key_type, const void* d_keys_in, 
                              void* d_keys_tmp, const void* d_vals_in, void* d_vals_out,
                              void* d_vals_tmp, uint64_t n, int end_bit, uint32_t stall_mask,
                              uint32_t max_spin, uint32_t* d_stats, void* stream);
+/* 64-bit keys: uint64 (GPS_KEY_U32 = "unsigned"), int64 (GPS_KEY_I32 = "signed") and float64
+ * (GPS_KEY_F32 = "floating point") by the same order-preserving maps, | GPS_KEY_DESCENDING; 8 digit
+ * passes, 32-bit payload (d_vals_*, all three or none), end_bit 1..64 for unsigned keys.  Same
+ * kernels, instantiated for 64-bit keys with half as many keys per thread; same buffer rules. */
+int gps_sort_keys64(gps_ctx* ctx, int key_type, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
+                    const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,
+                    int end_bit, void* stream);
+int gps_sort_keys64_fallback(gps_ctx* ctx, int key_type, const void* d_keys_in, void* d_keys_out,
+                             void* d_keys_tmp, const void* d_vals_in, void* d_vals_out,
+                             void* d_vals_tmp, uint64_t n, int end_bit, uint32_t stall_mask,
+                             uint32_t max_spin, uint32_t* d_stats, void* stream);
 /* = gps_sort_keys32(GPS_KEY_U32, ...) */
 int gps_sort_u32(gps_ctx* ctx, const void* d_keys_in, void* d_keys_out, void* d_keys_tmp,
                  const void* d_vals_in, void* d_vals_out, void* d_vals_tmp, uint64_t n,

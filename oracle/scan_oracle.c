@@ -244,6 +244,64 @@ void oracle_sort_u32(const uint32_t *keys_in, uint32_t *keys_out, uint32_t *keys
     }
 }
 
+/* ---- 64-bit keys: the same textbook LSD loop, 8 bits per pass; key_type 0 = uint64, 1 = int64,
+ * 2 = float64 bit patterns, | 0x100 = descending (the maps of the 32-bit sort on 64 bits) ---- */
+static uint64_t oracle_key_map64(uint64_t k, int type)
+{
+    const int t = type & 0xFF;
+    if (t == 1) k ^= 0x8000000000000000ull;
+    if (t == 2) k ^= ((k >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+    return (type & 0x100) ? ~k : k;
+}
+static uint64_t oracle_key_unmap64(uint64_t k, int type)
+{
+    const int t = type & 0xFF;
+    if (type & 0x100) k = ~k;
+    if (t == 1) k ^= 0x8000000000000000ull;
+    if (t == 2) k ^= ((k >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+    return k;
+}
+/* keys_tmp: work array of n keys; vals (nullable, all three or none): 32-bit payload */
+void oracle_sort_keys64(int key_type, const uint64_t *keys_in, uint64_t *keys_out, uint64_t *keys_tmp,
+                        const uint32_t *vals_in, uint32_t *vals_out, uint32_t *vals_tmp, uint64_t n, int end_bit)
+{
+    const int passes = (end_bit + 7) / 8;
+    if (passes == 0 || n == 0) return;
+    /* pass 0 reads the mapped input; ping-pong so that the last pass lands in keys_out */
+    uint64_t *bufs[2] = {keys_out, keys_tmp};
+    uint32_t *vbufs[2] = {vals_out, vals_tmp};
+    int cur = (passes & 1) ? 1 : 0; /* index of the buffer holding the CURRENT source after the initial map */
+    uint64_t *sk = bufs[cur];
+    uint32_t *sv = vals_in ? vbufs[cur] : 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        sk[i] = oracle_key_map64(keys_in[i], key_type);
+        if (sv) sv[i] = vals_in[i];
+    }
+    for (int pass = 0; pass < passes; ++pass) {
+        uint64_t *dk = bufs[cur ^ 1];
+        uint32_t *dv = sv ? vbufs[cur ^ 1] : 0;
+        const int shift = 8 * pass;
+        const uint32_t mask = (pass == passes - 1 && (end_bit & 7)) ? ((1u << (end_bit & 7)) - 1u) : 0xFFu;
+        uint64_t count[256] = {0}, sum = 0;
+        for (uint64_t i = 0; i < n; ++i) ++count[(sk[i] >> shift) & mask];
+        for (int d = 0; d < 256; ++d) {
+            const uint64_t c = count[d];
+            count[d] = sum;
+            sum += c;
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t pos = count[(sk[i] >> shift) & mask]++;
+            dk[pos] = sk[i];
+            if (sv) dv[pos] = sv[i];
+        }
+        cur ^= 1;
+        sk = dk;
+        sv = dv;
+    }
+    /* passes flips from the start buffer: ends in bufs[0] == keys_out */
+    for (uint64_t i = 0; i < n; ++i) keys_out[i] = oracle_key_unmap64(keys_out[i], key_type);
+}
+
 /* ---- all-ones closed form (UtilityKernels.cuh:22-38) ------------------------- */
 uint64_t oracle_validate_ones(const uint32_t *scan, uint64_t n, int exclusive)
 {

@@ -144,6 +144,24 @@ class Oracle:
         ko = ko.view(keys.dtype)
         return ko if vals is None else (ko, vo)
 
+    def sort_keys64(self, keys: np.ndarray, vals: np.ndarray | None = None, key_type: str = "u64",
+                    descending: bool = False, end_bit: int = 64):
+        """keys: uint64 / int64 / float64 array; stable sort by that type's order (on the low end_bit bits
+        for uint64)."""
+        kt = {"u64": 0, "i64": 1, "f64": 2}[key_type] | (0x100 if descending else 0)
+        bits = np.ascontiguousarray(keys).view(np.uint64)
+        ko, ktmp = np.empty_like(bits), np.empty_like(bits)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        vo = vt = None
+        if vals is not None:
+            vals = np.ascontiguousarray(vals, dtype=np.uint32)
+            vo, vt = np.empty_like(vals), np.empty_like(vals)
+        self.lib.oracle_sort_keys64.restype = None
+        self.lib.oracle_sort_keys64.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_uint64, C.c_int]
+        self.lib.oracle_sort_keys64(kt, ptr(bits), ptr(ko), ptr(ktmp), ptr(vals), ptr(vo), ptr(vt), bits.size, end_bit)
+        ko = ko.view(keys.dtype)
+        return ko if vals is None else (ko, vo)
+
     def validate_ones(self, scan: np.ndarray, exclusive: bool) -> int:
         return self.lib.oracle_validate_ones(np.ascontiguousarray(scan, dtype=np.uint32), scan.size, int(exclusive))
 

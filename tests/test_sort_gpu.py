@@ -215,3 +215,101 @@ def test_sort_decoupled_fallback(ps, oracle, mask, spin):
     got = ps.sort(torch.from_numpy(xi).cuda(), key_type="i32", fallback=True, stall_mask=mask, max_spin=spin)
     ps.check()
     assert np.array_equal(got.cpu().numpy(), np.sort(xi, kind="stable"))
+
+
+# ---- 64-bit keys (gps_sort_keys64): the same kernels instantiated on uint64 keys, 8 digit passes ----
+SIZES64 = [1, 2, 31, 257, 4095, 4097, 5119, 5120, 5121, 6143, 6144, 6145, 12_289, 100_003, (1 << 20) + 7, (1 << 22) + 4099]
+
+
+def dev64(x):
+    return torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).cuda()
+
+
+def host64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def test_sort64_keys_and_pairs_bit_exact(ps, gps, oracle):
+    """uint64 keys and (key, 32-bit payload) pairs: bit-exact against the oracle and cub::DeviceRadixSort
+    over ragged sizes around the 6144-key (keys) and 5120-key (pairs) tiles; ties decide the payload order."""
+    rng = np.random.default_rng(64)
+    for n in SIZES64:
+        x = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+        out = ps.sort(dev64(x), key_type="u64")
+        ps.check()
+        assert np.array_equal(host64(out), oracle.sort_keys64(x)), n
+        v = np.arange(n, dtype=np.uint32)
+        ties = (rng.integers(0, 5, size=n, dtype=np.uint64) * np.uint64(0x0100000001000193))  # few values per byte
+        for keys in (x, ties):
+            ko, vo = ps.sort(dev64(keys), dev(v), key_type="u64")
+            ps.check()
+            wk, wv = oracle.sort_keys64(keys, v)
+            assert np.array_equal(host64(ko), wk) and np.array_equal(host(vo), wv), n
+            ck, cv = torch.empty_like(ko), torch.empty_like(vo)
+            gps.cub_sort(dev64(keys), ck, dev(v), cv)
+            torch.cuda.synchronize()
+            assert torch.equal(ck, ko) and torch.equal(cv, vo), n
+
+
+@pytest.mark.parametrize("end_bit", [1, 8, 13, 32, 33, 40, 47, 56, 61, 64])
+def test_sort64_bit_ranges(ps, gps, oracle, end_bit):
+    n = 200_003
+    x = np.random.default_rng(end_bit).integers(0, 2**64, size=n, dtype=np.uint64)
+    v = np.arange(n, dtype=np.uint32)
+    ko, vo = ps.sort(dev64(x), dev(v), key_type="u64", end_bit=end_bit)
+    ps.check()
+    order = np.argsort(x & np.uint64((1 << end_bit) - 1), kind="stable")
+    assert np.array_equal(host64(ko), x[order]) and np.array_equal(host(vo), v[order])
+    ck, cv = torch.empty_like(ko), torch.empty_like(vo)
+    gps.cub_sort(dev64(x), ck, dev(v), cv, end_bit=end_bit)
+    torch.cuda.synchronize()
+    assert torch.equal(ck, ko) and torch.equal(cv, vo)
+    assert np.array_equal(host64(ps.sort(dev64(x), key_type="u64", end_bit=end_bit)), x[order])
+
+
+def test_sort64_int64_float64_descending(ps, oracle):
+    rng = np.random.default_rng(65)
+    for n in [1, 5119, 5121, 6145, 300_007]:
+        v = np.arange(n, dtype=np.uint32)
+        bits = rng.integers(0, 2**64, size=n, dtype=np.uint64)  # every pattern: NaN payloads, -0.0, infinities
+        ki, kf = bits.view(np.int64), bits.view(np.float64).copy()
+        if n > 8:
+            kf[:6] = [0.0, -0.0, np.inf, -np.inf, 1.5, -1.5]
+        for kt, k, t in (("u64", bits, torch.int64), ("i64", ki, torch.int64), ("f64", kf, torch.float64)):
+            for desc in (False, True):
+                kd = torch.from_numpy(np.ascontiguousarray(k)).cuda().view(t) if kt != "u64" else dev64(k)
+                ko, vo = ps.sort(kd, dev(v), key_type=kt, descending=desc)
+                ps.check()
+                wk, wv = oracle.sort_keys64(k, v, kt, descending=desc)
+                assert np.array_equal(host64(ko.view(torch.int64)), wk.view(np.uint64)) and np.array_equal(host(vo), wv), (n, kt, desc)
+        assert np.array_equal(ps.sort(torch.from_numpy(ki).cuda(), key_type="i64").cpu().numpy(), np.sort(ki))
+
+
+@pytest.mark.parametrize("mask,spin", [(0xFFFFFFFF, 4), (7, 4), (1, 1)])
+def test_sort64_decoupled_fallback(ps, oracle, mask, spin):
+    for n in [1, 5121, 6145, 9 * 6144 + 5, 300_007]:
+        x = np.random.default_rng(n).integers(0, 2**64, size=n, dtype=np.uint64)
+        v = np.arange(n, dtype=np.uint32)
+        stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+        ko, vo = ps.sort(dev64(x), dev(v), key_type="u64", fallback=True, stall_mask=mask, max_spin=spin, stats=stats)
+        ps.check()
+        wk, wv = oracle.sort_keys64(x, v)
+        assert np.array_equal(host64(ko), wk) and np.array_equal(host(vo), wv), (n, mask)
+        keys = ps.sort(dev64(x), key_type="u64", fallback=True, stall_mask=mask, max_spin=spin, end_bit=45)
+        ps.check()
+        assert np.array_equal(host64(keys), oracle.sort_keys64(x, end_bit=45)), (n, mask)
+
+
+def test_sort64_2p27_sortedness_and_multiset():
+    """1 GiB of uint64 keys: non-decreasing output with the same multiset (sum, sum of squares mod 2^64)."""
+    import gpuprefixsums_b200 as gps
+
+    n = 1 << 27
+    big = gps.PrefixSum(1 << 20)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randint(-(1 << 62), (1 << 62), (n,), dtype=torch.int64, device="cuda", generator=g) * 3 + 1  # wraps: all 64 bits vary
+    out = big.sort(x, key_type="i64")
+    big.check()
+    assert bool((out[1:] >= out[:-1]).all()), "not sorted"
+    assert int(x.sum()) == int(out.sum()) and int((x * x).sum()) == int((out * out).sum())
+    big.close()
