@@ -89,6 +89,19 @@ for n in (N, 10_240, 3):
     check(lib.gps_sort_u32(ctx, a, b, c, None, None, None, n, 8, None))
     check(lib.gps_sort_keys32(ctx, 2, a, b, c, a, d, e, n, 32, None))  # float32 key maps, pairs
     check(lib.gps_sort_keys32(ctx, 1, a, b, c, None, None, None, n, 32, None))
+# round 2: 64-bit keys (keys / pairs, key maps, partial last digit, Decoupled Fallback with emulated stalls)
+sort64_sizes = (N // 2, 6144, 5121, 3)
+for n in sort64_sizes:
+    check(lib.gps_sort_keys64(ctx, 0, a, b, c, None, None, None, n, 64, None))
+    check(lib.gps_sort_keys64(ctx, 0, a, b, c, a, d, e, n, 64, None))
+    check(lib.gps_sort_keys64(ctx, 0, a, b, c, None, None, None, n, 45, None))
+    check(lib.gps_sort_keys64(ctx, 2 | 0x100, a, b, c, a, d, e, n, 64, None))  # float64 maps, descending, pairs
+    check(lib.gps_sort_keys64_fallback(ctx, 0, a, b, c, a, d, e, n, 64, 7, 2, stats, None))
+    check(lib.gps_sort_keys64_fallback(ctx, 1, a, b, c, None, None, None, n, 64, 0xFFFFFFFF, 4, None, None))
+if len(sys.argv) > 1 and sys.argv[1] == "sort64":  # only the 64-bit sort (and everything above it)
+    check(lib.gps_check(ctx, None))
+    print("san_driver done")
+    sys.exit(0)
 # host-buffer pipeline, queued calls
 import ctypes
 hin, hout = C.c_void_p(), C.c_void_p()
