@@ -76,6 +76,7 @@ struct gps_ctx {
     bool blocked_fb_configured[2][2] = {{false, false}, {false, false}};
     bool rts_blocked_configured[2][2] = {{false, false}, {false, false}};
     int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile, 3 blocked tile
+    int ticket_free = 1;            // GPS_ALGO_CSDL: ticket-free Decoupled Fallback where it is faster (gps_config.h)
     int rts_variant = 0;            // 0 auto, 1 register-tile propagate, 2 blocked-tile propagate
     int sharded_pdl = GPS_SHARDED_PDL_DEFAULT;  // see NoPdlScope
     int sharded_l2 = GPS_SHARDED_L2_DEFAULT;    // option "sharded_l2"
@@ -186,6 +187,22 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
     if (n == 0) {
         e = launch_carry_only<T>(c->s, cs, st);
     } else {
+        if (algo == GPS_ALGO_CSDL && c->csdl_variant == 0 && c->ticket_free && !(c->s.flags & PF_STATIC_TILE)) {
+            // mid sizes: Decoupled Fallback with tile = blockIdx.x (no ticket; deadlock-free under any dispatch
+            // order because no CTA of that kernel waits for another one) -- gps_config.h has the measurements
+            const bool reg_fb = n >= GPS_TICKET_FREE_REG_MIN_N && n <= GPS_TICKET_FREE_REG_MAX_N;
+            const bool smem_fb = n > GPS_REG_SMALL_MAX_N && n <= GPS_TICKET_FREE_SMEM_MAX_N;
+            if (reg_fb || smem_fb) {
+                const FallbackParams f{kNoStall, GPS_FALLBACK_DEFAULT_SPIN, nullptr};
+                c->s.flags |= PF_STATIC_TILE;
+                e = reg_fb ? launch_csdl_fallback<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL>(c->s, in, out, n, cs, f, st)
+                           : launch_csdl_smem_fallback<T, GPS_SMEM_NT, GPS_SMEM_V, INCL>(
+                                 c->s, in, out, n, cs, f, c->smem_fb_configured[dt_index<T>()][INCL ? 0 : 1], st);
+                c->s.flags &= ~PF_STATIC_TILE;
+                if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+                return GPS_OK;
+            }
+        }
         if (algo == GPS_ALGO_CSDL) {
             const int v = c->csdl_variant ? c->csdl_variant : GPS_CSDL_DEFAULT_VARIANT;
             algo = v == 2 ? GPS_ALGO_CSDL_TMA : v == 3 ? GPS_ALGO_CSDL_SMEM : v == 4 ? GPS_ALGO_CSDL_BLOCKED : GPS_ALGO_CSDL_REG;
@@ -805,6 +822,9 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
     if (!strcmp(key, "csdl_variant")) {
         if (value < 0 || value > 4) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..4");
         c->csdl_variant = (int)value;
+    } else if (!strcmp(key, "ticket_free")) {
+        if (value != 0 && value != 1) return fail(GPS_ERR_INVALID, "ticket_free must be 0 or 1");
+        c->ticket_free = (int)value;
     } else if (!strcmp(key, "fallback_variant")) {
         if (value < 0 || value > 3) return fail(GPS_ERR_INVALID, "fallback_variant must be 0..3");
         c->fallback_variant = (int)value;

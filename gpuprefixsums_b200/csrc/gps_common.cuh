@@ -83,6 +83,7 @@ enum : uint32_t {
     PF_POLL_ACQUIRE = 256u,      // poll with ld.acquire.gpu (else ld.relaxed.gpu)
     PF_LOOKBACK_WAIT_ALL = 512u, // experiment: consume a window only when all 32 are ready
     PF_LOOKBACK_SINGLE = 1024u,  // one-thread look-back (reference LookbackSingle, CSDL.cuh:28-47)
+    PF_EAGER_LOOKBACK = 2048u,   // smem tile: warp 0 walks the look-back WHILE the tile is in flight (the other warps reduce it)
     PF_PDL = 4096u,              // host: launch with programmatic stream serialization (see pdl_entry)
     PF_PDL_FOLD = 32768u,        // host: the one-block fold of gps_reduce_publish is launched programmatically
     PF_L2_OUT_EVICT_FIRST = 65536u, // tile stores carry an L2 evict_first policy (the sharded scan: keep the input the
@@ -266,6 +267,11 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
     for (uint32_t i = 0; i < (1u << 22); ++i)
         if (mbar_try_wait(bar, parity)) return true;
     return false;
+}
+// named barrier over a subset of the CTA's warps (id 1..15; `threads` a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 // global -> shared::cta, completion signalled on an mbarrier (bytes % 16 == 0)
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes,

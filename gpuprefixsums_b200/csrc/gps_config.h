@@ -167,6 +167,26 @@
 #define GPS_CSDL_DEFAULT_VARIANT 4
 #endif
 
+// Ticket-free Decoupled Fallback as GPS_ALGO_CSDL's kernel where it measured faster than plain CSDL with an
+// atomic ticket ("ticket_free" = 1, the default; 0 = plain kernels everywhere).  A CTA of a Decoupled Fallback
+// kernel never depends on another CTA making progress, so tile = blockIdx.x is deadlock-free under ANY dispatch
+// order and the ~0.7 us ticket round trip at the head of every CTA disappears.  us per launch, back to back with
+// programmatic dependent launch (tools/gpu_r2_s.sh, gpu_r2_t.sh; profiles/r02_ticket_free.txt), plain + ticket ->
+// fallback + blockIdx: 2^20 5.98 -> 5.65, 2^21 7.27 -> 6.57 (register tile <256,4>); 2^23 13.56 -> 12.15,
+// 2^24 27.2 -> 26.2, 2^25 48.9 -> 48.1 (smem tile <128,8>); it loses at 2^22 (9.04 -> 9.74), below 2^19 (the
+// fallback kernel's extra barriers) and from 2^26 (88.0 -> 89.3), which keep the plain kernels.  Through the
+// library inside a CUDA graph (tools/ticket_free_ab.py): 2^20 5.57 -> 5.17, 2^21 7.05 -> 6.20, 2^23 13.25 -> 12.01,
+// 3 * 2^22 18.48 -> 16.35, 2^24 24.9 -> 24.9 (cold L2 33.0 -> 32.3), 2^25 46.9 -> 47.0: the upper bound is 2^24.
+#ifndef GPS_TICKET_FREE_REG_MIN_N
+#define GPS_TICKET_FREE_REG_MIN_N ((1u << 19) + 1u)
+#endif
+#ifndef GPS_TICKET_FREE_REG_MAX_N
+#define GPS_TICKET_FREE_REG_MAX_N (1u << 21)
+#endif
+#ifndef GPS_TICKET_FREE_SMEM_MAX_N  // the smem tile takes over above GPS_REG_SMALL_MAX_N
+#define GPS_TICKET_FREE_SMEM_MAX_N (1u << 24)
+#endif
+
 // spin budget of GPS_ALGO_CSDL_FALLBACK (no emulated stalls): polls of a not-ready
 // window before the CTA recomputes the blocking tile itself
 #ifndef GPS_FALLBACK_DEFAULT_SPIN

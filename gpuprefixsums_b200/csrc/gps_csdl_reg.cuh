@@ -320,9 +320,16 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 32 + 4 * V))
 {
     pdl_entry();
     __shared__ uint32_t s_tile;
-    if (threadIdx.x == 0) s_tile = claim_tile(p);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    uint32_t tile;
+    if (p.flags & PF_STATIC_TILE) {
+        // Decoupled Fallback needs no ticket: no CTA ever depends on another CTA making progress, so
+        // tile = blockIdx.x is deadlock-free under any dispatch order
+        tile = blockIdx.x;
+    } else {
+        if (threadIdx.x == 0) s_tile = claim_tile(p);
+        __syncthreads();
+        tile = s_tile;
+    }
     if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
         if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
         return;

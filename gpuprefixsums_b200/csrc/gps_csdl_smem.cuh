@@ -133,6 +133,63 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     const uint32_t row0 = warp * (32u * V) + lane;  // this thread's uint4 of row 0 (index in tile)
     const uint64_t vbase = (uint64_t)tile * TILE_VEC + row0;
 
+    // ---- eager look-back (PF_EAGER_LOOKBACK, full tiles other than tile 0; block-uniform): the walk over the
+    // predecessors' descriptors needs nothing of THIS tile, so warp 0 starts it right after the claim and it
+    // runs while the TMA load is in flight; warps 1.. reduce the whole tile (warp 0's rows dealt round-robin
+    // among them) and publish the aggregate without waiting for warp 0.  The ~2 L2 round trips of the look-back
+    // leave the CTA's critical path: load -> reduce -> (prefix already there) -> scan + store.
+    if constexpr (NW >= 3) {
+        if ((p.flags & PF_EAGER_LOOKBACK) && full && tile != 0u) {
+            __shared__ T s_part[NW];
+            if (warp == 0) {
+                const T prefix = lookback_warp<T, WIN, GPS_LOOKBACK_MAXWIN>(p, tile, lane);
+                if (lane == 0) s_prefix = prefix;
+            } else {
+                if (!mbar_wait_bounded(&s_bar, 0u)) atomicOr(p.status, STATUS_WATCHDOG);  // never expected
+                T acc = T(0), acc0 = T(0);
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const uint4 r = s_data[row0 + 32u * k];
+                    acc += (from_bits<T>(r.x) + from_bits<T>(r.y)) + (from_bits<T>(r.z) + from_bits<T>(r.w));
+                }
+#pragma unroll 1
+                for (int k = (int)warp - 1; k < V; k += NW - 1) {
+                    const uint4 r = s_data[lane + 32u * k];
+                    acc0 += (from_bits<T>(r.x) + from_bits<T>(r.y)) + (from_bits<T>(r.z) + from_bits<T>(r.w));
+                }
+                const T wsum = warp_reduce(acc), w0 = warp_reduce(acc0);
+                if (lane == 0) {
+                    s_warp[warp] = wsum;
+                    s_part[warp] = w0;
+                }
+                named_bar_sync(1u, NT - 32u);
+                if (warp == 1) {
+                    const T part = (lane >= 1u && lane < (uint32_t)NW) ? s_part[lane] : T(0);
+                    const T w0sum = warp_reduce(part);
+                    if (lane == 0) s_warp[0] = w0sum;
+                    __syncwarp();
+                    const T wr = lane < (uint32_t)NW ? s_warp[lane] : T(0);
+                    const T agg = warp_reduce(wr);  // the same operation every warp repeats below: same bits
+                    if (lane == 0) desc_publish(p, p.desc + tile, pack_desc(to_bits(agg), p.epoch, ST_AGGREGATE));
+                }
+            }
+            __syncthreads();
+            if (warp == 0) (void)mbar_try_wait(&s_bar, 0u);  // phase long complete: orders this warp's reads after the TMA writes
+            const T wraw = lane < (uint32_t)NW ? s_warp[lane] : T(0);
+            const T aggregate = warp_reduce(wraw);
+            const T winc = warp_inclusive_scan(wraw, lane);
+            const T warp_prefix = __shfl_sync(kFullMask, warp_exclusive_of(winc, wraw, lane), (int)warp);
+            const T prefix = s_prefix;
+            if (tid == 0) {
+                const T inclusive = prefix + aggregate;
+                desc_publish(p, p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
+                if (tile == p.num_tiles - 1) write_total<T>(p, inclusive);
+            }
+            smem_tile_finish<T, V, INCLUSIVE, G>(s_data, row0, vbase, true, p.n, p.out, lane, prefix + warp_prefix, p.flags);
+            return;
+        }
+    }
+
     if (full) {
         if (!mbar_wait_bounded(&s_bar, 0u)) {  // never expected; do not hang the GPU
             atomicOr(p.status, STATUS_WATCHDOG);
@@ -222,12 +279,15 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_mbar_init();
-        const uint32_t t = claim_tile(p);
+        // Decoupled Fallback needs no ticket: a CTA never depends on another CTA making progress, so tile =
+        // blockIdx.x is deadlock-free under ANY dispatch order (PF_STATIC_TILE; plain CSDL with static tiles
+        // relies on in-order dispatch, as cub::DeviceScan does)
+        const uint32_t t = (p.flags & PF_STATIC_TILE) ? blockIdx.x : claim_tile(p);
         s_tile = t;
         if (((uint64_t)t + 1u) * TILE_KEYS <= p.n) {
             mbar_arrive_expect_tx(&s_bar, TILE_BYTES);
-            bulk_load(s_data, reinterpret_cast<const unsigned char*>(p.in) + (uint64_t)t * TILE_BYTES,
-                      TILE_BYTES, &s_bar);
+            tile_bulk_load(p.flags, s_data, reinterpret_cast<const unsigned char*>(p.in) + (uint64_t)t * TILE_BYTES,
+                           TILE_BYTES, &s_bar);
         }
     }
     __syncthreads();
@@ -428,7 +488,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     if (tid == 0 && f.stats && n_fallbacks) atomicAdd(f.stats + 1, n_fallbacks);
     __syncthreads();
 
-    smem_tile_finish<T, V, INCLUSIVE, G>(s_data, row0, vbase, full, p.n, p.out, lane, s_prefix + warp_prefix);
+    smem_tile_finish<T, V, INCLUSIVE, G>(s_data, row0, vbase, full, p.n, p.out, lane, s_prefix + warp_prefix, p.flags);
 }
 
 

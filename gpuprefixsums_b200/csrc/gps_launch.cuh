@@ -214,7 +214,7 @@ cudaError_t launch_csdl_fallback(Scratch& s, const void* in, void* out, uint64_t
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
     const cudaError_t e = launch_scan_kernel(csdl_fallback_kernel<T, NT, V, INCL>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
-    if (e == cudaSuccess) s.counter_base += p.num_tiles;
+    if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;
 }
 
@@ -245,7 +245,7 @@ cudaError_t launch_csdl_smem_fallback(Scratch& s, const void* in, void* out, uin
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
     const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
-    if (e == cudaSuccess) s.counter_base += p.num_tiles;
+    if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;
 }
 

@@ -105,6 +105,10 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   2^27 keys; below, the lane-strided smem tile above 2^21 keys when no stalls
  *                   are emulated, else the register tile), 1 = register tile, 2 = smem-resident
  *                   tile, 3 = blocked smem-resident tile
+ *   "ticket_free"   1 (default) = GPS_ALGO_CSDL runs the Decoupled Fallback kernel with tile =
+ *                   blockIdx.x (no atomic ticket; deadlock-free under any CTA dispatch order, since
+ *                   no CTA of that kernel waits for another) for 2^19 < n <= 2^21 and
+ *                   2^22 < n <= 2^24 keys, where it measured up to 12 % faster; 0 = plain kernels
  *   "rts_variant"   Reduce-then-Scan propagate kernel: 0 = auto (blocked tile from 2^27 keys),
  *                   1 = register tile, 2 = blocked smem-resident tile
  *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)

@@ -449,7 +449,7 @@ def test_descriptor_protocols_and_tile_order(gps, oracle, protocol, tile_order):
     x = oracle.random_u32(n, seed=9)
     want, _ = oracle.scan_u32(x, exclusive=True)
     # the default kernel (blocked tile) and the Decoupled Fallback kernels included: the options
-    # apply to every chained variant (the fallback kernels always take tickets)
+    # apply to every chained variant (tile_order 1: the register / smem Decoupled Fallback kernels run ticket-free too)
     for algo in ("csdl_blocked", "csdl_smem", "csdl_reg", "csdl_tma", "csdl_fallback", "csdl"):
         out = ps.scan(to_dev_u32(x), algo=algo, exclusive=True)
         ps.check()
@@ -638,4 +638,69 @@ def test_occupancy_estimation_variant(gps, oracle):
         got = ps.scan(to_dev_u32(x))  # the never-reset ticket counter is still in step
         ps.check()
         assert np.array_equal(to_np_u32(got), oracle.scan_u32(x)[0])
+    ps.close()
+
+
+def test_ticket_free_decoupled_fallback_default(gps, oracle):
+    """GPS_ALGO_CSDL's mid-size kernels (round 2): Decoupled Fallback with tile = blockIdx.x, no ticket
+    (2^19 < n <= 2^21 on the register tile, 2^22 < n <= 2^24 on the smem tile; "ticket_free" = 0 restores the
+    plain ticketed kernels).  Both settings bit-exact on the range boundaries, ragged sizes, in place,
+    exclusive, with a carry and a total, float32 in tolerance, and 40 launches back to back (epochs, no ticket
+    counter to advance) interleaved with ticketed launches of other sizes."""
+    ps = gps.PrefixSum((1 << 25) + 4096)
+    sizes = [(1 << 19), (1 << 19) + 1, (1 << 20) + 4099, 1 << 21, (1 << 21) + 1, 1 << 22, (1 << 22) + 1,
+             (1 << 23) + 777, (1 << 24) - 5, 1 << 24, (1 << 24) + 1, (1 << 25) + 1]
+    for n in sizes:
+        x = oracle.random_u32(n, seed=n % 1000)
+        d = to_dev_u32(x)
+        for tf in (1, 0):
+            ps.set_option("ticket_free", tf)
+            for exclusive in (False, True):
+                want, total = oracle.scan_u32(x, exclusive=exclusive, carry=11)
+                tot = torch.zeros(1, dtype=torch.int32, device="cuda")
+                out = ps.scan(d, exclusive=exclusive, carry=11, total_out=tot)
+                ps.check()
+                assert np.array_equal(to_np_u32(out), want), (n, tf, exclusive)
+                assert int(tot.cpu().numpy().view(np.uint32)[0]) == total, (n, tf, exclusive)
+            buf = d.clone()
+            ps.scan(buf, buf)  # in place
+            ps.check()
+            assert np.array_equal(to_np_u32(buf), oracle.scan_u32(x)[0]), (n, tf, "in place")
+    ps.set_option("ticket_free", 1)
+    xf = oracle.random_f32((1 << 23) + 5, seed=3)
+    outf = ps.scan(torch.from_numpy(xf).cuda()).cpu().numpy()
+    ps.check()
+    assert oracle.check_f32(xf, outf, rtol=2e-5, atol=1e-6)[0] == 0
+    # back to back, sizes of both ticket-free ranges interleaved with ticketed kernels; every result checked
+    rng = np.random.default_rng(5)
+    cases = [(1 << 20) + 17, (1 << 23) + 9, (1 << 22), 100_003, (1 << 21), (1 << 24)]
+    xs = {n: oracle.random_u32(n, seed=n % 77) for n in cases}
+    ds = {n: to_dev_u32(xs[n]) for n in cases}
+    outs = []
+    for it in range(40):
+        n = cases[int(rng.integers(0, len(cases)))]
+        outs.append((n, ps.scan(ds[n], exclusive=bool(it & 1)), bool(it & 1)))
+    ps.check()
+    wants = {(n, e): oracle.scan_u32(xs[n], exclusive=e)[0] for n in cases for e in (False, True)}
+    for n, o, e in outs:
+        assert np.array_equal(to_np_u32(o), wants[(n, e)]), (n, e)
+    ps.close()
+
+
+def test_ticket_free_fallback_under_emulated_stalls(gps, oracle):
+    """tile_order = 1 makes the emulated-deadlock harness run ticket-free as well: stalled tiles are rescued by
+    their successors' fallbacks exactly as with tickets (register and smem tiles; the blocked tile keeps tickets)."""
+    ps = gps.PrefixSum(1 << 23)
+    ps.set_option("tile_order", 1)
+    for variant in (1, 2):
+        ps.set_option("fallback_variant", variant)
+        for n in [(1 << 20) + 4099, (1 << 22) + 5]:
+            x = oracle.random_u32(n, seed=n % 91)
+            for exclusive in (False, True):
+                stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+                out = ps.scan_emulated_deadlock(to_dev_u32(x), exclusive=exclusive, stall_mask=7, max_spin=4, stats=stats)
+                ps.check()
+                assert np.array_equal(to_np_u32(out), oracle.scan_u32(x, exclusive=exclusive)[0]), (variant, n, exclusive)
+                st = stats.cpu().numpy()
+                assert st[1] > 0 and st[2] > 0, f"no fallbacks recorded: {st}"
     ps.close()

@@ -602,6 +602,76 @@ static int run_all(Env& env, const char* filter)
                 return launch_csdl_smem<T, 128, 8, INCL, 1>(env.s, in, out, env.n, cs, cfgx, 0);
             });
         }
+        // eager look-back (warp 0 walks while the tile is in flight), with poll back-off and the other mid-size knobs
+        for (uint32_t sleep_ns : {0u, 100u, 300u}) {
+            for (uint32_t fl : {(uint32_t)PF_EAGER_LOOKBACK, (uint32_t)(PF_EAGER_LOOKBACK | PF_L2_IN_EVICT_FIRST),
+                                (uint32_t)(PF_EAGER_LOOKBACK | PF_STATIC_TILE), (uint32_t)PF_L2_IN_EVICT_FIRST}) {
+                if (sleep_ns && !(fl & PF_EAGER_LOOKBACK)) continue;
+                env.s.flags = fl | pdl_base;
+                env.s.poll_sleep_ns = sleep_ns;
+                char name[96];
+                static bool cfge = false;
+                snprintf(name, sizeof(name), "exp/smem<128,8>/eager%u/sleep%u", fl, sleep_ns);
+                run_variant(env, name, true, [&](const void* in, void* out) {
+                    CarrySpec cs;
+                    return launch_csdl_smem<T, 128, 8, INCL, 1>(env.s, in, out, env.n, cs, cfge, 0);
+                });
+            }
+        }
+        env.s.poll_sleep_ns = 0;
+        // Decoupled Fallback without tickets (tile = blockIdx.x is deadlock-free there), spin budgets, no stalls
+        static uint32_t* fb_stats = nullptr;  // {spins, fallbacks, insertions, windows} summed over the variant's launches
+        if (!fb_stats) CK(cudaMalloc(&fb_stats, 4 * sizeof(uint32_t)));
+        for (uint32_t spin : {16u, 64u, 256u, 1024u}) {
+            for (uint32_t fl : {0u, (uint32_t)PF_STATIC_TILE, (uint32_t)(PF_STATIC_TILE | PF_L2_IN_EVICT_FIRST)}) {
+                env.s.flags = fl | pdl_base;
+                char name[96];
+                static bool cfgf = false;
+                snprintf(name, sizeof(name), "exp/smem_fb<128,8>/flags%u/spin%u", fl, spin);
+                CK(cudaMemset(fb_stats, 0, 4 * sizeof(uint32_t)));
+                run_variant(env, name, true, [&](const void* in, void* out) {
+                    CarrySpec cs;
+                    FallbackParams f{kNoStall, spin, fb_stats};
+                    return launch_csdl_smem_fallback<T, 128, 8, INCL>(env.s, in, out, env.n, cs, f, cfgf, 0);
+                });
+                uint32_t h[4];
+                CK(cudaMemcpy(h, fb_stats, sizeof(h), cudaMemcpyDeviceToHost));
+                printf("{\"variant\": \"%s/stats\", \"spins\": %u, \"fallbacks\": %u, \"insertions\": %u, \"windows\": %u}\n", name,
+                       h[0], h[1], h[2], h[3]);
+            }
+        }
+        // the same on the register tiles of the small sizes (<128,4> up to 2^17, <256,4> up to 2^22), stats off
+        for (uint32_t fl : {0u, (uint32_t)PF_STATIC_TILE}) {
+            env.s.flags = fl | pdl_base;
+            char name[96];
+            snprintf(name, sizeof(name), "exp/reg<256,4>/w1/flags%u", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 256, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
+            });
+            snprintf(name, sizeof(name), "exp/reg<128,4>/w1/flags%u", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 128, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
+            });
+            const FallbackParams f{kNoStall, 64u, nullptr};
+            snprintf(name, sizeof(name), "exp/reg_fb<256,4>/flags%u/spin64", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_fallback<T, 256, 4, INCL>(env.s, in, out, env.n, cs, f, 0);
+            });
+            snprintf(name, sizeof(name), "exp/reg_fb<128,4>/flags%u/spin64", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_fallback<T, 128, 4, INCL>(env.s, in, out, env.n, cs, f, 0);
+            });
+            static bool cfgs = false;
+            snprintf(name, sizeof(name), "exp/smem_fb<128,8>/nostats/flags%u/spin64", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_smem_fallback<T, 128, 8, INCL>(env.s, in, out, env.n, cs, f, cfgs, 0);
+            });
+        }
         env.s.flags = PF_LOOKBACK_WAIT_ALL;
         {
             static int occw = 0;
