@@ -177,6 +177,9 @@
 // fallback kernel's extra barriers) and from 2^26 (88.0 -> 89.3), which keep the plain kernels.  Through the
 // library inside a CUDA graph (tools/ticket_free_ab.py): 2^20 5.57 -> 5.17, 2^21 7.05 -> 6.20, 2^23 13.25 -> 12.01,
 // 3 * 2^22 18.48 -> 16.35, 2^24 24.9 -> 24.9 (cold L2 33.0 -> 32.3), 2^25 46.9 -> 47.0: the upper bound is 2^24.
+// Small sizes come first (gps_api.cu, dispatch_scan_tk): a grid of at most ONE wave of the small register-tile
+// kernels runs the PLAIN kernel with tile = blockIdx.x -- equally deadlock-free, and cheaper than the fallback
+// kernel (2^20: 5.14 us, 2^21: 6.41); the register-tile range below then only applies on devices too small for that.
 #ifndef GPS_TICKET_FREE_REG_MIN_N
 #define GPS_TICKET_FREE_REG_MIN_N ((1u << 19) + 1u)
 #endif

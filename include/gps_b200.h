@@ -105,10 +105,13 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   2^27 keys; below, the lane-strided smem tile above 2^21 keys when no stalls
  *                   are emulated, else the register tile), 1 = register tile, 2 = smem-resident
  *                   tile, 3 = blocked smem-resident tile
- *   "ticket_free"   1 (default) = GPS_ALGO_CSDL runs the Decoupled Fallback kernel with tile =
- *                   blockIdx.x (no atomic ticket; deadlock-free under any CTA dispatch order, since
- *                   no CTA of that kernel waits for another) for 2^19 < n <= 2^21 and
- *                   2^22 < n <= 2^24 keys, where it measured up to 12 % faster; 0 = plain kernels
+ *   "ticket_free"   1 (default) = GPS_ALGO_CSDL takes tile = blockIdx.x instead of an atomic ticket
+ *                   where that is provably deadlock-free under ANY CTA dispatch order: (a) grids of
+ *                   at most one wave of the small register-tile kernels (every CTA becomes resident
+ *                   without another CTA of the grid finishing first; up to ~3.6 M keys on 148 SMs);
+ *                   (b) the Decoupled Fallback kernel (no CTA of it waits for another) for
+ *                   2^19 < n <= 2^21 when (a) does not apply and for 2^22 < n <= 2^24 keys.
+ *                   6..14 % faster there; 0 = atomic tickets everywhere
  *   "rts_variant"   Reduce-then-Scan propagate kernel: 0 = auto (blocked tile from 2^27 keys),
  *                   1 = register tile, 2 = blocked smem-resident tile
  *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)

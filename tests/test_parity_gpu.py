@@ -648,7 +648,8 @@ def test_ticket_free_decoupled_fallback_default(gps, oracle):
     exclusive, with a carry and a total, float32 in tolerance, and 40 launches back to back (epochs, no ticket
     counter to advance) interleaved with ticketed launches of other sizes."""
     ps = gps.PrefixSum((1 << 25) + 4096)
-    sizes = [(1 << 19), (1 << 19) + 1, (1 << 20) + 4099, 1 << 21, (1 << 21) + 1, 1 << 22, (1 << 22) + 1,
+    sizes = [1, 1000, 2049, (1 << 17), (1 << 17) + 1, (1 << 18) + 33,  # one wave of the plain register tile: blockIdx order too
+             (1 << 19), (1 << 19) + 1, (1 << 20) + 4099, 1 << 21, (1 << 21) + 1, 1 << 22, (1 << 22) + 1,
              (1 << 23) + 777, (1 << 24) - 5, 1 << 24, (1 << 24) + 1, (1 << 25) + 1]
     for n in sizes:
         x = oracle.random_u32(n, seed=n % 1000)
