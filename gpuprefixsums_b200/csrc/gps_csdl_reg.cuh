@@ -14,8 +14,9 @@ namespace gps {
 // CSDL, register path
 // ---------------------------------------------------------------------------------
 // WIN: look-back windows per round trip; PROF: compile the phase timers in (tuning only)
-template <typename T, int NT, int V, bool INCLUSIVE, int WIN = 2, bool PROF = false>
-__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, 24 + 4 * V)) csdl_reg_kernel(const __grid_constant__ ScanParams p)
+// REGS: register budget per thread (decides the CTAs per SM the kernel is compiled for)
+template <typename T, int NT, int V, bool INCLUSIVE, int WIN = 2, bool PROF = false, int REGS = 24 + 4 * V>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) csdl_reg_kernel(const __grid_constant__ ScanParams p)
 {
     using Tile = RegTile<T, NT, V>;
     constexpr int NW = Tile::NW;

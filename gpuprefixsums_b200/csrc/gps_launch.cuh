@@ -124,14 +124,14 @@ cudaError_t launch_carry_only(Scratch& s, const CarrySpec& cs, cudaStream_t st)
 }
 
 // ---- CSDL register path --------------------------------------------------------------
-template <typename T, int NT, int V, bool INCL, int WIN = 2, bool PROF = false>
+template <typename T, int NT, int V, bool INCL, int WIN = 2, bool PROF = false, int REGS = 24 + 4 * V>
 cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
                             cudaStream_t st)
 {
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
     const cudaError_t e =
-        launch_scan_kernel(csdl_reg_kernel<T, NT, V, INCL, WIN, PROF>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
+        launch_scan_kernel(csdl_reg_kernel<T, NT, V, INCL, WIN, PROF, REGS>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
     // one claim per CTA -- of a launch that actually happened
     if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;

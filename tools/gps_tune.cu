@@ -654,6 +654,16 @@ static int run_all(Env& env, const char* filter)
                 CarrySpec cs;
                 return launch_csdl_reg<T, 128, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
             });
+            snprintf(name, sizeof(name), "exp/reg<256,4>r36/w1/flags%u", fl);  // 7 CTAs per SM: 2^22 keys = 1024 tiles fit one wave of 1036
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 256, 4, INCL, 1, false, 36>(env.s, in, out, env.n, cs, 0);
+            });
+            snprintf(name, sizeof(name), "exp/reg<256,4>r32/w1/flags%u", fl);  // 8 CTAs per SM
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 256, 4, INCL, 1, false, 32>(env.s, in, out, env.n, cs, 0);
+            });
             const FallbackParams f{kNoStall, 64u, nullptr};
             snprintf(name, sizeof(name), "exp/reg_fb<256,4>/flags%u/spin64", fl);
             run_variant(env, name, true, [&](const void* in, void* out) {
