@@ -194,7 +194,10 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
             // grid having to finish first), plain CSDL with tile = blockIdx.x cannot deadlock either -- whatever the
             // dispatch order, the tile a CTA waits for belongs to a CTA that is resident or will be as soon as
             // OTHER grids drain (a programmatically launched successor only starts once all of this grid's CTAs
-            // have, pdl_entry).  No ticket: 2^10 2.38 -> 2.10 us, 2^17 3.46 -> 3.04, 2^20 5.98 -> 5.14, 2^21 7.27 -> 6.41
+            // have, pdl_entry).  The one assumption: kernels sharing the device terminate independently of this
+            // scan (under in-order dispatch, cub::DeviceScan's assumption, not even that); "ticket_free" = 0 for
+            // callers who can guarantee neither.  No ticket: 2^10 2.38 -> 2.10 us, 2^17 3.46 -> 3.04, 2^20 5.98 -> 5.14,
+            // 2^21 7.27 -> 6.41
             const bool tiny = n <= GPS_REG_TINY_MAX_N && div_up(n, GPS_REG_TINY_NT * GPS_REG_TINY_V * 4) <= c->s.desc_tiles;
             const uint64_t tiles = tiny ? div_up(n, GPS_REG_TINY_NT * GPS_REG_TINY_V * 4) : div_up(n, GPS_REG_SMALL_NT * GPS_REG_SMALL_V * 4);
             int& resident = c->reg_resident[dt_index<T>()][INCL ? 0 : 1][tiny ? 1 : 0];

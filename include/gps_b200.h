@@ -106,12 +106,15 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   are emulated, else the register tile), 1 = register tile, 2 = smem-resident
  *                   tile, 3 = blocked smem-resident tile
  *   "ticket_free"   1 (default) = GPS_ALGO_CSDL takes tile = blockIdx.x instead of an atomic ticket
- *                   where that is provably deadlock-free under ANY CTA dispatch order: (a) grids of
- *                   at most one wave of the small register-tile kernels (every CTA becomes resident
- *                   without another CTA of the grid finishing first; up to ~3.6 M keys on 148 SMs);
- *                   (b) the Decoupled Fallback kernel (no CTA of it waits for another) for
+ *                   where that does not rest on in-order CTA dispatch alone: (a) grids of at most
+ *                   one wave of the small register-tile kernels (up to ~3.6 M keys on 148 SMs):
+ *                   every CTA becomes resident without another CTA of the grid finishing first, so
+ *                   it cannot deadlock under any dispatch order as long as the OTHER kernels on the
+ *                   device terminate independently of this scan (and under in-order dispatch, what
+ *                   cub::DeviceScan relies on, not even that is needed); (b) the Decoupled Fallback
+ *                   kernel -- no CTA of it waits for another, unconditionally deadlock-free -- for
  *                   2^19 < n <= 2^21 when (a) does not apply and for 2^22 < n <= 2^24 keys.
- *                   6..14 % faster there; 0 = atomic tickets everywhere
+ *                   9..18 % faster there.  0 = atomic tickets everywhere (needs neither assumption)
  *   "rts_variant"   Reduce-then-Scan propagate kernel: 0 = auto (blocked tile from 2^27 keys),
  *                   1 = register tile, 2 = blocked smem-resident tile
  *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)
