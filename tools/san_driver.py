@@ -36,6 +36,24 @@ for variant in (1, 2, 3):
         check(lib.gps_memcpy_d2d(f, a, N * 4, None))
         check(lib.gps_scan_emulated_deadlock(ctx, kind, capi.U32, f, f, N, 3, 1, stats, None))  # in place
 check(lib.gps_set_option(ctx, b"fallback_variant", 0))
+# end of round 2: ticket-free launches -- the default dispatch at these sizes (one-wave register tile with blockIdx order),
+# its ticketed counterpart, and the Decoupled Fallback kernels with tile = blockIdx.x (register / smem tile), with stalls
+for tf in (1, 0):
+    check(lib.gps_set_option(ctx, b"ticket_free", tf))
+    for kind in (capi.INCLUSIVE, capi.EXCLUSIVE):
+        for n in (N, 1 << 20, 2049):
+            check(lib.gps_scan(ctx, capi.ALGO_CSDL, kind, capi.U32, a, b, n, 3, None, None))
+check(lib.gps_set_option(ctx, b"ticket_free", 1))
+check(lib.gps_set_option(ctx, b"tile_order", 1))
+for variant in (1, 2):
+    check(lib.gps_set_option(ctx, b"fallback_variant", variant))
+    for kind in (capi.INCLUSIVE, capi.EXCLUSIVE):
+        check(lib.gps_scan(ctx, capi.ALGO_CSDL_FALLBACK, kind, capi.U32, a, b, 1 << 20, 1, None, None))
+        check(lib.gps_scan_emulated_deadlock(ctx, kind, capi.U32, a, b, N, 7, 2, stats, None))
+        check(lib.gps_memcpy_d2d(f, a, N * 4, None))
+        check(lib.gps_scan_emulated_deadlock(ctx, kind, capi.F32, f, f, N, 3, 1, stats, None))  # in place
+check(lib.gps_set_option(ctx, b"fallback_variant", 0))
+check(lib.gps_set_option(ctx, b"tile_order", 0))
 for variant in (1, 2):
     check(lib.gps_set_option(ctx, b"rts_variant", variant))
     for kind in (capi.INCLUSIVE, capi.EXCLUSIVE):
