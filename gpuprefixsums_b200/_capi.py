@@ -73,6 +73,7 @@ SIGNATURES = {
     "gps_validate_ones": (_i32, [_vp, _u64, _i32, _u32, C.POINTER(_u64)]),
     "gps_validate_ones_wide": (_i32, [_vp, _u64, _i32, _i32, C.POINTER(_u64)]),
     "gps_sort_fingerprint": (_i32, [_vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
+    "gps_sort_fingerprint64": (_i32, [_vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "gps_compare_u32": (_i32, [_vp, _vp, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "gps_compare_f32": (_i32, [_vp, _vp, _vp, _u64, C.c_float, C.c_float, C.POINTER(_u64), C.POINTER(C.c_float)]),
     "gps_set_device": (_i32, [_i32]),

@@ -1356,13 +1356,14 @@ int gps_validate_ones_wide(const void* d, uint64_t n, int kind, int dtype, uint6
     return GPS_OK;
 }
 
-int gps_sort_fingerprint(const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2])
+static int sort_fingerprint_impl(bool keys64, const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2])
 {
     if (!h_inversions || !h_sums || (n && !d_keys)) return fail(GPS_ERR_INVALID, "null pointer");
     unsigned long long* d_err = nullptr;
     GPS_CUDA(cudaMalloc(&d_err, 3 * sizeof(unsigned long long)));
     GPS_CUDA(cudaMemset(d_err, 0, 3 * sizeof(unsigned long long)));
-    if (n) sort_fingerprint_kernel<<<util_grid(n), 256>>>(static_cast<const uint32_t*>(d_keys), n, d_err);
+    if (n && keys64) sort_fingerprint_kernel<uint64_t><<<util_grid(n), 256>>>(static_cast<const uint64_t*>(d_keys), n, d_err);
+    if (n && !keys64) sort_fingerprint_kernel<uint32_t><<<util_grid(n), 256>>>(static_cast<const uint32_t*>(d_keys), n, d_err);
     unsigned long long h[3] = {0, 0, 0};
     cudaError_t e = cudaMemcpy(h, d_err, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d_err);
@@ -1371,6 +1372,16 @@ int gps_sort_fingerprint(const void* d_keys, uint64_t n, uint64_t* h_inversions,
     h_sums[0] = h[1];
     h_sums[1] = h[2];
     return GPS_OK;
+}
+
+int gps_sort_fingerprint(const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2])
+{
+    return sort_fingerprint_impl(false, d_keys, n, h_inversions, h_sums);
+}
+
+int gps_sort_fingerprint64(const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2])
+{
+    return sort_fingerprint_impl(true, d_keys, n, h_inversions, h_sums);
 }
 
 int gps_compare_u32(const void* d_a, const void* d_b, uint64_t n, uint64_t* h_errs, uint64_t* h_first_bad)

@@ -115,15 +115,16 @@ __global__ void validate_ones_u64_kernel(const uint64_t* d, uint64_t n, uint64_t
 
 // sortedness + multiset fingerprint of a sort: errs[0] = inversions between neighbours,
 // errs[1] = sum of keys, errs[2] = sum of key * (key >> 7 | 1) (both mod 2^64)
-__global__ void sort_fingerprint_kernel(const uint32_t* d, uint64_t n, unsigned long long* errs)
+template <typename K>  // uint32_t or uint64_t keys
+__global__ void sort_fingerprint_kernel(const K* d, uint64_t n, unsigned long long* errs)
 {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long inv = 0, s1 = 0, s2 = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint32_t k = d[i];
+        const K k = d[i];
         if (i && d[i - 1] > k) ++inv;
         s1 += k;
-        s2 += (unsigned long long)k * ((k >> 7) | 1u);
+        s2 += (unsigned long long)k * ((unsigned long long)(k >> 7) | 1ull);
     }
     if (inv) atomicAdd(errs, inv);
     atomicAdd(errs + 1, s1);

@@ -238,7 +238,74 @@ class RadixSortDispatcher : public ExtensionBase {
     }
 };
 
+// 64-bit keys (gps_sort_keys64): same protocol; the key buffers are filled as 2 n random 32-bit words
+class RadixSort64Dispatcher : public ExtensionBase {
+    bool runOne(uint64_t n, uint64_t seed, bool pairs, int key_type)
+    {
+        check(gps_init_random(m_a, 2 * n, GPS_U32, seed, 0xFFFFFFFFu, 0, nullptr), "gps_init_random");
+        uint64_t inv = 0, before[2], after[2];
+        check(gps_sort_fingerprint64(m_a, n, &inv, before), "fingerprint");
+        // pairs: the payload is the first n 32-bit words of the key buffer; keys and payload must each come out as
+        // the same multiset (fingerprints), the keys in order
+        char* b = static_cast<char*>(m_b);
+        char* c = static_cast<char*>(m_c);
+        void* vals_in = pairs ? m_a : nullptr;              // the first n 32-bit words of the key buffer
+        void* vals = pairs ? b + k_maxBytes / 2 : nullptr;  // keys take at most half of each buffer in pair mode
+        void* vals_tmp = pairs ? c + k_maxBytes / 2 : nullptr;
+        uint64_t vinv = 0, vbefore[2] = {0, 0}, vafter[2] = {0, 0};
+        if (pairs) check(gps_sort_fingerprint(vals_in, n, &vinv, vbefore), "fingerprint");
+        check(gps_sort_keys64(m_ctx, key_type, m_a, m_b, m_c, vals_in, vals, vals_tmp, n, 64, nullptr), "gps_sort_keys64");
+        if (!check(gps_check(m_ctx, nullptr), "gps_check")) return false;
+        check(gps_sort_fingerprint64(m_b, n, &inv, after), "fingerprint");
+        // signed order = unsigned order of key ^ 2^63: inversions are only counted for unsigned keys
+        bool good = (key_type != GPS_KEY_U32 || inv == 0) && before[0] == after[0] && before[1] == after[1];
+        if (good && pairs) {
+            check(gps_sort_fingerprint(vals, n, &vinv, vafter), "fingerprint");
+            good = vbefore[0] == vafter[0] && vbefore[1] == vafter[1];
+        }
+        return good;
+    }
+
+   public:
+    // three buffers of maxKeys 64-bit keys; pair tests use half of each for keys and half for the payload
+    explicit RadixSort64Dispatcher(uint64_t maxKeys) : ExtensionBase(maxKeys * 8, 3, "GPS radix sort, 64-bit keys") {}
+
+    void TestAll()
+    {
+        printf("Beginning GPS radix sort (64-bit keys) validation test: \n");
+        uint32_t passed = 0, total = 0;
+        const uint64_t maxKeys = k_maxBytes / 8;
+        for (int pairs = 0; pairs < 2; ++pairs) {
+            const uint64_t tile = pairs ? 5120 : 6144;
+            for (uint64_t n = tile - 3; n <= tile + 3; ++n) {
+                ++total;
+                if (runOne(n, 100 + n, pairs, GPS_KEY_U32)) ++passed;
+                else printf("\n Test failed at size %llu \n", (unsigned long long)n);
+            }
+            for (uint64_t n : {(uint64_t)1, (uint64_t)255, (uint64_t)1 << 20, pairs ? maxKeys / 4 : maxKeys}) {
+                ++total;
+                if (runOne(n, 7 + n, pairs, n == 255 ? GPS_KEY_I32 : GPS_KEY_U32)) ++passed;
+                else printf("\n Test failed at size %llu \n", (unsigned long long)n);
+            }
+            printf(".");
+        }
+        if (passed == total) printf("\n%u/%u All tests passed.\n\n", passed, total);
+        else printf("\n%u/%u Test failed.\n\n", passed, total);
+        if (passed != total) m_ok = false;
+    }
+    double BatchTiming(uint64_t n, uint32_t batchCount)
+    {
+        printf("Beginning GPS radix sort (64-bit keys) batch timing test at:\nSize: %llu\nTest size: %u\n", (unsigned long long)n,
+               batchCount);
+        check(gps_init_random(m_a, 2 * n, GPS_U32, 1, 0xFFFFFFFFu, 0, nullptr), "gps_init_random");
+        return timeLoop(n, batchCount, "64-bit keys", [&] {
+            check(gps_sort_keys64(m_ctx, GPS_KEY_U32, m_a, m_b, m_c, nullptr, nullptr, nullptr, n, 64, nullptr), "gps_sort_keys64");
+        });
+    }
+};
+
 }  // namespace gps_host
+using gps_host::RadixSort64Dispatcher;
 using gps_host::RadixSortDispatcher;
 using gps_host::StructScanDispatcher;
 using gps_host::Uint64ScanDispatcher;

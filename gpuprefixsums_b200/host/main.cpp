@@ -43,6 +43,12 @@ int main(int argc, char** argv)
             rs.BatchTiming(1 << 28, 20);
             ok = ok && rs.ok();
         }
+        {
+            RadixSort64Dispatcher rs64(1 << 27);
+            rs64.TestAll();
+            rs64.BatchTiming(1 << 27, 10);
+            ok = ok && rs64.ok();
+        }
         return ok ? 0 : 1;
     }
     {

@@ -314,6 +314,8 @@ int gps_validate_ones_wide(const void* d, uint64_t n, int kind, int dtype, uint6
 /* Sort checker: *h_inversions = number of i with keys[i-1] > keys[i]; h_sums = two order-
  * independent fingerprints of the key multiset (compare input against output).  Synchronous. */
 int gps_sort_fingerprint(const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2]);
+/* the same on uint64 keys (gps_sort_keys64) */
+int gps_sort_fingerprint64(const void* d_keys, uint64_t n, uint64_t* h_inversions, uint64_t h_sums[2]);
 int gps_compare_u32(const void* d_a, const void* d_b, uint64_t n, uint64_t* h_errs,
                     uint64_t* h_first_bad);
 /* float32: counts |a-b| > rtol*|d_bound[i]| + atol (d_bound nullable -> |b|) */

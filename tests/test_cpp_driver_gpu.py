@@ -27,12 +27,12 @@ def test_gps_main_full_reference_protocol():
 
 
 def test_gps_main_extensions():
-    """The C++ hosts of the widened rows (struct / uint64 scans, radix sort) over the C ABI."""
+    """The C++ hosts of the widened rows (struct / uint64 scans, radix sort on 32- and 64-bit keys) over the C ABI."""
     out = subprocess.run([BIN, "--ext"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
-    assert out.stdout.count("All tests passed.") == 3, out.stdout[-3000:]
+    assert out.stdout.count("All tests passed.") == 4, out.stdout[-3000:]
     assert "Test failed" not in out.stdout and "failed (" not in out.stdout
-    assert len(re.findall(r"Estimated speed at \d+ [\w -]+: [0-9.E+]+ per sec", out.stdout)) == 3
+    assert len(re.findall(r"Estimated speed at \d+ [\w -]+: [0-9.E+]+ per sec", out.stdout)) == 4
 
 
 REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "ref_main_dropin")
