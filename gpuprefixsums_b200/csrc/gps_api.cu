@@ -73,7 +73,7 @@ struct gps_ctx {
     bool smem_configured[2][2] = {{false, false}, {false, false}};
     bool blocked_configured[2][2] = {{false, false}, {false, false}};
     bool smem_fb_configured[2][2] = {{false, false}, {false, false}};
-    int reg_resident[2][2][2] = {};  // [dtype][kind][tiny shape]: CTAs of the small register-tile kernels the device holds at once (0 = not asked yet)
+    int reg_resident[2][2][3] = {};  // [dtype][kind][small / tiny / mid shape]: CTAs of the register-tile kernels the device holds at once (0 = not asked yet)
     bool blocked_fb_configured[2][2] = {{false, false}, {false, false}};
     bool rts_blocked_configured[2][2] = {{false, false}, {false, false}};
     int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile, 3 blocked tile
@@ -215,6 +215,27 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
                 c->s.flags |= PF_STATIC_TILE;
                 e = tiny ? launch_csdl_reg<T, GPS_REG_TINY_NT, GPS_REG_TINY_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st)
                          : launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                c->s.flags &= ~PF_STATIC_TILE;
+                if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
+                return GPS_OK;
+            }
+        }
+        if (algo == GPS_ALGO_CSDL && c->csdl_variant == 0 && c->ticket_free && !(c->s.flags & PF_STATIC_TILE) &&
+            n <= GPS_TICKET_FREE_SMEM_MAX_N) {
+            // ... and the sizes just above one wave of the <256,4> tile fit one wave of the <128,8> register tile
+            // (9 CTAs per SM): the same argument, the same blockIdx order (gps_config.h GPS_REG_MID_*)
+            const uint64_t tiles = div_up(n, GPS_REG_MID_NT * GPS_REG_MID_V * 4);
+            int& resident = c->reg_resident[dt_index<T>()][INCL ? 0 : 1][2];
+            if (!resident) {
+                int per_sm = 0;
+                const cudaError_t q = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                    &per_sm, csdl_reg_kernel<T, GPS_REG_MID_NT, GPS_REG_MID_V, INCL, GPS_LOOKBACK_WIN, false>, GPS_REG_MID_NT, 0);
+                resident = q == cudaSuccess && per_sm > 0 ? per_sm * c->s.sm_count : -1;
+                if (q != cudaSuccess) cudaGetLastError();
+            }
+            if (resident > 0 && tiles <= (uint64_t)resident && tiles <= c->s.desc_tiles) {
+                c->s.flags |= PF_STATIC_TILE;
+                e = launch_csdl_reg<T, GPS_REG_MID_NT, GPS_REG_MID_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 c->s.flags &= ~PF_STATIC_TILE;
                 if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
                 return GPS_OK;

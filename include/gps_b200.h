@@ -107,13 +107,14 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   tile, 3 = blocked smem-resident tile
  *   "ticket_free"   1 (default) = GPS_ALGO_CSDL takes tile = blockIdx.x instead of an atomic ticket
  *                   where that does not rest on in-order CTA dispatch alone: (a) grids of at most
- *                   one wave of the small register-tile kernels (up to ~3.6 M keys on 148 SMs):
+ *                   one wave of a register-tile kernel (<256,4> up to ~3.6 M keys on 148 SMs,
+ *                   <128,8> from there to ~5.4 M):
  *                   every CTA becomes resident without another CTA of the grid finishing first, so
  *                   it cannot deadlock under any dispatch order as long as the OTHER kernels on the
  *                   device terminate independently of this scan (and under in-order dispatch, what
  *                   cub::DeviceScan relies on, not even that is needed); (b) the Decoupled Fallback
  *                   kernel -- no CTA of it waits for another, unconditionally deadlock-free -- for
- *                   2^19 < n <= 2^21 when (a) does not apply and for 2^22 < n <= 2^24 keys.
+ *                   the sizes up to 2^24 keys that (a) does not cover.
  *                   9..18 % faster there.  0 = atomic tickets everywhere (needs neither assumption)
  *   "rts_variant"   Reduce-then-Scan propagate kernel: 0 = auto (blocked tile from 2^27 keys),
  *                   1 = register tile, 2 = blocked smem-resident tile

@@ -650,6 +650,7 @@ def test_ticket_free_decoupled_fallback_default(gps, oracle):
     ps = gps.PrefixSum((1 << 25) + 4096)
     sizes = [1, 1000, 2049, (1 << 17), (1 << 17) + 1, (1 << 18) + 33,  # one wave of the plain register tile: blockIdx order too
              (1 << 19), (1 << 19) + 1, (1 << 20) + 4099, 1 << 21, (1 << 21) + 1, 1 << 22, (1 << 22) + 1,
+             3_800_000, 4_500_001, 1332 * 4096, 1332 * 4096 + 1,  # one wave of the <128,8> register tile, and just above it
              (1 << 23) + 777, (1 << 24) - 5, 1 << 24, (1 << 24) + 1, (1 << 25) + 1]
     for n in sizes:
         x = oracle.random_u32(n, seed=n % 1000)

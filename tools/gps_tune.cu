@@ -654,6 +654,16 @@ static int run_all(Env& env, const char* filter)
                 CarrySpec cs;
                 return launch_csdl_reg<T, 128, 4, INCL, 1>(env.s, in, out, env.n, cs, 0);
             });
+            snprintf(name, sizeof(name), "exp/reg<128,8>/w1/flags%u", fl);  // 56 registers -> 9 CTAs of 128 threads per SM: one wave = 1332 tiles of 4096 keys
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 128, 8, INCL, 1>(env.s, in, out, env.n, cs, 0);
+            });
+            snprintf(name, sizeof(name), "exp/reg<128,6>/w1/flags%u", fl);  // 48 registers -> 10 CTAs per SM: one wave = 1480 tiles of 3072 keys
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_reg<T, 128, 6, INCL, 1>(env.s, in, out, env.n, cs, 0);
+            });
             snprintf(name, sizeof(name), "exp/reg<256,4>r36/w1/flags%u", fl);  // 7 CTAs per SM: 2^22 keys = 1024 tiles fit one wave of 1036
             run_variant(env, name, true, [&](const void* in, void* out) {
                 CarrySpec cs;

@@ -14,7 +14,7 @@ import gpuprefixsums_b200 as gps  # noqa: E402
 
 ps = gps.PrefixSum(1 << 26)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-sizes = [1 << lg for lg in range(10, 27)] + [(1 << 20) + (1 << 19), 3 << 20, 3 << 22, 3 << 23]
+sizes = [1 << lg for lg in range(10, 27)] + [(1 << 20) + (1 << 19), 3 << 20, 3_800_000, 4_500_000, 5_000_000, 6_000_000, 3 << 22, 3 << 23]
 side = torch.cuda.Stream()
 for n in sorted(sizes):
     x = torch.empty(n, dtype=torch.int32, device="cuda")
