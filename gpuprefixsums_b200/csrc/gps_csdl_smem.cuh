@@ -247,6 +247,98 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
 }
 
 // ---------------------------------------------------------------------------------
+// Persistent one-wave variant: the grid is at most ONE wave of CTAs (the host passes gridDim.x <= CTAs the
+// device holds at once) and CTA c scans tiles c, c + gridDim.x, c + 2 gridDim.x, ... in that order.  No ticket
+// and no dependence on the dispatch order: every tile below the one a CTA waits for belongs to a CTA that is
+// resident and works through ITS tiles in increasing order, so by induction on the tile index every wait ends
+// (given that all CTAs of the grid do become resident, i.e. that other kernels on the device drain).  Per
+// tile it saves the ticket's round trip and the launch of a new CTA; the tile pipeline is csdl_smem_kernel's.
+// ---------------------------------------------------------------------------------
+template <typename T, int NT, int V, bool INCLUSIVE, int WIN = 1, int G = 4, int REGS = 40>
+__global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
+    csdl_smem_persistent_kernel(const __grid_constant__ ScanParams p)
+{
+    constexpr int NW = NT / 32;
+    constexpr uint32_t TILE_VEC = NT * V;
+    constexpr uint32_t TILE_KEYS = TILE_VEC * 4;
+    constexpr uint32_t TILE_BYTES = TILE_KEYS * 4;
+    __shared__ __align__(128) uint4 s_data[TILE_VEC];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ T s_warp[NW];
+    __shared__ T s_prefix;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u;
+    const uint32_t warp = tid >> 5;
+    const uint32_t row0 = warp * (32u * V) + lane;
+    pdl_entry();
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t parity = 0;
+#pragma unroll 1
+    for (uint32_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const bool full = ((uint64_t)tile + 1u) * TILE_KEYS <= p.n;  // block-uniform
+        const uint64_t vbase = (uint64_t)tile * TILE_VEC + row0;
+        if (full) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&s_bar, TILE_BYTES);
+                tile_bulk_load(p.flags, s_data, reinterpret_cast<const unsigned char*>(p.in) + (uint64_t)tile * TILE_BYTES,
+                               TILE_BYTES, &s_bar);
+            }
+            if (!mbar_wait_bounded(&s_bar, parity)) {  // never expected; do not hang the GPU
+                atomicOr(p.status, STATUS_WATCHDOG);
+                return;
+            }
+            parity ^= 1u;
+        } else {
+            const uint32_t* in1 = reinterpret_cast<const uint32_t*>(p.in);
+#pragma unroll 1
+            for (int k = 0; k < V; ++k) {
+                const uint64_t e = (vbase + 32u * k) * 4u;
+                uint4 r;
+                r.x = e + 0 < p.n ? in1[e + 0] : 0u;
+                r.y = e + 1 < p.n ? in1[e + 1] : 0u;
+                r.z = e + 2 < p.n ? in1[e + 2] : 0u;
+                r.w = e + 3 < p.n ? in1[e + 3] : 0u;
+                s_data[row0 + 32u * k] = r;
+            }
+        }
+        // ---- pass 1: aggregate first
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const uint4 r = s_data[row0 + 32u * k];
+            acc += (from_bits<T>(r.x) + from_bits<T>(r.y)) + (from_bits<T>(r.z) + from_bits<T>(r.w));
+        }
+        const T wsum = warp_reduce(acc);
+        if (lane == 0) s_warp[warp] = wsum;
+        __syncthreads();
+        const T wraw = lane < (uint32_t)NW ? s_warp[lane] : T(0);
+        const T aggregate = warp_reduce(wraw);
+        if (warp == 0 && lane == 0 && tile != 0)
+            desc_publish(p, p.desc + tile, pack_desc(to_bits(aggregate), p.epoch, ST_AGGREGATE));
+        const T winc = warp_inclusive_scan(wraw, lane);
+        const T warp_prefix = __shfl_sync(kFullMask, warp_exclusive_of(winc, wraw, lane), (int)warp);
+        if (warp == 0) {
+            const T prefix = tile == 0 ? acquire_carry<T>(p, lane) : lookback_warp<T, WIN, GPS_LOOKBACK_MAXWIN>(p, tile, lane);
+            if (lane == 0) {
+                const T inclusive = prefix + aggregate;
+                desc_publish(p, p.desc + tile, pack_desc(to_bits(inclusive), p.epoch, ST_INCLUSIVE));
+                s_prefix = prefix;
+                if (tile == p.num_tiles - 1) write_total<T>(p, inclusive);
+            }
+        }
+        __syncthreads();
+        smem_tile_finish<T, V, INCLUSIVE, G>(s_data, row0, vbase, full, p.n, p.out, lane, s_prefix + warp_prefix, p.flags);
+        __syncthreads();  // the tile buffer, s_warp and s_prefix are reused by the next tile
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // The same tile pipeline with Decoupled Fallback (and optional emulated stalls): the
 // smem-resident counterpart of csdl_fallback_kernel in gps_csdl_reg.cuh, which documents the
 // protocol (EmulatedDeadlocking.cuh:63-151 of the reference: spin budget, whole-CTA
@@ -517,7 +609,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_mbar_init();
-        const uint32_t t = claim_tile(p);
+        const uint32_t t = (p.flags & PF_STATIC_TILE) ? blockIdx.x : claim_tile(p);  // ticket-free: see csdl_smem_fallback_kernel
         s_tile = t;
         Tile::issue_load(s_data, &s_bar, p.in, t, p.n);
     }

@@ -157,7 +157,27 @@ cudaError_t launch_csdl_smem(Scratch& s, const void* in, void* out, uint64_t n, 
     return e;
 }
 
-// ---- CSDL blocked shared-memory tile (TMA bulk load + per-warp TMA bulk store) --------
+// persistent one-wave variant: `resident` = in/out cache of the CTAs the device holds at once (0 = ask the runtime)
+template <typename T, int NT, int V, bool INCL, int WIN = 1, int G = 4, int REGS = 40>
+cudaError_t launch_csdl_smem_persistent(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
+                                        int& resident, cudaStream_t st)
+{
+    auto kern = csdl_smem_persistent_kernel<T, NT, V, INCL, WIN, G, REGS>;
+    if (resident == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        int per_sm = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0);
+        if (e != cudaSuccess) return e;
+        resident = per_sm > 0 ? per_sm * s.sm_count : -1;
+    }
+    if (resident <= 0) return cudaErrorInvalidConfiguration;
+    ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
+    const uint32_t grid = p.num_tiles < (uint32_t)resident ? p.num_tiles : (uint32_t)resident;
+    return launch_scan_kernel(kern, grid, NT, 0, st, s.flags & PF_PDL, p);  // no tickets: counter_base stays
+}
+
+// ---- CSDL blocked shared-memory tile (TMA bulk load + per-warp TMA bulk store) --------// ---- CSDL blocked shared-memory tile (TMA bulk load + per-warp TMA bulk store) --------
 template <typename T, int NT, int V, bool INCL, int WIN = 1, int REGS = 40>
 cudaError_t launch_csdl_blocked(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
                                 bool& configured, cudaStream_t st)
@@ -262,7 +282,7 @@ cudaError_t launch_csdl_blocked_fallback(Scratch& s, const void* in, void* out, 
     }
     ScanParams p = make_scan_params(s, in, out, n, (uint32_t)(NT * V * 4), cs, st);
     const cudaError_t e = launch_scan_kernel(kern, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p, f);
-    if (e == cudaSuccess) s.counter_base += p.num_tiles;
+    if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;
 }
 

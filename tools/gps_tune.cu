@@ -619,6 +619,34 @@ static int run_all(Env& env, const char* filter)
             }
         }
         env.s.poll_sleep_ns = 0;
+        // persistent one-wave kernel (CTA c scans tiles c, c + grid, ...): no ticket, no CTA launch per tile
+        for (uint32_t fl : {0u, (uint32_t)PF_L2_IN_EVICT_FIRST}) {
+            env.s.flags = fl | pdl_base;
+            char name[96];
+            static int res_p = 0;
+            snprintf(name, sizeof(name), "exp/smem_persistent<128,8>/flags%u", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_smem_persistent<T, 128, 8, INCL, 1>(env.s, in, out, env.n, cs, res_p, 0);
+            });
+        }
+        // the blocked tile (default from 2^27 keys): ticket vs blockIdx order, plain and Decoupled Fallback
+        for (uint32_t fl : {0u, (uint32_t)PF_STATIC_TILE}) {
+            env.s.flags = fl | pdl_base;
+            char name[96];
+            static bool cfgb = false, cfgbf = false;
+            snprintf(name, sizeof(name), "exp/blocked<256,9>/flags%u", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_blocked<T, 256, 9, INCL, 1>(env.s, in, out, env.n, cs, cfgb, 0);
+            });
+            const FallbackParams fbp{kNoStall, 64u, nullptr};
+            snprintf(name, sizeof(name), "exp/blocked_fb<256,9>/flags%u/spin64", fl);
+            run_variant(env, name, true, [&](const void* in, void* out) {
+                CarrySpec cs;
+                return launch_csdl_blocked_fallback<T, 256, 9, INCL>(env.s, in, out, env.n, cs, fbp, cfgbf, 0);
+            });
+        }
         // Decoupled Fallback without tickets (tile = blockIdx.x is deadlock-free there), spin budgets, no stalls
         static uint32_t* fb_stats = nullptr;  // {spins, fallbacks, insertions, windows} summed over the variant's launches
         if (!fb_stats) CK(cudaMalloc(&fb_stats, 4 * sizeof(uint32_t)));

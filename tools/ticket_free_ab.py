@@ -16,6 +16,10 @@ IN_PLACE = "--in-place" in sys.argv  # time gps_scan(x, x): results are then not
 ps = gps.PrefixSum(1 << 26)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 sizes = [1 << lg for lg in range(10, 27)] + [(1 << 20) + (1 << 19), 3 << 20, 3_800_000, 4_500_000, 5_000_000, 6_000_000, 3 << 22, 3 << 23]
+if "big" in sys.argv:  # only the upper mid sizes (a build with a wider ticket-free range)
+    sizes = [1 << 24, 3 << 23, 1 << 25, 3 << 24, 1 << 26, 100_000_000, (1 << 27) - 4096]
+    ps.close()
+    ps = gps.PrefixSum(1 << 27)
 side = torch.cuda.Stream()
 for n in sorted(sizes):
     x = torch.empty(n, dtype=torch.int32, device="cuda")
