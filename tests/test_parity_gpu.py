@@ -691,12 +691,12 @@ def test_ticket_free_decoupled_fallback_default(gps, oracle):
 
 def test_ticket_free_fallback_under_emulated_stalls(gps, oracle):
     """tile_order = 1 makes the emulated-deadlock harness run ticket-free as well: stalled tiles are rescued by
-    their successors' fallbacks exactly as with tickets (register and smem tiles; the blocked tile keeps tickets)."""
+    their successors' fallbacks exactly as with tickets (register, smem and blocked tiles)."""
     ps = gps.PrefixSum(1 << 23)
     ps.set_option("tile_order", 1)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         ps.set_option("fallback_variant", variant)
-        for n in [(1 << 20) + 4099, (1 << 22) + 5]:
+        for n in [(1 << 20) + 4099, (1 << 22) + 5] + ([(1 << 23) - 11] if variant == 3 else []):
             x = oracle.random_u32(n, seed=n % 91)
             for exclusive in (False, True):
                 stats = torch.zeros(4, dtype=torch.int32, device="cuda")
