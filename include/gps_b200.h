@@ -112,7 +112,9 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   every CTA becomes resident without another CTA of the grid finishing first, so
  *                   it cannot deadlock under any dispatch order as long as the OTHER kernels on the
  *                   device terminate independently of this scan (and under in-order dispatch, what
- *                   cub::DeviceScan relies on, not even that is needed); (b) the Decoupled Fallback
+ *                   cub::DeviceScan relies on, not even that is needed -- e.g. for two such scans
+ *                   in flight on different streams at once, each waiting for slots the other
+ *                   holds); (b) the Decoupled Fallback
  *                   kernel -- no CTA of it waits for another, unconditionally deadlock-free -- for
  *                   the sizes up to 2^24 keys that (a) does not cover.
  *                   9..18 % faster there.  0 = atomic tickets everywhere (needs neither assumption)

@@ -706,3 +706,34 @@ def test_ticket_free_fallback_under_emulated_stalls(gps, oracle):
                 st = stats.cpu().numpy()
                 assert st[1] > 0 and st[2] > 0, f"no fallbacks recorded: {st}"
     ps.close()
+
+
+def test_ticket_free_scans_concurrently_on_two_streams(gps, oracle):
+    """Two contexts on two streams, their ticket-free scans (one-wave register tiles, Decoupled Fallback smem tile) in flight at
+    the same time: together the one-wave grids exceed what the device holds, so CTAs of one grid wait for slots the other grid
+    occupies.  The Decoupled Fallback kernels need nothing for that; the one-wave kernels finish because CTAs are dispatched in
+    index order (include/gps_b200.h, "ticket_free").  Every result is checked."""
+    a, b = gps.PrefixSum(1 << 24), gps.PrefixSum(1 << 24)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    sizes = [(1 << 21) + 77, 3_500_000, 5_000_000, (1 << 23) + 5, 1 << 20, 3_600_000]
+    xs = {n: oracle.random_u32(n, seed=n % 101) for n in sizes}
+    ds = {n: to_dev_u32(xs[n]) for n in sizes}
+    wants = {n: oracle.scan_u32(xs[n])[0] for n in sizes}
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(6):
+        for i, n in enumerate(sizes):
+            m = sizes[(i + 3) % len(sizes)]
+            with torch.cuda.stream(sa):
+                oa = a.scan(ds[n], stream=sa)
+            with torch.cuda.stream(sb):
+                ob = b.scan(ds[m], stream=sb)
+            outs.append((n, oa))
+            outs.append((m, ob))
+    torch.cuda.synchronize()
+    a.check()
+    b.check()
+    for n, o in outs:
+        assert np.array_equal(to_np_u32(o), wants[n]), n
+    a.close()
+    b.close()
