@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
     // runs while the TMA load is in flight; warps 1.. reduce the whole tile (warp 0's rows dealt round-robin
     // among them) and publish the aggregate without waiting for warp 0.  The ~2 L2 round trips of the look-back
     // leave the CTA's critical path: load -> reduce -> (prefix already there) -> scan + store.
+    // MEASURED (profiles/r02_ticket_free.txt A): bit-exact, and no gain at any size -- what a mid-size CTA waits for is the
+    // slowest predecessor LOAD, not the polls.  Kept for the tuning harness only (no library option sets the flag).
     if constexpr (NW >= 3) {
         if ((p.flags & PF_EAGER_LOOKBACK) && full && tile != 0u) {
             __shared__ T s_part[NW];
@@ -253,6 +255,8 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
 // resident and works through ITS tiles in increasing order, so by induction on the tile index every wait ends
 // (given that all CTAs of the grid do become resident, i.e. that other kernels on the device drain).  Per
 // tile it saves the ticket's round trip and the launch of a new CTA; the tile pipeline is csdl_smem_kernel's.
+// MEASURED (profiles/r02_ticket_free.txt I): no gain from 2^22 to 2^28 -- a looping CTA serialises load -> look-back ->
+// store per slot exactly like a fresh CTA.  Instantiated by the tuning harness only.
 // ---------------------------------------------------------------------------------
 template <typename T, int NT, int V, bool INCLUSIVE, int WIN = 1, int G = 4, int REGS = 40>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS))
