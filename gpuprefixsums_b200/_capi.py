@@ -50,6 +50,7 @@ SIGNATURES = {
     "gps_destroy": (None, [_vp]),
     "gps_check": (_i32, [_vp, _vp]),
     "gps_set_option": (_i32, [_vp, C.c_char_p, C.c_int64]),
+    "gps_get_option": (_i32, [_vp, C.c_char_p, _vp]),
     "gps_scratch_bytes": (_u64, [_u64]),
     "gps_scan": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _u32, _vp, _vp]),
     "gps_scan_wide": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _u64, _vp, _vp, _vp]),

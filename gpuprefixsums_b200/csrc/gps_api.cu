@@ -78,6 +78,7 @@ struct gps_ctx {
     bool rts_blocked_configured[2][2] = {{false, false}, {false, false}};
     int fallback_variant = 0;       // 0 auto, 1 register tile, 2 smem-resident tile, 3 blocked tile
     int ticket_free = 1;            // GPS_ALGO_CSDL: ticket-free Decoupled Fallback where it is faster (gps_config.h)
+    int rescued = 0;                // gps_check saw STATUS_RESCUED since the last gps_get_option("rescued")
     int rts_variant = 0;            // 0 auto, 1 register-tile propagate, 2 blocked-tile propagate
     int sharded_pdl = GPS_SHARDED_PDL_DEFAULT;  // see NoPdlScope
     int sharded_l2 = GPS_SHARDED_L2_DEFAULT;    // option "sharded_l2"
@@ -202,19 +203,33 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
             const uint64_t tiles = tiny ? div_up(n, GPS_REG_TINY_NT * GPS_REG_TINY_V * 4) : div_up(n, GPS_REG_SMALL_NT * GPS_REG_SMALL_V * 4);
             int& resident = c->reg_resident[dt_index<T>()][INCL ? 0 : 1][tiny ? 1 : 0];
             if (!resident) {
-                int per_sm = 0;
-                const cudaError_t q =
+                // (the smaller of the lean kernel's and the rescue-carrying kernel's occupancy: either may be launched)
+                int per_sm = 0, per_sm_r = 0;
+                cudaError_t q =
                     tiny ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                &per_sm, csdl_reg_kernel<T, GPS_REG_TINY_NT, GPS_REG_TINY_V, INCL, GPS_LOOKBACK_WIN, false>, GPS_REG_TINY_NT, 0)
                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                                &per_sm, csdl_reg_kernel<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN, false>, GPS_REG_SMALL_NT, 0);
+                if (q == cudaSuccess)
+                    q = tiny ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                   &per_sm_r, csdl_reg_kernel<T, GPS_REG_TINY_NT, GPS_REG_TINY_V, INCL, GPS_LOOKBACK_WIN, false, 24 + 4 * GPS_REG_TINY_V, true>,
+                                   GPS_REG_TINY_NT, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                                   &per_sm_r, csdl_reg_kernel<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN, false, 24 + 4 * GPS_REG_SMALL_V, true>,
+                                   GPS_REG_SMALL_NT, 0);
+                per_sm = std::min(per_sm, per_sm_r);
                 resident = q == cudaSuccess && per_sm > 0 ? per_sm * c->s.sm_count : -1;
                 if (q != cudaSuccess) cudaGetLastError();
             }
             if (resident > 0 && tiles <= (uint64_t)resident) {
                 c->s.flags |= PF_STATIC_TILE;
-                e = tiny ? launch_csdl_reg<T, GPS_REG_TINY_NT, GPS_REG_TINY_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st)
-                         : launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                constexpr int RT = 24 + 4 * GPS_REG_TINY_V, RS = 24 + 4 * GPS_REG_SMALL_V;
+                if (c->ticket_free == 1)  // with the warp-level rescue: needs nothing of the dispatch order or of other kernels
+                    e = tiny ? launch_csdl_reg<T, GPS_REG_TINY_NT, GPS_REG_TINY_V, INCL, GPS_LOOKBACK_WIN, false, RT, true>(c->s, in, out, n, cs, st)
+                             : launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN, false, RS, true>(c->s, in, out, n, cs, st);
+                else  // "ticket_free" = 2: the lean kernels
+                    e = tiny ? launch_csdl_reg<T, GPS_REG_TINY_NT, GPS_REG_TINY_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st)
+                             : launch_csdl_reg<T, GPS_REG_SMALL_NT, GPS_REG_SMALL_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 c->s.flags &= ~PF_STATIC_TILE;
                 if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
                 return GPS_OK;
@@ -227,15 +242,23 @@ int dispatch_scan_tk(gps_ctx* c, int algo, const void* in, void* out, uint64_t n
             const uint64_t tiles = div_up(n, GPS_REG_MID_NT * GPS_REG_MID_V * 4);
             int& resident = c->reg_resident[dt_index<T>()][INCL ? 0 : 1][2];
             if (!resident) {
-                int per_sm = 0;
-                const cudaError_t q = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                int per_sm = 0, per_sm_r = 0;
+                cudaError_t q = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                     &per_sm, csdl_reg_kernel<T, GPS_REG_MID_NT, GPS_REG_MID_V, INCL, GPS_LOOKBACK_WIN, false>, GPS_REG_MID_NT, 0);
+                if (q == cudaSuccess)
+                    q = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &per_sm_r, csdl_reg_kernel<T, GPS_REG_MID_NT, GPS_REG_MID_V, INCL, GPS_LOOKBACK_WIN, false, 24 + 4 * GPS_REG_MID_V, true>,
+                        GPS_REG_MID_NT, 0);
+                per_sm = std::min(per_sm, per_sm_r);
                 resident = q == cudaSuccess && per_sm > 0 ? per_sm * c->s.sm_count : -1;
                 if (q != cudaSuccess) cudaGetLastError();
             }
             if (resident > 0 && tiles <= (uint64_t)resident && tiles <= c->s.desc_tiles) {
                 c->s.flags |= PF_STATIC_TILE;
-                e = launch_csdl_reg<T, GPS_REG_MID_NT, GPS_REG_MID_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
+                constexpr int RM = 24 + 4 * GPS_REG_MID_V;
+                e = c->ticket_free == 1
+                        ? launch_csdl_reg<T, GPS_REG_MID_NT, GPS_REG_MID_V, INCL, GPS_LOOKBACK_WIN, false, RM, true>(c->s, in, out, n, cs, st)
+                        : launch_csdl_reg<T, GPS_REG_MID_NT, GPS_REG_MID_V, INCL, GPS_LOOKBACK_WIN>(c->s, in, out, n, cs, st);
                 c->s.flags &= ~PF_STATIC_TILE;
                 if (e != cudaSuccess) return fail(GPS_ERR_CUDA, "scan launch failed: %s", cudaGetErrorString(e));
                 return GPS_OK;
@@ -856,6 +879,11 @@ int gps_check(gps_ctx* c, void* stream)
     GPS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     uint32_t st = 0;
     GPS_CUDA(cudaMemcpy(&st, c->s.status, sizeof(st), cudaMemcpyDeviceToHost));
+    if (st & STATUS_RESCUED) {  // informational: a ticket-free one-wave scan rescued a late tile (results are valid)
+        c->rescued = 1;
+        st &= ~STATUS_RESCUED;
+        if (!st) GPS_CUDA(cudaMemset(c->s.status, 0, sizeof(uint32_t)));
+    }
     if (st) {
         // CTAs that bailed out may have skipped ticket claims: bring the host's ticket base back
         // in step with the device counter once everything has drained
@@ -870,6 +898,24 @@ int gps_check(gps_ctx* c, void* stream)
     return GPS_OK;
 }
 
+int gps_get_option(gps_ctx* c, const char* key, int64_t* value)
+{
+    if (!c || !key || !value) return fail(GPS_ERR_INVALID, "null argument");
+    if (!strcmp(key, "rescued")) {  // 1 if a gps_check since the last query saw a rescued tile; reading clears it
+        *value = c->rescued;
+        c->rescued = 0;
+    } else if (!strcmp(key, "ticket_free")) {
+        *value = c->ticket_free;
+    } else if (!strcmp(key, "pdl")) {
+        *value = (c->s.flags & PF_PDL) ? 1 : 0;
+    } else if (!strcmp(key, "tile_order")) {
+        *value = (c->s.flags & PF_STATIC_TILE) ? 1 : 0;
+    } else {
+        return fail(GPS_ERR_INVALID, "unknown option '%s'", key);
+    }
+    return GPS_OK;
+}
+
 int gps_set_option(gps_ctx* c, const char* key, int64_t value)
 {
     if (!c || !key) return fail(GPS_ERR_INVALID, "null argument");
@@ -877,7 +923,7 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
         if (value < 0 || value > 4) return fail(GPS_ERR_INVALID, "csdl_variant must be 0..4");
         c->csdl_variant = (int)value;
     } else if (!strcmp(key, "ticket_free")) {
-        if (value != 0 && value != 1) return fail(GPS_ERR_INVALID, "ticket_free must be 0 or 1");
+        if (value < 0 || value > 2) return fail(GPS_ERR_INVALID, "ticket_free must be 0, 1 or 2");
         c->ticket_free = (int)value;
     } else if (!strcmp(key, "fallback_variant")) {
         if (value < 0 || value > 3) return fail(GPS_ERR_INVALID, "fallback_variant must be 0..3");
@@ -893,6 +939,10 @@ int gps_set_option(gps_ctx* c, const char* key, int64_t value)
         // test hook: jump the launch epoch (e.g. just below the 2^30 wrap)
         if (value < 0 || value >= (1ll << 30)) return fail(GPS_ERR_INVALID, "epoch out of range");
         c->s.epoch = (uint32_t)value;
+    } else if (!strcmp(key, "debug_delay_tile")) {
+        // test hook: the CTA of tile (value - 1) of the register-tile kernels starts ~40 ms late (0 = off)
+        if (value < 0 || value > 0xFFFFFFFFll) return fail(GPS_ERR_INVALID, "debug_delay_tile out of range");
+        c->s.debug_delay_tile = (uint32_t)value;
     } else if (!strcmp(key, "debug_counter")) {
         // test hook: jump the never-reset ticket counter (e.g. just below the 2^32 wrap)
         DeviceGuard g(c->device);

@@ -56,6 +56,7 @@ struct ScanParams {
     uint32_t poll_sleep_ns;
     uint32_t flags;           // PF_* bits
     unsigned long long* prof; // optional (tuning): kProfSlots x kProfFields counters
+    uint32_t debug_delay_tile; // test hook: the CTA of tile (value - 1) sleeps ~40 ms before it starts (0 = off)
 };
 // profiling counters (per tile, accumulated): SM cycles spent in each phase + look-back effort
 enum : int { PROF_TILES = 0, PROF_CLAIM, PROF_LOAD, PROF_REDUCE, PROF_LOOKBACK, PROF_FINISH,
@@ -93,7 +94,9 @@ enum : uint32_t {
 };
 
 enum : uint32_t { ST_NOT_READY = 0, ST_AGGREGATE = 1, ST_INCLUSIVE = 2, ST_MASK = 3 };
-enum : uint32_t { STATUS_WATCHDOG = 1u, STATUS_SLOT_TIMEOUT = 2u };
+// STATUS_RESCUED is informational (a one-wave ticket-free scan rescued a tile whose CTA was late, see rescue_tile_warp)
+enum : uint32_t { STATUS_WATCHDOG = 1u, STATUS_SLOT_TIMEOUT = 2u, STATUS_RESCUED = 0x100u };
+constexpr uint32_t kRescuePolls = 1u << 14;  // unsuccessful polls of the nearest tile (~10 ms) before a rescue
 constexpr uint32_t kFullMask = 0xFFFFFFFFu;
 // CTAs per SM the scan kernels are compiled for: as many as fit at `regs` registers/thread
 constexpr int min_ctas_per_sm(int nt, int regs = 40) { return 65536 / (nt * regs) > 0 ? 65536 / (nt * regs) : 1; }
@@ -557,6 +560,43 @@ __device__ __forceinline__ uint32_t claim_tile(const ScanParams& p)
 // virtual INCLUSIVE/0 entry (they are never the nearest INCLUSIVE because tile 0
 // itself always publishes INCLUSIVE).  Returns the exclusive prefix of `tile`.
 // ---------------------------------------------------------------------------------
+// Warp-level Decoupled Fallback for the plain kernels that run ticket-free (tile = blockIdx.x, one-wave grids): when the
+// nearest predecessor has not published after kRescuePolls polls -- its CTA is not resident yet, which in-order dispatch
+// never lets happen -- the polling warp re-reduces that tile from the INPUT (full by construction: a blocker is never the
+// last tile) and inserts its aggregate with CAS, exactly what the Decoupled Fallback kernels do block-wide
+// (EmulatedDeadlocking.cuh:103-151 of the reference).  The walk then continues on what it finds there -- its own word or
+// the owner's.  Cold path only: a separate function, called through the look-back's OnStuck hook after the caller has parked
+// its tile's registers in shared memory (RegTile::park), so that the hot path keeps its register allocation; out of place only
+// (in place the owner's stores could race with the re-read; those launches keep the give-up watchdog).  With it the
+// one-wave ticket-free scans need neither in-order dispatch nor anything of the kernels they share the device with.
+template <typename T>
+__device__ __noinline__ void rescue_tile_warp(const ScanParams& p, uint32_t tile_keys, uint32_t b, uint32_t lane)
+{
+    const uint4* in4 = reinterpret_cast<const uint4*>(p.in) + (uint64_t)b * (tile_keys / 4u);
+    T acc = T(0);
+#pragma unroll 1
+    for (uint32_t i = lane; i < tile_keys / 4u; i += 32u) {
+        const uint4 r = ldg_stream(in4 + i);
+        acc += (from_bits<T>(r.x) + from_bits<T>(r.y)) + (from_bits<T>(r.z) + from_bits<T>(r.w));
+    }
+    T red = warp_reduce(acc);
+    if (b == 0u) red += acquire_carry<T>(p, lane);  // tile 0 is INCLUSIVE incl. the carry
+    if (lane == 0u) {
+        const uint64_t mine = pack_desc(to_bits(red), p.epoch, b ? ST_AGGREGATE : ST_INCLUSIVE);
+        uint64_t seen = ld_relaxed_gpu(p.desc + b);
+        while (!desc_valid(seen, p.epoch)) {  // CAS from the stale word we observe to ours; the owner may get there first
+            const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(p.desc + b), (unsigned long long)seen,
+                                           (unsigned long long)mine);
+            if (old == seen) {
+                atomicOr(p.status, STATUS_RESCUED);
+                break;
+            }
+            seen = old;
+        }
+    }
+    __syncwarp();
+}
+
 struct LookbackStats {
     uint32_t windows = 0;  // descriptor windows consumed
     uint32_t polls = 0;    // polls that found the nearest tile not ready
@@ -566,9 +606,15 @@ struct LookbackStats {
 // are issued back to back, so one L2 round trip covers 32*WIN predecessors.
 // MAXWIN = how many windows per round trip a far-behind walk may grow to (see below); the kernels
 // whose tile lives in registers keep MAXWIN = WIN (no spare registers for the extra descriptors)
-template <typename T, int WIN = 2, int MAXWIN_ = 0>
+// OnStuck: hook called (warp-uniformly, with the nearest unpublished tile) every kRescuePolls unsuccessful polls; the
+// ticket-free register-tile kernels rescue that tile there (rescue_tile_warp), everybody else passes nothing
+struct NoRescue {
+    static constexpr bool enabled = false;
+    __device__ __forceinline__ void operator()(uint32_t) const {}
+};
+template <typename T, int WIN = 2, int MAXWIN_ = 0, typename OnStuck = NoRescue>
 __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, uint32_t lane,
-                                           LookbackStats* stats = nullptr)
+                                           LookbackStats* stats = nullptr, OnStuck on_stuck = OnStuck())
 {
     T prefix = T(0);
     int64_t top = (int64_t)tile - 1;
@@ -660,6 +706,8 @@ __device__ __forceinline__ T lookback_warp(const ScanParams& p, uint32_t tile, u
         if (consumed == 0u) {
             const bool bail = watchdog_tick(polls, p.status);
             if (__any_sync(kFullMask, bail)) break;  // warp-uniform exit
+            // (polls is warp-uniform: every lane ticks once per round)
+            if (OnStuck::enabled && (polls & (kRescuePolls - 1u)) == 0u) on_stuck((uint32_t)top);
             if (p.poll_sleep_ns) __nanosleep(p.poll_sleep_ns);
             continue;
         }

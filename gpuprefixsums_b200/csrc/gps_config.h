@@ -180,6 +180,8 @@
 // Small sizes come first (gps_api.cu, dispatch_scan_tk): a grid of at most ONE wave of the small register-tile
 // kernels runs the PLAIN kernel with tile = blockIdx.x -- equally deadlock-free, and cheaper than the fallback
 // kernel (2^20: 5.14 us, 2^21: 6.41); the register-tile range below then only applies on devices too small for that.
+// "ticket_free" = 1 (default) launches the one-wave kernels WITH the warp-level rescue (gps_common.cuh rescue_tile_warp:
+// unconditional forward progress out of place, +0.07..0.25 us), = 2 the lean ones.
 // A third register tile, <128,8> (56 registers: 9 CTAs per SM, one wave = 1332 tiles = 5.4 M keys on 148 SMs), takes the
 // sizes between one wave of <256,4> (888 tiles = 3.6 M keys) and its own wave, blockIdx order: 3.8 M keys 8.30 -> 8.07 us,
 // 2^22 9.01 -> 8.44, 4.5 M 9.58 -> 8.59, 5 M 9.45 -> 9.02 (tools/gpu_r2_ab.sh; profiles/r02_ticket_free.txt G)

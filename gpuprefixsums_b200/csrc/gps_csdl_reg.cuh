@@ -10,12 +10,33 @@
 
 namespace gps {
 
+// look-back hook of the ticket-free register-tile kernels: park the tile, rescue the late predecessor, fetch the tile back
+template <typename T, typename Tile>
+struct RegRescue {
+    static constexpr bool enabled = true;
+    const ScanParams& p;
+    Tile& t;
+    T* park;
+    uint32_t lane;
+    bool active;  // ticket-free launch, out of place
+    __device__ __forceinline__ void operator()(uint32_t b) const
+    {
+        if (!active) return;
+        t.park(park, lane);
+        __syncwarp();
+        rescue_tile_warp<T>(p, Tile::TILE_KEYS, b, lane);
+        t.unpark(park, lane);
+    }
+};
+
 // ---------------------------------------------------------------------------------
 // CSDL, register path
 // ---------------------------------------------------------------------------------
 // WIN: look-back windows per round trip; PROF: compile the phase timers in (tuning only)
 // REGS: register budget per thread (decides the CTAs per SM the kernel is compiled for)
-template <typename T, int NT, int V, bool INCLUSIVE, int WIN = 2, bool PROF = false, int REGS = 24 + 4 * V>
+// RESCUE: compile the warp-level Decoupled Fallback into the look-back's cold path (ticket-free one-wave launches that must
+// not depend on anything; costs ~0.1 us per launch in code size, so the other instantiations leave it out)
+template <typename T, int NT, int V, bool INCLUSIVE, int WIN = 2, bool PROF = false, int REGS = 24 + 4 * V, bool RESCUE = false>
 __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) csdl_reg_kernel(const __grid_constant__ ScanParams p)
 {
     using Tile = RegTile<T, NT, V>;
@@ -23,6 +44,7 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) csdl_reg_kernel
     __shared__ T s_warp[NW];
     __shared__ T s_prefix;
     __shared__ uint32_t s_tile;
+    __shared__ T s_park[RESCUE ? 32 * Tile::PARK_WORDS : 1];  // warp 0's tile while it rescues a late predecessor (cold path)
     pdl_entry();
 
     const uint32_t lane = lane_id();
@@ -43,6 +65,10 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) csdl_reg_kernel
     if (tile >= p.num_tiles) {  // ticket accounting out of step (an earlier launch failed): never index past the descriptors
         if (threadIdx.x == 0) atomicOr(p.status, STATUS_WATCHDOG);
         return;
+    }
+    if (p.debug_delay_tile && tile + 1u == p.debug_delay_tile) {  // test hook: a CTA that starts ~40 ms late
+#pragma unroll 1
+        for (int i = 0; i < 400; ++i) __nanosleep(100000u);
     }
     const bool full = ((uint64_t)tile + 1u) * Tile::TILE_KEYS <= p.n;
     const uint64_t vbase = Tile::vec_base(tile, warp, lane);
@@ -77,6 +103,11 @@ __global__ void __launch_bounds__(NT, min_ctas_per_sm(NT, REGS)) csdl_reg_kernel
         T prefix;
         if (tile == 0)
             prefix = acquire_carry<T>(p, lane);
+        else if constexpr (RESCUE)
+            // ticket-free launches (one-wave grids) rescue a late predecessor instead of waiting for it
+            prefix = lookback_warp<T, WIN, 0, RegRescue<T, Tile>>(
+                p, tile, lane, PROF ? &lbs : nullptr,
+                RegRescue<T, Tile>{p, t, s_park, lane, (p.flags & PF_STATIC_TILE) && p.in != p.out});
         else
             prefix = (p.flags & PF_SKIP_LOOKBACK) ? T(0) : lookback_warp<T, WIN>(p, tile, lane, PROF ? &lbs : nullptr);
         if (profiler) tprof[4] = clock64();

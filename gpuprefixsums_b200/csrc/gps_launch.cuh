@@ -49,6 +49,7 @@ struct Scratch {
     void* partials = nullptr;     // one key-sized value per RTS tile
     uint32_t partials_capacity = 0;
     uint32_t counter_base = 0;
+    uint32_t debug_delay_tile = 0;  // test hook (gps_set_option "debug_delay_tile"): tile + 1 whose CTA starts late
     uint32_t epoch = 0;
     int sm_count = 148;
     uint32_t poll_sleep_ns = 0;
@@ -104,6 +105,7 @@ inline ScanParams make_scan_params(Scratch& s, const void* in, void* out, uint64
     p.poll_sleep_ns = s.poll_sleep_ns;
     p.flags = s.flags;
     p.prof = s.prof;
+    p.debug_delay_tile = s.debug_delay_tile;
     return p;
 }
 
@@ -124,14 +126,14 @@ cudaError_t launch_carry_only(Scratch& s, const CarrySpec& cs, cudaStream_t st)
 }
 
 // ---- CSDL register path --------------------------------------------------------------
-template <typename T, int NT, int V, bool INCL, int WIN = 2, bool PROF = false, int REGS = 24 + 4 * V>
+template <typename T, int NT, int V, bool INCL, int WIN = 2, bool PROF = false, int REGS = 24 + 4 * V, bool RESCUE = false>
 cudaError_t launch_csdl_reg(Scratch& s, const void* in, void* out, uint64_t n, const CarrySpec& cs,
                             cudaStream_t st)
 {
     using Tile = RegTile<T, NT, V>;
     ScanParams p = make_scan_params(s, in, out, n, Tile::TILE_KEYS, cs, st);
     const cudaError_t e =
-        launch_scan_kernel(csdl_reg_kernel<T, NT, V, INCL, WIN, PROF, REGS>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
+        launch_scan_kernel(csdl_reg_kernel<T, NT, V, INCL, WIN, PROF, REGS, RESCUE>, p.num_tiles, NT, 0, st, s.flags & PF_PDL, p);
     // one claim per CTA -- of a launch that actually happened
     if (e == cudaSuccess && !(s.flags & PF_STATIC_TILE)) s.counter_base += p.num_tiles;
     return e;

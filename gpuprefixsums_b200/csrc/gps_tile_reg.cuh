@@ -93,6 +93,30 @@ struct RegTile {
         }
     }
 
+    // Cold path only: park the registers of this tile in (shared) memory and fetch them back, lane-major (conflict free).
+    // Between the two calls nothing of the tile is live, so a function CALL there costs the hot path no spill.
+    static constexpr uint32_t PARK_WORDS = 5u * V + 1u;  // per lane
+    __device__ __forceinline__ void park(T* s, uint32_t lane) const
+    {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s[(4 * k + c) * 32 + lane] = x[k][c];
+            s[(4 * V + k) * 32 + lane] = lane_excl[k];
+        }
+        s[5 * V * 32 + lane] = warp_total;
+    }
+    __device__ __forceinline__ void unpark(const T* s, uint32_t lane)
+    {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) x[k][c] = s[(4 * k + c) * 32 + lane];
+            lane_excl[k] = s[(4 * V + k) * 32 + lane];
+        }
+        warp_total = s[5 * V * 32 + lane];
+    }
+
     // warp-level scan of the V rows; leaves lane_excl[] and warp_total
     __device__ __forceinline__ void scan_warp(uint32_t lane)
     {

@@ -88,6 +88,13 @@ class PrefixSum:
     def set_option(self, key: str, value: int) -> None:
         check(lib.gps_set_option(self._ctx, key.encode(), int(value)))
 
+    def get_option(self, key: str) -> int:
+        """Read an option back ("ticket_free", "pdl", "tile_order"; "rescued": 1 if a check() since the last query saw a
+        rescued tile -- reading clears it)."""
+        v = C.c_int64(0)
+        check(lib.gps_get_option(self._ctx, key.encode(), C.byref(v)))
+        return int(v.value)
+
     def check(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Synchronise and raise if a look-back watchdog tripped since the last check."""
         check(lib.gps_check(self._ctx, _stream_ptr(stream, self.device)))

@@ -106,21 +106,25 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   are emulated, else the register tile), 1 = register tile, 2 = smem-resident
  *                   tile, 3 = blocked smem-resident tile
  *   "ticket_free"   1 (default) = GPS_ALGO_CSDL takes tile = blockIdx.x instead of an atomic ticket
- *                   where that does not rest on in-order CTA dispatch alone: (a) grids of at most
- *                   one wave of a register-tile kernel (<256,4> up to ~3.6 M keys on 148 SMs,
- *                   <128,8> from there to ~5.4 M):
- *                   every CTA becomes resident without another CTA of the grid finishing first, so
- *                   it cannot deadlock under any dispatch order as long as the OTHER kernels on the
- *                   device terminate independently of this scan (and under in-order dispatch, what
- *                   cub::DeviceScan relies on, not even that is needed -- e.g. for two such scans
- *                   in flight on different streams at once, each waiting for slots the other
- *                   holds); (b) the Decoupled Fallback
- *                   kernel -- no CTA of it waits for another, unconditionally deadlock-free -- for
- *                   the sizes up to 2^24 keys that (a) does not cover.
- *                   9..18 % faster there.  0 = atomic tickets everywhere (needs neither assumption)
+ *                   where that does not rest on in-order CTA dispatch: (a) grids of at most one wave
+ *                   of a register-tile kernel (<256,4> up to ~3.6 M keys on 148 SMs, <128,8> from
+ *                   there to ~5.4 M) -- every CTA becomes resident without another CTA of the grid
+ *                   finishing first, and a walk whose nearest predecessor stays unpublished for
+ *                   ~10 ms re-reduces that tile itself and inserts it with CAS (warp-level Decoupled
+ *                   Fallback on the cold path; gps_get_option "rescued"), so nothing is assumed of
+ *                   the dispatch order or of the kernels sharing the device (in place the rescue is
+ *                   off: those launches need other kernels on the device to terminate independently
+ *                   of the scan, or in-order dispatch -- what cub::DeviceScan relies on); (b) the
+ *                   Decoupled Fallback kernel -- no CTA of it waits for another -- for the sizes up
+ *                   to 2^24 keys that (a) does not cover.  6..24 % faster there.
+ *                   2 = the same dispatch with the lean one-wave kernels (no rescue code: another
+ *                   0.07..0.25 us per launch, (a) then rests on the assumption stated for in place).
+ *                   0 = atomic tickets everywhere
  *   "rts_variant"   Reduce-then-Scan propagate kernel: 0 = auto (blocked tile from 2^27 keys),
  *                   1 = register tile, 2 = blocked smem-resident tile
  *   "tile_order"    0 = atomic ticket (default), 1 = blockIdx.x order (as cub::DeviceScan)
+ *   "debug_delay_tile" test hook: the CTA of tile (value - 1) of the register-tile kernels starts
+ *                   ~40 ms late (0 = off) -- what out-of-order dispatch would look like
  *   "desc_protocol" 0 = atom.exch + ld.relaxed (default), 1 = st.release + ld.acquire,
  *                   2 = st.relaxed + ld.relaxed
  *   "lookback"      0 = warp-parallel (default, LookbackWarp), 1 = single thread
@@ -140,6 +144,10 @@ int gps_check(gps_ctx* ctx, void* stream);
  *                   GPS_ERR_WATCHDOG
  *   "host_chunk_keys" chunk size of gps_scan_host (default 2^24; before first use) */
 int gps_set_option(gps_ctx* ctx, const char* key, int64_t value);
+/* Reads an option back: "ticket_free", "pdl", "tile_order", and "rescued" -- 1 if a gps_check since
+ * the last query saw that a ticket-free one-wave scan rescued a predecessor tile whose CTA was late
+ * (warp-level Decoupled Fallback; the results are valid, the flag is informational and reading clears it). */
+int gps_get_option(gps_ctx* ctx, const char* key, int64_t* value);
 /* Scratch a context of capacity max_n needs on the device, in bytes (descriptors + RTS
  * partials + counters) -- the "temp storage size" of the Unity port's caller-owned-buffer
  * API (GPUPrefixSumsUnity/Runtime/ReduceThenScan.cs:156-279,

@@ -655,7 +655,7 @@ def test_ticket_free_decoupled_fallback_default(gps, oracle):
     for n in sizes:
         x = oracle.random_u32(n, seed=n % 1000)
         d = to_dev_u32(x)
-        for tf in (1, 0):
+        for tf in (1, 2, 0):  # 1: ticket-free with the warp-level rescue (default), 2: lean ticket-free kernels, 0: tickets
             ps.set_option("ticket_free", tf)
             for exclusive in (False, True):
                 want, total = oracle.scan_u32(x, exclusive=exclusive, carry=11)
@@ -737,3 +737,48 @@ def test_ticket_free_scans_concurrently_on_two_streams(gps, oracle):
         assert np.array_equal(to_np_u32(o), wants[n]), n
     a.close()
     b.close()
+
+
+def test_late_cta_is_rescued_by_the_one_wave_kernels(gps, oracle):
+    """What out-of-order dispatch would look like: the CTA of one tile starts ~40 ms late ("debug_delay_tile").  The
+    ticket-free one-wave kernels (tile = blockIdx.x) do not wait for it: after ~10 ms of polling, a successor's look-back warp
+    re-reduces that tile from the input and inserts its aggregate with CAS (warp-level Decoupled Fallback) -- results bit-exact,
+    "rescued" reported.  With tickets ("ticket_free" = 0) and in place the scan simply waits: exact too, nothing rescued."""
+    ps = gps.PrefixSum(1 << 23)
+    for n, late in [((1 << 15) + 3, 3), ((1 << 20) + 4099, 17), (4_200_000, 1), (1 << 21, 300), ((1 << 20), 0)]:
+        x = oracle.random_u32(n, seed=n % 977)
+        d = to_dev_u32(x)
+        for exclusive in (False, True):
+            want, total = oracle.scan_u32(x, exclusive=exclusive, carry=5)
+            ps.set_option("ticket_free", 1)
+            ps.set_option("debug_delay_tile", late + 1)
+            ps.get_option("rescued")  # clear
+            tot = torch.zeros(1, dtype=torch.int32, device="cuda")
+            out = ps.scan(d, exclusive=exclusive, carry=5, total_out=tot)
+            ps.check()
+            assert np.array_equal(to_np_u32(out), want), (n, late, exclusive)
+            assert int(tot.cpu().numpy().view(np.uint32)[0]) == total
+            assert ps.get_option("rescued") == 1, (n, late)
+            assert ps.get_option("rescued") == 0  # reading clears it
+            # in place: no rescue (the owner's stores could race with a re-read), the scan waits for the late CTA
+            buf = d.clone()
+            ps.scan(buf, buf, exclusive=exclusive, carry=5)
+            ps.check()
+            assert np.array_equal(to_np_u32(buf), want), (n, late, exclusive, "in place")
+            assert ps.get_option("rescued") == 0
+            # tickets: the late CTA holds a later ticket than... no: it holds ITS ticket and everybody behind it waits
+            ps.set_option("ticket_free", 0)
+            out = ps.scan(d, exclusive=exclusive, carry=5)
+            ps.check()
+            assert np.array_equal(to_np_u32(out), want), (n, late, exclusive, "tickets")
+            assert ps.get_option("rescued") == 0
+    # float32: the rescuer's sum and the owner's differ in rounding at most
+    ps.set_option("ticket_free", 1)
+    ps.set_option("debug_delay_tile", 9)
+    xf = oracle.random_f32((1 << 20) + 77, seed=8)
+    outf = ps.scan(torch.from_numpy(xf).cuda()).cpu().numpy()
+    ps.check()
+    assert oracle.check_f32(xf, outf, rtol=2e-5, atol=1e-6)[0] == 0
+    assert ps.get_option("rescued") == 1
+    ps.set_option("debug_delay_tile", 0)
+    ps.close()

@@ -43,7 +43,14 @@ for tf in (1, 0):
     for kind in (capi.INCLUSIVE, capi.EXCLUSIVE):
         for n in (N, 1 << 20, 2049):
             check(lib.gps_scan(ctx, capi.ALGO_CSDL, kind, capi.U32, a, b, n, 3, None, None))
+# the warp-level rescue of the one-wave kernels: one tile's CTA starts late, a successor re-reduces it (tiny / small / mid tile)
 check(lib.gps_set_option(ctx, b"ticket_free", 1))
+for n, late in ((40_000, 3), (N, 9), (1 << 20, 200)):
+    check(lib.gps_set_option(ctx, b"debug_delay_tile", late + 1))
+    check(lib.gps_scan(ctx, capi.ALGO_CSDL, capi.INCLUSIVE, capi.U32, a, b, n, 3, None, None))
+    check(lib.gps_scan(ctx, capi.ALGO_CSDL, capi.EXCLUSIVE, capi.F32, a, b, n, 0, None, None))
+check(lib.gps_set_option(ctx, b"debug_delay_tile", 0))
+check(lib.gps_check(ctx, None))
 check(lib.gps_set_option(ctx, b"tile_order", 1))
 for variant in (1, 2):
     check(lib.gps_set_option(ctx, b"fallback_variant", variant))

@@ -28,7 +28,7 @@ for n in sorted(sizes):
     gps.cub_scan(x, ref)
     if IN_PLACE:
         out = x
-    for tf in (0, 1, 0, 1):
+    for tf in ((0, 1, 2, 0, 1, 2) if "three" in sys.argv else (0, 1, 0, 1)):
         ps.set_option("ticket_free", tf)
         ps.scan(x, out)
         ps.check()
