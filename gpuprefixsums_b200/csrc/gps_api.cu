@@ -1642,6 +1642,11 @@ int sharded_status(gps_shard_group* g)
             rc = fail(GPS_ERR_CUDA, "device %d: status read failed: %s", g->devices[i], cudaGetErrorString(cudaGetLastError()));
             continue;
         }
+        if (st[1] & STATUS_RESCUED) {  // informational (a late tile was rescued; results are valid), as in gps_check
+            c->rescued = 1;
+            st[1] &= ~STATUS_RESCUED;
+            if (!st[1]) cudaMemset(c->s.status, 0, sizeof(uint32_t));
+        }
         if (st[1]) {
             cudaMemset(c->s.status, 0, sizeof(uint32_t));
             c->s.counter_base = st[0];

@@ -206,6 +206,27 @@ def test_sharded_scan_host_single_process(oracle, G):
         sh.close()
 
 
+def test_sharded_scan_host_with_a_late_cta(oracle):
+    """A rescued tile (the warp-level Decoupled Fallback of the ticket-free one-wave kernels, here provoked with the
+    "debug_delay_tile" hook in every chunk's scan) is informational for the multi-GPU host entry too: the call succeeds,
+    the result is exact."""
+    import gpuprefixsums_b200 as gps
+
+    ndev = torch.cuda.device_count()
+    sh = gps.ShardedHostScan([0, 1 % ndev], chunk_keys=1 << 16)
+    try:
+        sh.set_option("debug_delay_tile", 4)
+        n = (1 << 18) + 4099  # 5 chunks of 32 tiles each
+        x = oracle.random_u32(n, seed=17)
+        h_in = torch.from_numpy(x.view(np.int32)).pin_memory()
+        h_out = torch.full((n,), -1, dtype=torch.int32).pin_memory()
+        sh.scan_host(h_in, h_out)  # waits; raises if the group reports an error
+        assert np.array_equal(h_out.numpy().view(np.uint32), oracle.scan_u32(x)[0])
+        sh.set_option("debug_delay_tile", 0)
+    finally:
+        sh.close()
+
+
 def test_sharded_scan_host_io_routing(oracle):
     """The chunks may be routed through a subset of the group's GPUs, in any chain order (what the
     host-I/O calibration decides on boxes with unequal host paths); results do not change."""
