@@ -517,7 +517,10 @@ __device__ __forceinline__ T acquire_carry(const ScanParams& p, uint32_t lane)
             bool ok = true;
             while ((uint32_t)(s >> 32) != p.slot_tag) {
                 if (++polls >= budget) {
-                    atomicOr(p.status, STATUS_WATCHDOG | STATUS_SLOT_TIMEOUT);
+                    // its own bit only: the look-back pollers bail out early on STATUS_WATCHDOG (watchdog_tick), but a
+                    // slot that timed out is about to be published with a DEFINED value (it contributes nothing) --
+                    // they must keep waiting for it, or the reported-but-defined result would depend on timing
+                    atomicOr(p.status, STATUS_SLOT_TIMEOUT);
                     ok = false;
                     break;
                 }
